@@ -1,0 +1,139 @@
+"""ORACLE (test infrastructure): plain-torch CPU restatement of the reference's 3-D conv blocks.
+
+Each builder cites the reference lines it follows.  The arithmetic itself
+(Conv3d / ConvTranspose3d / BatchNorm3d / GroupNorm) is the third-party dependency
+torch (reference pin: pytorch-1.9.0, spec-file.txt:253; 2.11.0 here).  state_dict
+key names and shapes equal the reference's, which is how
+tests/test_oracle_blocks.py pins these classes: the reference modules' weights are
+loaded with strict=True and outputs compared on the golden fixtures
+(tests/golden/make_golden.py, generated from /root/reference in the build container).
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def _norm3d(ch, gn, groups=32):
+    return nn.GroupNorm(groups, ch) if gn else nn.BatchNorm3d(ch)
+
+
+def convbn_3d(cin, cout, kernel_size, stride, pad, dilation=1, gn=False, groups=32):
+    """submodule.py:32-50."""
+    return nn.Sequential(
+        nn.Conv3d(cin, cout, kernel_size=kernel_size, padding=pad, dilation=dilation, stride=stride, bias=False),
+        _norm3d(cout, gn, groups))
+
+
+def _deconvbn_3d(cin, cout, gn):
+    """submodule.py:127-147,197-208: ConvTranspose3d(k3,s2,p1,op1,bias=False) + norm."""
+    return nn.Sequential(
+        nn.ConvTranspose3d(cin, cout, kernel_size=3, padding=1, output_padding=1, stride=2, bias=False),
+        _norm3d(cout, gn))
+
+
+def _cbr(cin, cout, k, s, p, d=1, gn=False):
+    return nn.Sequential(convbn_3d(cin, cout, k, s, p, d, gn=gn), nn.ReLU(inplace=True))
+
+
+class Hourglass(nn.Module):
+    """submodule.py:85-168 (class ``hourglass``)."""
+
+    def __init__(self, inplanes, gn=False):
+        super().__init__()
+        c2 = inplanes * 2
+        self.conv1 = _cbr(inplanes, c2, 3, 2, 1, gn=gn)           # :89-97
+        self.conv2 = convbn_3d(c2, c2, 3, 1, 1, gn=gn)            # :99-105
+        self.conv3 = _cbr(c2, c2, 3, 2, 1, gn=gn)                 # :107-115
+        self.conv4 = _cbr(c2, c2, 3, 1, 1, gn=gn)                 # :117-125
+        self.conv5 = _deconvbn_3d(c2, c2, gn)                     # :127-136
+        self.conv6 = _deconvbn_3d(c2, inplanes, gn)               # :138-147
+
+    def forward(self, x, presqu, postsqu):                        # :149-168
+        out = self.conv1(x)
+        pre = self.conv2(out)
+        pre = F.relu(pre + postsqu) if postsqu is not None else F.relu(pre)
+        out = self.conv4(self.conv3(pre))
+        post = F.relu(self.conv5(out) + (presqu if presqu is not None else pre))
+        return self.conv6(post), pre, post
+
+
+class HourglassDownsample16(nn.Module):
+    """submodule.py:223-268 (class ``hourglass_downsample_16``; helpers :170-208)."""
+
+    def __init__(self, inplanes, gn=False):
+        super().__init__()
+        c2 = inplanes * 2
+        self.conv1 = _cbr(inplanes, c2, 3, 2, 1, gn=gn)
+        self.conv2 = _cbr(c2, c2, 3, 1, 1, gn=gn)
+        for i in (3, 5, 7):
+            setattr(self, f"conv{i}", _cbr(c2, c2, 3, 2, 1, gn=gn))
+            setattr(self, f"conv{i + 1}", _cbr(c2, c2, 3, 1, 1, gn=gn))
+        for i in (9, 10, 11):
+            setattr(self, f"conv{i}", _deconvbn_3d(c2, c2, gn))
+        self.conv12 = _deconvbn_3d(c2, inplanes, gn)
+
+    def forward(self, x):                                         # :245-268
+        o2 = self.conv2(self.conv1(x))
+        o4 = self.conv4(self.conv3(o2))
+        o6 = self.conv6(self.conv5(o4))
+        o8 = self.conv8(self.conv7(o6))
+        o10 = self.conv10(self.conv9(o8) + o6)
+        o11 = self.conv11(o10 + o4)
+        return self.conv12(o11 + o2)
+
+
+class GlobalTrunk(nn.Module):
+    """Restated global-branch 3-D trunk (DSGN lineage, README.md:68).
+
+    dres0 = 2 x (convbn_3d 3^3 + ReLU)  64->32->32
+    dres1 = convbn_3d+ReLU, convbn_3d ; out = dres1(x) + x
+    hg    = hourglass(32)(x, None, None)[0] + x
+    Blocks are the reference's (submodule.py:32-50,85-168); the wiring is restated
+    because the reference does not ship the global model class (models/__init__.py:1-2).
+    """
+
+    def __init__(self, cin=64, ch=32, gn=False):
+        super().__init__()
+        self.dres0 = nn.Sequential(_cbr(cin, ch, 3, 1, 1, gn=gn), _cbr(ch, ch, 3, 1, 1, gn=gn))
+        self.dres1 = nn.Sequential(_cbr(ch, ch, 3, 1, 1, gn=gn), convbn_3d(ch, ch, 3, 1, 1, gn=gn))
+        self.hg = Hourglass(ch, gn=gn)
+
+    def forward(self, cost):
+        x = self.dres0(cost)
+        x = self.dres1(x) + x
+        return self.hg(x, None, None)[0] + x
+
+
+class Vernier3D(nn.Module):
+    """The 3-D part of VernierScale (vernier_type='BEV_type3'): layers vernier.py:250-289,
+    forward vernier.py:414-438.  Attribute names equal the reference's so a VernierScale
+    state_dict (filtered to these prefixes) loads with strict=True."""
+
+    def __init__(self, dim=32, n_sample_w=128, gn=False, pool=4):
+        super().__init__()
+        self.n_sample_w = n_sample_w
+        self.vimg_feat = _cbr(2 * dim, dim, 1, 1, 0, gn=gn)                 # :250-252
+        self.conv1 = _cbr(2 * dim, dim, 7, 1, 3, gn=gn)                     # :253-255
+        self.conv2 = _cbr(dim, dim, 5, 1, 2, gn=gn)                         # :256-258
+        self.conv3 = _cbr(dim, dim, 5, 1, 4, d=2, gn=gn)                    # :259-261
+        self.conv4 = _cbr(2 * dim, dim, 3, 1, 1, gn=gn)                     # :262-264
+        self.hg_conv3d = Hourglass(dim, gn) if n_sample_w <= 16 else HourglassDownsample16(dim, gn)  # :265-268
+        self.fg_cls_head = nn.Sequential(convbn_3d(dim, dim, 3, 1, 1, gn=gn), nn.ReLU(inplace=True),
+                                         nn.Conv3d(dim, 1, 3, 1, 1, bias=False), nn.Sigmoid())      # :269-278
+        self.pool_3d = nn.AvgPool3d((pool, 1, 1), stride=(pool, 1, 1))      # :289
+
+    def forward(self, voxel):
+        """-> (voxel_BEV [N, dim*nh/4, nw, nl], occupancy [N, nh, nw, nl])  (vernier.py:414-438)."""
+        vimg = self.vimg_feat(voxel)
+        voxel = self.conv1(voxel)
+        voxel = self.conv2(voxel) + voxel
+        voxel = self.conv3(voxel) + voxel
+        if self.n_sample_w <= 16:
+            voxel = self.hg_conv3d(voxel, None, None)[0] + voxel
+        else:
+            voxel = self.hg_conv3d(voxel) + voxel
+        occupancy = self.fg_cls_head(voxel)
+        voxel = torch.cat([voxel, vimg * occupancy], dim=1)
+        voxel = self.pool_3d(self.conv4(voxel))
+        N, Fc, H, W, L = voxel.shape
+        return voxel.reshape(N, -1, W, L), occupancy.squeeze(1)

@@ -1,0 +1,116 @@
+"""Generate tests/golden/*.npz by RUNNING THE REFERENCE'S OWN MODULES (CPU, this container).
+
+    PYTHONPATH=/root/reference python tests/golden/make_golden.py
+
+Needs /root/reference (absent on the GPU box) -> the outputs are committed.  Inputs and weights
+are not stored: they are regenerated bit-identically from tests/golden/synth.py.
+Reference entry points exercised:
+  snvc.models.submodule.hourglass                 (submodule.py:85-168)   bn and gn
+  snvc.models.submodule.hourglass_downsample_16   (submodule.py:223-268)
+  snvc.models.vernier.VernierScale.construct_voxel        (vernier.py:323-360)
+  snvc.models.vernier.VernierScale.predict_3d_heatmaps    (vernier.py:414-458), BEV_type3
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, "/root/reference")
+import synth  # noqa: E402
+
+# matplotlib is imported at module import time by vernier.py:11 / visualization/points.py:8
+for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.cm", "mpl_toolkits", "mpl_toolkits.mplot3d"):
+    sys.modules.setdefault(name, types.ModuleType(name))
+sys.modules["mpl_toolkits.mplot3d"].Axes3D = object
+
+from snvc.models import submodule as ref_sub  # noqa: E402
+from snvc.models import vernier as ref_vernier  # noqa: E402
+
+torch.set_grad_enabled(False)
+
+
+def case_hourglass(gn):
+    m = ref_sub.hourglass(32, gn=gn).eval()
+    m.load_state_dict(synth.det_state_dict(m, 11 + int(gn)), strict=True)
+    x = torch.from_numpy(synth.det_uniform((1, 32, 8, 16, 16), 101))
+    out, pre, post = m(x, None, None)
+    # second call exercises the presqu / postsqu arguments (submodule.py:152-164)
+    out2, pre2, post2 = m(x, pre.clone(), post.clone())
+    return dict(out=out.numpy(), pre=pre.numpy(), post=post.numpy(),
+                out2=out2.numpy(), pre2=pre2.numpy(), post2=post2.numpy())
+
+
+def case_hg16():
+    m = ref_sub.hourglass_downsample_16(32, gn=False).eval()
+    m.load_state_dict(synth.det_state_dict(m, 21), strict=True)
+    x = torch.from_numpy(synth.det_uniform((1, 32, 16, 16, 16), 102))
+    return dict(out=m(x).numpy())
+
+
+def vernier_cfg(grid=(16, 32, 48), gn=False):
+    ns = types.SimpleNamespace
+    st = lambda nm, nb, blk, nbl, nch: ns(num_modules=nm, num_branches=nb, block=blk, num_blocks=nbl,
+                                          num_channels=nch, fuse_method="SUM")
+    hr = ns(name="hrnet-w32", head_type="default", init_weights=False, pre_trained_path="",
+            extra=ns(stage1=st(1, 1, "bottleneck", [4], [64]), stage2=st(1, 2, "basic", [4, 4], [32, 64]),
+                     stage3=st(4, 3, "basic", [4, 4, 4], [32, 64, 128]),
+                     stage4=st(3, 4, "basic", [4, 4, 4, 4], [32, 64, 128, 256])))
+    return ns(vernier_type="BEV_type3", gn=gn, backbone="hrnet", hrnet=hr, hrfeat=ns(output_channel=32),
+              num_parts=9, grid_resolution=list(grid), n_sample_h=grid[0], n_sample_w=grid[1],
+              n_sample_l=grid[2], x_range=[-3.2, 3.2], y_range=[-1.6, 1.6], z_range=[-4.8, 4.8],
+              resolution=[64, 64])
+
+
+VERNIER_3D_PREFIXES = ("vimg_feat.", "conv1.", "conv2.", "conv3.", "conv4.", "hg_conv3d.", "fg_cls_head.")
+
+
+def synth_roi_points(N, P, res, seed):
+    """Pixel coordinates in [-0.1*res, 1.1*res): mostly inside the ROI, some outside (zeros padding)."""
+    return synth.det_uniform((N, 2, P), seed, -0.1 * res, 1.1 * res, bf16=False)
+
+
+def case_vernier():
+    cfg = vernier_cfg()
+    torch.manual_seed(0)
+    m = ref_vernier.VernierScale(cfg).eval()
+    nh, nw, nl = cfg.grid_resolution
+    sd = m.state_dict()
+    sub = torch.nn.Module()
+    for p in ("vimg_feat", "conv1", "conv2", "conv3", "conv4", "hg_conv3d", "fg_cls_head"):
+        setattr(sub, p, getattr(m, p))
+    new = synth.det_state_dict(sub, 31)
+    sd.update(new)
+    m.load_state_dict(sd, strict=True)
+    N, P = 1, nh * nw * nl
+    lf = torch.from_numpy(synth.det_uniform((N, 32, 16, 16), 201))
+    rf = torch.from_numpy(synth.det_uniform((N, 32, 16, 16), 202))
+    gl = torch.from_numpy(synth_roi_points(N, P, 64, 203))
+    gr = torch.from_numpy(synth_roi_points(N, P, 64, 204))
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        vox = m.construct_voxel(lf, rf, gl.clone(), gr.clone())          # [1,64,16,32,48]
+    cap = {}
+    h = m.pool_3d.register_forward_hook(lambda mod, i, o: cap.__setitem__("pooled", o))
+    ncf, occ, _, coords, _ = m.predict_3d_heatmaps(vox)
+    h.remove()
+    pooled = cap["pooled"]
+    bev = pooled.reshape(pooled.shape[0], -1, pooled.shape[3], pooled.shape[4])
+    v = vox.numpy()
+    return dict(voxel_sub=v[:, :, ::2, ::4, ::4].copy(),
+                voxel_chan_sum=v.astype(np.float64).sum(axis=(0, 2, 3, 4)),
+                voxel_abs_sum=np.abs(v.astype(np.float64)).sum(),
+                voxel_bev=bev.numpy(), occupancy=occ.numpy(), ncf=ncf.numpy(), coordinates=coords.numpy())
+
+
+if __name__ == "__main__":
+    cases = {"hourglass_bn": lambda: case_hourglass(False), "hourglass_gn": lambda: case_hourglass(True),
+             "hg16_bn": case_hg16, "vernier_bev3": case_vernier}
+    for name, fn in cases.items():
+        d = fn()
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **{k: np.asarray(v) for k, v in d.items()})
+        print(name, {k: (np.asarray(v).shape, float(np.abs(v).max())) for k, v in d.items()})
