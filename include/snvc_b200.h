@@ -1,0 +1,185 @@
+/*
+ * snvc_b200 -- C ABI of the B200-native (sm_100a) dense stereo-to-voxel hot path.
+ *
+ * This is the drop-in boundary for the path named in BASELINE.json:north_star.  Each entry
+ * point below replaces one native / library call of the reference (Nicholasli1995/SNVC); the
+ * reference interface it replaces is cited as file:line into the reference tree.
+ * INTEGRATION.md shows the reference-side (ctypes) binding.
+ *
+ * Conventions (all entry points)
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless its name ends in
+ *     `_host`; all buffers (outputs, workspaces) are allocated by the caller;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); work is enqueued
+ *     asynchronously, the library never synchronises and never allocates device memory;
+ *   - return value: 0 = ok, < 0 = argument error (SNVC_E_*), > 0 = a cudaError_t / CUresult;
+ *     snvc_last_error() returns a thread-local human-readable message for the last non-zero return;
+ *   - 64-bit element offsets throughout (the reference kernel's int32 indexing overflows above
+ *     2^31 outputs, BuildCostVolume_cuda.cu:69-82);
+ *   - thread-safe / re-entrant: no mutable global state (the reference is called from one Python
+ *     thread per device under nn.DataParallel, tools/inference_agnostic.py:472).
+ */
+#ifndef SNVC_B200_H_
+#define SNVC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNVC_ABI_VERSION 1
+
+/* element types */
+#define SNVC_F32 0
+#define SNVC_BF16 1
+#define SNVC_F64 2
+
+/* volume layouts: NCDHW is the reference's (torch contiguous); NDHWC (channels-last) is what
+ * the tcgen05 conv3d consumes */
+#define SNVC_NCDHW 0
+#define SNVC_NDHWC 1
+
+/* argument errors */
+#define SNVC_E_BADARG (-1)
+#define SNVC_E_UNSUPPORTED (-2)
+#define SNVC_E_NOTCUDA (-3)
+#define SNVC_E_DRIVER (-4)
+
+int snvc_version(void);
+const char* snvc_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * A1  plane-sweep cost volume, forward.
+ * Replaces build_cost_volume_forward(left, right, shift, downsample)
+ *   snvc/extension/build_cost_volume/src/BuildCostVolume.cpp:13-27,46
+ *   snvc/extension/build_cost_volume/src/BuildCostVolume_cuda.cu:208-256 (host), :63-98 (kernel)
+ * left,right : [N, C, IH, IW] contiguous, element type `dtype` (SNVC_F32 | SNVC_F64)
+ * shift      : [N, D] same element type, >= 0 (checked by the Python layer, __init__.py:12)
+ * cost       : out_layout NCDHW -> [N, 2C, D, IH/ds, IW/ds];  NDHWC -> [N, D, IH/ds, IW/ds, 2C]
+ * supported (dtype, out_dtype, out_layout): (F32,F32,NCDHW) (F64,F64,NCDHW) (F32,BF16,NDHWC)
+ * IH, IW must be multiples of `downsample` (the reference mis-indexes otherwise, .cu:78-86).
+ */
+int snvc_cost_volume_fwd(const void* left, const void* right, const void* shift, void* cost,
+                         int64_t N, int64_t C, int64_t IH, int64_t IW, int64_t D, int32_t downsample,
+                         int32_t dtype, int32_t out_dtype, int32_t out_layout, void* stream);
+
+/* A1b  cost volume, backward (deterministic, atomics-free).
+ * Replaces build_cost_volume_backward(grad, shift, downsample)
+ *   BuildCostVolume.cpp:29-43,47;  BuildCostVolume_cuda.cu:259-303 (host), :152-205 (kernel)
+ * grad : [N, 2C, D, H, W] (NCDHW);  grad_left, grad_right : [N, C, H*ds, W*ds] (fully written).
+ * dtype: SNVC_F32 | SNVC_F64.
+ */
+int snvc_cost_volume_bwd(const void* grad, const void* shift, void* grad_left, void* grad_right,
+                         int64_t N, int64_t C, int64_t H, int64_t W, int64_t D, int32_t downsample,
+                         int32_t dtype, void* stream);
+
+/* Debug: x_low per (n, d, pw) (or -1 when the right sample is outside the image), computed by the
+ * same device code as the forward kernel; used by the bit-exact index parity tests. */
+int snvc_cost_volume_xlow(const float* shift, int32_t* xlow, int64_t N, int64_t IW, int64_t D,
+                          int32_t downsample, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * A3  instance branch: high-resolution local ROI voxel sampling.
+ * Replaces VernierScale._sample_2d_feat / construct_voxel (snvc/models/vernier.py:323-360):
+ * coordinate normalisation (:335-338), 2 x torch.nn.functional.grid_sample (bilinear, zeros,
+ * align_corners=False; :339-340) and torch.cat (:346), in one pass.
+ * feat_l, feat_r : [N, C, Hf, Wf] fp32 contiguous
+ * pts_l, pts_r   : [N, 2, P] fp32 pixel coordinates (x row, y row), P = nh*nw*nl
+ * res_x, res_y   : cfg.resolution[1], cfg.resolution[0]  (divisors of x and y, :335-336)
+ * out            : NCDHW -> [N, 2C, P] (F32);  NDHWC -> [N, P, 2C] (BF16 or F32)
+ * workspace      : >= snvc_roi_voxel_sample_workspace_bytes(N, C, Hf, Wf) bytes (NHWC copies)
+ */
+int64_t snvc_roi_voxel_sample_workspace_bytes(int64_t N, int64_t C, int64_t Hf, int64_t Wf);
+int snvc_roi_voxel_sample_fwd(const float* feat_l, const float* feat_r, const float* pts_l,
+                              const float* pts_r, void* out, void* workspace, int64_t N, int64_t C,
+                              int64_t Hf, int64_t Wf, int64_t P, float res_x, float res_y,
+                              int32_t out_dtype, int32_t out_layout, void* stream);
+/* Debug: floor corner indices and in-bounds masks per point: idx [N, P, 2] int32 (x_nw, y_nw),
+ * mask [N, P] uint8 (bit0 nw, bit1 ne, bit2 sw, bit3 se). */
+int snvc_roi_voxel_sample_indices(const float* pts, int32_t* idx, uint8_t* mask, int64_t N, int64_t P,
+                                  int64_t Hf, int64_t Wf, float res_x, float res_y, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * A4  global branch: trilinear frustum-to-voxel lift (grid computed in-kernel from P).
+ * Replaces (restated composition): project_rect_to_image
+ * (snvc/utils/torch_utils.py:36-45) + normalisation by CV_{X,Y,Z}_{MIN,MAX} (key names
+ * snvc/models/loss3d.py:15-17) + 5-D torch.nn.functional.grid_sample + validity mask.
+ * vol   : NCDHW [N,C,D,H,W] (F32) or NDHWC [N,D,H,W,C] (BF16)
+ * proj  : [N, 3, 4] fp32 projection matrices
+ * zs,ys,xs : voxel-centre coordinates, fp32, lengths Z, Y, X (torch_utils.py:85-94 convention)
+ * cv_range_host : HOST pointer, 6 floats {CV_X_MIN, CV_X_MAX, CV_Y_MIN, CV_Y_MAX, CV_Z_MIN, CV_Z_MAX}
+ * out   : NCDHW [N,C,Z,Y,X] (F32) or NDHWC [N,Z,Y,X,C] (BF16 | F32)
+ * valid : optional [N,Z,Y,X] uint8 (may be NULL)
+ */
+int snvc_frustum_lift_fwd(const void* vol, const float* proj, const float* zs, const float* ys,
+                          const float* xs, const float* cv_range_host, void* out, uint8_t* valid,
+                          int64_t N, int64_t C, int64_t D, int64_t H, int64_t W, int64_t Z, int64_t Y,
+                          int64_t X, int32_t align_corners, int32_t in_dtype, int32_t in_layout,
+                          int32_t out_dtype, int32_t out_layout, void* stream);
+/* Debug: floor corner (x0,y0,z0) per voxel: idx [N,Z,Y,X,3] int32, valid [N,Z,Y,X] uint8. */
+int snvc_frustum_lift_indices(const float* proj, const float* zs, const float* ys, const float* xs,
+                              const float* cv_range_host, int32_t* idx, uint8_t* valid, int64_t N,
+                              int64_t D, int64_t H, int64_t W, int64_t Z, int64_t Y, int64_t X,
+                              int32_t align_corners, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * A2  3-D convolution stack (tcgen05 / TMEM implicit GEMM, bf16 x bf16 -> fp32).
+ * Replaces the cuDNN calls behind nn.Conv3d / nn.ConvTranspose3d + BatchNorm3d(eval) + ReLU +
+ * residual adds of convbn_3d / hourglass / hourglass_downsample_16
+ * (snvc/models/submodule.py:32-50, 85-168, 170-268) and the instance 3-D CNN
+ * (snvc/models/vernier.py:250-289, 414-438).
+ *
+ * Activations are NDHWC bf16.  Weights are pre-packed by snvc_conv3d_pack_weights into
+ * [taps][Cout_pad][Cin] bf16 (tap-major, K-contiguous).
+ */
+typedef struct snvc_conv3d_desc {
+  int32_t N;                 /* batch */
+  int32_t Cin, Cout;         /* Cin in {16,32,64}; Cout <= 64 (padded to a multiple of 16 inside) */
+  int32_t Di, Hi, Wi;        /* input spatial extent */
+  int32_t Do, Ho, Wo;        /* output spatial extent */
+  int32_t kernel;            /* cubic kernel size k (1,3,5,7) */
+  int32_t stride;            /* 1 or 2 */
+  int32_t pad;
+  int32_t dilation;
+  int32_t transposed;        /* 1: ConvTranspose3d(k=3, s=2, p=1, output_padding=1) */
+  int32_t relu;              /* apply ReLU */
+  int32_t residual_mode;     /* 0 none, 1 add before ReLU, 2 add after ReLU */
+  int32_t sigmoid;           /* apply sigmoid last (fg_cls_head) */
+  int32_t out_dtype;         /* SNVC_BF16 | SNVC_F32 */
+  int32_t out_cstride;       /* channel stride of y's innermost dim (>= Cout); 0 -> Cout */
+  int32_t out_coffset;       /* first channel written inside that stride */
+  int32_t res_cstride;       /* same for the residual tensor; 0 -> Cout */
+  int32_t res_coffset;
+  int32_t reserved[4];
+} snvc_conv3d_desc;
+
+/* w: Conv3d [Cout,Cin,k,k,k] fp32 (transposed=0) or ConvTranspose3d [Cin,Cout,k,k,k] fp32
+ * (transposed=1), DEVICE pointer.  w_packed: k^3 * Cout_pad * Cin bf16, Cout_pad = roundup(Cout,16). */
+int64_t snvc_conv3d_packed_weight_bytes(int32_t Cin, int32_t Cout, int32_t kernel);
+int snvc_conv3d_pack_weights(const float* w, void* w_packed, int32_t Cin, int32_t Cout, int32_t kernel,
+                             int32_t transposed, void* stream);
+/* x [N,Di,Hi,Wi,Cin] bf16; scale,bias [Cout] fp32 (folded eval-mode BatchNorm; NULL = 1 / 0);
+ * residual: NDHWC bf16 with the output's spatial shape, or NULL; y: NDHWC.
+ * y = act( scale * conv(x) + bias [+ residual] ) [+ residual] */
+int snvc_conv3d_fwd(const void* x, const void* w_packed, const float* scale, const float* bias,
+                    const void* residual, void* y, const snvc_conv3d_desc* desc, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Layout / elementwise helpers on the path.
+ */
+/* NCDHW fp32 [N,C,S] <-> NDHWC bf16 [N,S,C]  (S = D*H*W) */
+int snvc_ncdhw_f32_to_ndhwc_bf16(const float* src, void* dst, int64_t N, int64_t C, int64_t S, void* stream);
+int snvc_ndhwc_bf16_to_ncdhw_f32(const void* src, float* dst, int64_t N, int64_t C, int64_t S, void* stream);
+/* vernier.py:433: cat([voxel, vimg * occupancy], dim=1) -- writes channels [coffset, coffset+C) of a
+ * [N,S,cstride] bf16 buffer with vimg[N,S,C] * occ[N,S] (occ fp32). */
+int snvc_scale_by_occupancy(const void* vimg, const float* occ, void* dst, int64_t NS, int32_t C,
+                            int32_t cstride, int32_t coffset, void* stream);
+/* vernier.py:435-438: AvgPool3d((pool,1,1)) over the first spatial axis + reshape to BEV:
+ * x [N,Dh,H,W,C] bf16 NDHWC -> bev [N, C*(Dh/pool), H, W] fp32 (channel index c*(Dh/pool)+dh). */
+int snvc_avgpool_to_bev(const void* x, float* bev, int64_t N, int64_t Dh, int64_t H, int64_t W, int32_t C,
+                        int32_t pool, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNVC_B200_H_ */

@@ -1,0 +1,549 @@
+// A2 -- 3-D convolution / transposed convolution as a tcgen05 + TMEM implicit GEMM (sm_100a).
+//
+// Replaces the cuDNN calls behind nn.Conv3d / nn.ConvTranspose3d (+ eval BatchNorm3d, ReLU,
+// residual adds, sigmoid) in snvc/models/submodule.py:32-50,85-168,170-268 and
+// snvc/models/vernier.py:250-289,414-438.
+//
+// GEMM view, per filter tap t = (kd,kh,kw):   D[128 voxels, Cout] += A_t[128 voxels, Cin] * W_t[Cin, Cout]
+//   * activations are NDHWC bf16; one 5-D TMA box (Cin x TW x TH x TD x 1) per tap lands the
+//     128 x Cin operand tile in shared memory already in the canonical K-major swizzled UMMA
+//     layout (box rows = voxels, row = Cin bf16 = 64 or 128 B -> SWIZZLE_64B / SWIZZLE_128B);
+//     TMA out-of-bounds zero fill IS the convolution padding, TMA elementStrides IS the stride;
+//   * W_t (Cout x Cin, K-major) is a 2-D TMA box from the tap-major packed weights;
+//   * one elected thread issues tcgen05.mma (M=128, N=Cout, K=16) Cin/16 times per tap, all taps
+//     accumulate in TMEM (fp32); two TMEM accumulators so the epilogue of tile i overlaps the MMAs
+//     of tile i+1;
+//   * 4 epilogue warps read TMEM (tcgen05.ld 32x32b), apply folded-BN scale/bias, residual, ReLU,
+//     sigmoid in fp32 and store bf16 (or fp32) NDHWC rows with 128-bit stores.
+// Transposed conv (k3,s2,p1,op1) is decomposed into its 8 output-parity classes (1,2,2,2,4,4,4,8
+// taps) -- no zero insertion; each class is the same kernel with a different tap table and an
+// output stride of 2.
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+// Persistent: grid = min(#tiles, #SMs), static round-robin tile schedule.
+#include <cuda.h>
+
+#include <algorithm>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace snvc {
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 8;
+constexpr int kTileM = 128;
+
+struct ConvParams {
+  int N, Cin, Cout, CoutPad;
+  int Do, Ho, Wo;              // output tensor extent
+  int Dj, Hj, Wj;              // iteration space of this launch
+  int TD, TH, TW;              // tile, TD*TH*TW == 128
+  int tiles_d, tiles_h, tiles_w;
+  int num_tiles;
+  int in_stride;               // input coord = j*in_stride + off[tap]
+  int out_stride, out_off_d, out_off_h, out_off_w;   // output coord = j*out_stride + out_off
+  int K;                       // cubic kernel size (weight slot = (kd*K + kh)*K + kw)
+  int nk[3];                   // taps per dim (d,h,w) in this launch
+  signed char off[3][8];       // input offset per dim-tap
+  signed char kid[3][8];       // kernel index per dim-tap
+  int stages, a_bytes, b_bytes;
+  int swizzle_bytes;           // 32 / 64 / 128 == Cin*2
+  int relu, residual_mode, sigmoid, out_f32;
+  int out_cstride, out_coffset, res_cstride, res_coffset;
+  const float* scale;
+  const float* bias;
+  const __nv_bfloat16* residual;
+  void* y;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  uint64_t t0 = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if ((++spins & 0x3FFu) == 0) {
+      uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) __trap();   // 4 s
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 x bf16 -> fp32
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, swizzled operand tile: rows of `swizzle_bytes` bytes, 8-row atoms back to back.
+//   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major: 1) | [32,46) SBO>>4 = 8 rows
+//   | [46,48) version = 1 (sm_100) | [61,64) layout: 2 = SW128, 4 = SW64, 6 = SW32
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, int swizzle_bytes) {
+  const uint64_t layout = swizzle_bytes == 128 ? 2ull : (swizzle_bytes == 64 ? 4ull : 6ull);
+  const uint64_t sbo = (uint64_t)(8 * swizzle_bytes) >> 4;
+  return (uint64_t)((addr >> 4) & 0x3FFFu) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+// kind::f16 instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7, 10), K-major both, N>>3 @17, M>>4 @24
+__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct TileCoord { int n, jd, jh, jw; };
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) {
+  TileCoord t;
+  int tw = tile % p.tiles_w; tile /= p.tiles_w;
+  int th = tile % p.tiles_h; tile /= p.tiles_h;
+  int td = tile % p.tiles_d; tile /= p.tiles_d;
+  t.n = tile; t.jd = td * p.TD; t.jh = th * p.TH; t.jw = tw * p.TW;
+  return t;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                      const __grid_constant__ ConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ float s_scale[64], s_bias[64];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  // dynamic smem base rounded up to 1024 B (swizzle-128B atoms are 1024 B)
+  const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
+  const int stage_bytes = p.a_bytes + p.b_bytes;
+  const int ntaps = p.nk[0] * p.nk[1] * p.nk[2];
+  const uint32_t tmem_cols = p.CoutPad * 2 <= 32 ? 32u : (p.CoutPad * 2 <= 64 ? 64u : 128u);
+
+  if (threadIdx.x < 64) {
+    s_scale[threadIdx.x] = (p.scale && threadIdx.x < p.Cout) ? p.scale[threadIdx.x] : 1.f;
+    s_bias[threadIdx.x] = (p.bias && threadIdx.x < p.Cout) ? p.bias[threadIdx.x] : 0.f;
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&tmem_full_bar[b]), 1);
+      mbar_init(smem_u32(&tmem_empty_bar[b]), 4);   // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                 "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, tile);
+        const int cd = tc.jd * p.in_stride, ch = tc.jh * p.in_stride, cw = tc.jw * p.in_stride;
+        for (int id = 0; id < p.nk[0]; ++id)
+          for (int ih = 0; ih < p.nk[1]; ++ih)
+            for (int iw = 0; iw < p.nk[2]; ++iw) {
+              mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+              const uint32_t fb = smem_u32(&full_bar[stage]);
+              const uint32_t sa = smem_base + stage * stage_bytes;
+              mbar_expect_tx(fb, (uint32_t)stage_bytes);
+              tma_load_5d(sa, &map_x, fb, 0, cw + p.off[2][iw], ch + p.off[1][ih], cd + p.off[0][id], tc.n);
+              const int slot = (p.kid[0][id] * p.K + p.kid[1][ih]) * p.K + p.kid[2][iw];
+              tma_load_2d(sa + p.a_bytes, &map_w, fb, 0, slot * p.CoutPad);
+              if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(kTileM, p.CoutPad);
+      const int ksteps = p.Cin >> 4;
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t use = (uint32_t)(it >> 1);
+        mbar_wait(smem_u32(&tmem_empty_bar[buf]), (use & 1u) ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.CoutPad);
+        for (int t = 0; t < ntaps; ++t) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          const uint64_t adesc = make_smem_desc(sa, p.swizzle_bytes);
+          const uint64_t bdesc = make_smem_desc(sa + p.a_bytes, p.swizzle_bytes);
+          for (int k = 0; k < ksteps; ++k)   // +32 B per K=16 step inside the swizzled row: +2 in the >>4 field
+            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (t | k) ? 1u : 0u);
+          umma_commit(smem_u32(&empty_bar[stage]));          // frees the smem slot once these MMAs retire
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(smem_u32(&tmem_full_bar[buf]));          // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;          // accumulator row == box-linear voxel index
+    const int r_w = row % p.TW, r_h = (row / p.TW) % p.TH, r_d = row / (p.TW * p.TH);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      const TileCoord tc = decode_tile(p, tile);
+      const int jd = tc.jd + r_d, jh = tc.jh + r_h, jw = tc.jw + r_w;
+      const bool in_range = jd < p.Dj && jh < p.Hj && jw < p.Wj;
+      const int od = jd * p.out_stride + p.out_off_d, oh = jh * p.out_stride + p.out_off_h,
+                ow = jw * p.out_stride + p.out_off_w;
+      const int64_t vox = (((int64_t)tc.n * p.Do + od) * p.Ho + oh) * p.Wo + ow;
+      mbar_wait(smem_u32(&tmem_full_bar[buf]), use & 1u);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.CoutPad);
+      for (int c0 = 0; c0 < p.CoutPad; c0 += 16) {
+        uint32_t acc[16];
+        tmem_ld16(taddr + (uint32_t)c0, acc);
+        tmem_ld_wait();
+        if (in_range) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(acc[j]), s_scale[(c0 + j) & 63], s_bias[(c0 + j) & 63]);
+          float r[16];
+          const bool full = (c0 + 16 <= p.Cout);
+          if (p.residual_mode) {
+            const __nv_bfloat16* rp = p.residual + vox * p.res_cstride + p.res_coffset + c0;
+            if (full) {
+              uint4 q0 = __ldg(reinterpret_cast<const uint4*>(rp));
+              uint4 q1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
+              r[0] = bf16_lo(q0.x); r[1] = bf16_hi(q0.x); r[2] = bf16_lo(q0.y); r[3] = bf16_hi(q0.y);
+              r[4] = bf16_lo(q0.z); r[5] = bf16_hi(q0.z); r[6] = bf16_lo(q0.w); r[7] = bf16_hi(q0.w);
+              r[8] = bf16_lo(q1.x); r[9] = bf16_hi(q1.x); r[10] = bf16_lo(q1.y); r[11] = bf16_hi(q1.y);
+              r[12] = bf16_lo(q1.z); r[13] = bf16_hi(q1.z); r[14] = bf16_lo(q1.w); r[15] = bf16_hi(q1.w);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) r[j] = (c0 + j < p.Cout) ? __bfloat162float(rp[j]) : 0.f;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float x = v[j];
+            if (p.residual_mode == 1) x += r[j];
+            if (p.relu) x = fmaxf(x, 0.f);
+            if (p.residual_mode == 2) x += r[j];
+            if (p.sigmoid) x = 1.f / (1.f + __expf(-x));
+            v[j] = x;
+          }
+          if (p.out_f32) {
+            float* o = reinterpret_cast<float*>(p.y) + vox * p.out_cstride + p.out_coffset + c0;
+            if (full && ((p.out_cstride | p.out_coffset) & 3) == 0) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (c0 + j < p.Cout) o[j] = v[j];
+            }
+          } else {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.y) + vox * p.out_cstride + p.out_coffset + c0;
+            if (full && ((p.out_cstride | p.out_coffset) & 7) == 0) {
+              uint4 q0 = {pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])};
+              uint4 q1 = {pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
+                          pack_bf16x2(v[14], v[15])};
+              *reinterpret_cast<uint4*>(o) = q0;
+              *(reinterpret_cast<uint4*>(o) + 1) = q1;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (c0 + j < p.Cout) o[j] = __float2bfloat16_rn(v[j]);
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[buf]));
+    }
+  }
+
+  // teardown: everyone done with TMEM before the allocating warp frees it
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ weight packing
+// w fp32: conv [Cout,Cin,k,k,k] / deconv [Cin,Cout,k,k,k]  ->  packed bf16 [k^3][CoutPad][Cin]
+__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cin, int Cout,
+                                    int CoutPad, int K3, int transposed, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int ci = (int)(i % Cin);
+    int64_t t = i / Cin;
+    int co = (int)(t % CoutPad);
+    int tap = (int)(t / CoutPad);
+    float v = 0.f;
+    if (co < Cout) v = transposed ? w[((int64_t)ci * Cout + co) * K3 + tap] : w[((int64_t)co * Cin + ci) * K3 + tap];
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)f;
+  });
+  return fn;
+}
+
+CUtensorMapSwizzle swizzle_mode(int bytes) {
+  return bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// pick (TD,TH,TW), product 128, minimising padded work; ties -> wider W (longer contiguous runs)
+void pick_tile(int Dj, int Hj, int Wj, int& TD, int& TH, int& TW) {
+  double best = -1;
+  for (int tw = 128; tw >= 1; tw >>= 1)
+    for (int th = 128 / tw; th >= 1; th >>= 1) {
+      int td = 128 / (tw * th);
+      double padded = (double)round_up(Dj, td) * round_up(Hj, th) * round_up(Wj, tw);
+      double eff = (double)Dj * Hj * Wj / padded;
+      // prefer tiles that are not degenerate slivers: mild bonus for tw >= 8
+      double score = eff + (tw >= 8 ? 1e-3 : 0) + (tw >= 4 ? 1e-4 : 0) + 1e-6 * tw;
+      if (score > best) { best = score; TD = td; TH = th; TW = tw; }
+    }
+}
+
+int launch_conv(const void* x, const void* w_packed, const float* scale, const float* bias, const void* residual, void* y,
+                const snvc_conv3d_desc& d, ConvParams p, cudaStream_t stream) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return fail(SNVC_E_DRIVER, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  p.scale = scale; p.bias = bias; p.residual = (const __nv_bfloat16*)residual; p.y = y;
+  pick_tile(p.Dj, p.Hj, p.Wj, p.TD, p.TH, p.TW);
+  p.tiles_d = (int)ceil_div(p.Dj, p.TD); p.tiles_h = (int)ceil_div(p.Hj, p.TH); p.tiles_w = (int)ceil_div(p.Wj, p.TW);
+  int64_t nt = (int64_t)p.N * p.tiles_d * p.tiles_h * p.tiles_w;
+  SNVC_CHECK_ARG(nt < (1ll << 31), "too many tiles");
+  p.num_tiles = (int)nt;
+  if (p.num_tiles == 0) return 0;
+  p.swizzle_bytes = p.Cin * 2;
+  p.a_bytes = kTileM * p.Cin * 2;
+  p.b_bytes = p.CoutPad * p.Cin * 2;
+  const int stage_bytes = p.a_bytes + p.b_bytes;
+  p.stages = std::max(2, std::min(kMaxStages, (200 * 1024) / stage_bytes));
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+
+  CUtensorMap map_x, map_w;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)p.Cin, (cuuint64_t)d.Wi, (cuuint64_t)d.Hi, (cuuint64_t)d.Di, (cuuint64_t)p.N};
+    cuuint64_t strides[4] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)d.Wi * p.Cin * 2, (cuuint64_t)d.Hi * d.Wi * p.Cin * 2,
+                             (cuuint64_t)d.Di * d.Hi * d.Wi * p.Cin * 2};
+    const int s = p.in_stride;
+    cuuint32_t box[5] = {(cuuint32_t)p.Cin, (cuuint32_t)((p.TW - 1) * s + 1), (cuuint32_t)((p.TH - 1) * s + 1),
+                         (cuuint32_t)((p.TD - 1) * s + 1), 1};
+    cuuint32_t estr[5] = {1, (cuuint32_t)s, (cuuint32_t)s, (cuuint32_t)s, 1};
+    CUresult r = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_mode(p.swizzle_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail((int)r, "cuTensorMapEncodeTiled(x) failed with CUresult %d", (int)r);
+  }
+  {
+    const int K3 = p.K * p.K * p.K;
+    cuuint64_t dims[2] = {(cuuint64_t)p.Cin, (cuuint64_t)K3 * p.CoutPad};
+    cuuint64_t strides[1] = {(cuuint64_t)p.Cin * 2};
+    cuuint32_t box[2] = {(cuuint32_t)p.Cin, (cuuint32_t)p.CoutPad};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_packed), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_mode(p.swizzle_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail((int)r, "cuTensorMapEncodeTiled(w) failed with CUresult %d", (int)r);
+  }
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(conv3d_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  // (the attribute is per device; set it again cheaply when another device is current)
+  cudaFuncSetAttribute(conv3d_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (attr_err != cudaSuccess) return fail((int)attr_err, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
+  const int grid = std::min(p.num_tiles, sm_count());
+  conv3d_tcgen05_kernel<<<grid, kThreads, smem, stream>>>(map_x, map_w, p);
+  return launch_status("conv3d_tcgen05_kernel");
+}
+
+}  // namespace
+}  // namespace snvc
+
+using namespace snvc;
+
+extern "C" int64_t snvc_conv3d_packed_weight_bytes(int32_t Cin, int32_t Cout, int32_t kernel) {
+  return (int64_t)kernel * kernel * kernel * round_up(Cout, 16) * Cin * 2;
+}
+
+extern "C" int snvc_conv3d_pack_weights(const float* w, void* w_packed, int32_t Cin, int32_t Cout, int32_t kernel,
+                                        int32_t transposed, void* stream) {
+  SNVC_CHECK_ARG(w && w_packed, "null pointer");
+  SNVC_CHECK_ARG(Cin > 0 && Cout > 0 && kernel > 0, "bad dimensions");
+  const int CoutPad = round_up(Cout, 16);
+  const int K3 = kernel * kernel * kernel;
+  const int64_t total = (int64_t)K3 * CoutPad * Cin;
+  int blocks = (int)std::min<int64_t>(ceil_div(total, 256), 1024);
+  pack_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)w_packed, Cin, Cout, CoutPad, K3,
+                                                                transposed, total);
+  return launch_status("pack_weights_kernel");
+}
+
+extern "C" int snvc_conv3d_fwd(const void* x, const void* w_packed, const float* scale, const float* bias,
+                               const void* residual, void* y, const snvc_conv3d_desc* dp, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SNVC_CHECK_ARG(dp != nullptr, "desc is null");
+  const snvc_conv3d_desc& d = *dp;
+  SNVC_CHECK_ARG(x && w_packed && y, "null pointer");
+  SNVC_CHECK_ARG(d.Cin == 16 || d.Cin == 32 || d.Cin == 64, "Cin must be 16, 32 or 64 (got %d)", d.Cin);
+  SNVC_CHECK_ARG(d.Cout >= 1 && d.Cout <= 64, "Cout must be in [1, 64] (got %d)", d.Cout);
+  SNVC_CHECK_ARG(d.N >= 0 && d.Di > 0 && d.Hi > 0 && d.Wi > 0, "bad input extent");
+  SNVC_CHECK_ARG(d.out_dtype == SNVC_BF16 || d.out_dtype == SNVC_F32, "out_dtype must be bf16 or f32");
+  SNVC_CHECK_ARG(d.residual_mode == 0 || residual != nullptr, "residual_mode set but residual is null");
+  SNVC_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(y) & 15) == 0,
+                 "x, w_packed and y must be 16-byte aligned");
+  if (d.N == 0) return 0;
+
+  ConvParams p{};
+  p.N = d.N; p.Cin = d.Cin; p.Cout = d.Cout; p.CoutPad = round_up(d.Cout, 16);
+  p.Do = d.Do; p.Ho = d.Ho; p.Wo = d.Wo;
+  p.K = d.kernel;
+  p.relu = d.relu; p.residual_mode = d.residual_mode; p.sigmoid = d.sigmoid; p.out_f32 = d.out_dtype == SNVC_F32;
+  p.out_cstride = d.out_cstride ? d.out_cstride : d.Cout;
+  p.out_coffset = d.out_coffset;
+  p.res_cstride = d.res_cstride ? d.res_cstride : d.Cout;
+  p.res_coffset = d.res_coffset;
+  SNVC_CHECK_ARG(p.out_coffset + d.Cout <= p.out_cstride, "output channel slice out of range");
+
+  if (!d.transposed) {
+    SNVC_CHECK_ARG(d.kernel >= 1 && d.kernel <= 7, "kernel must be in [1,7]");
+    SNVC_CHECK_ARG(d.stride == 1 || d.stride == 2, "stride must be 1 or 2");
+    SNVC_CHECK_ARG(d.dilation >= 1 && d.pad >= 0, "bad dilation / pad");
+    const int ext = d.dilation * (d.kernel - 1) + 1;
+    SNVC_CHECK_ARG(d.Do == (d.Di + 2 * d.pad - ext) / d.stride + 1 && d.Ho == (d.Hi + 2 * d.pad - ext) / d.stride + 1 &&
+                       d.Wo == (d.Wi + 2 * d.pad - ext) / d.stride + 1,
+                   "output extent does not match conv geometry");
+    SNVC_CHECK_ARG(d.dilation * (d.kernel - 1) - d.pad <= 127 && d.pad <= 127, "tap offset out of range");
+    p.Dj = d.Do; p.Hj = d.Ho; p.Wj = d.Wo;
+    p.in_stride = d.stride;
+    p.out_stride = 1; p.out_off_d = p.out_off_h = p.out_off_w = 0;
+    for (int a = 0; a < 3; ++a) {
+      p.nk[a] = d.kernel;
+      for (int j = 0; j < d.kernel; ++j) {
+        p.off[a][j] = (signed char)(j * d.dilation - d.pad);
+        p.kid[a][j] = (signed char)j;
+      }
+    }
+    return launch_conv(x, w_packed, scale, bias, residual, y, d, p, stream);
+  }
+
+  // ConvTranspose3d(k=3, s=2, p=1, output_padding=1): out[o] += x[i] * W[k], o = 2i - 1 + k.
+  //   even o = 2j   : k=1, i=j
+  //   odd  o = 2j+1 : k=2, i=j   and   k=0, i=j+1
+  SNVC_CHECK_ARG(d.kernel == 3 && d.stride == 2 && d.pad == 1 && d.dilation == 1,
+                 "transposed conv supports k=3, s=2, p=1, output_padding=1 only");
+  SNVC_CHECK_ARG(d.Do == 2 * d.Di && d.Ho == 2 * d.Hi && d.Wo == 2 * d.Wi, "transposed conv output must be 2x input");
+  p.Dj = d.Di; p.Hj = d.Hi; p.Wj = d.Wi;
+  p.in_stride = 1;
+  p.out_stride = 2;
+  for (int cls = 0; cls < 8; ++cls) {
+    const int par[3] = {(cls >> 2) & 1, (cls >> 1) & 1, cls & 1};
+    for (int a = 0; a < 3; ++a) {
+      if (par[a] == 0) {
+        p.nk[a] = 1; p.off[a][0] = 0; p.kid[a][0] = 1;
+      } else {
+        p.nk[a] = 2; p.off[a][0] = 0; p.kid[a][0] = 2; p.off[a][1] = 1; p.kid[a][1] = 0;
+      }
+    }
+    p.out_off_d = par[0]; p.out_off_h = par[1]; p.out_off_w = par[2];
+    if (int e = launch_conv(x, w_packed, scale, bias, residual, y, d, p, stream)) return e;
+  }
+  return 0;
+}

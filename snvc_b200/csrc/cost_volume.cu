@@ -1,0 +1,436 @@
+// A1 / A1b -- plane-sweep cost volume for sm_100a.
+//
+// Semantics: snvc/extension/build_cost_volume/src/BuildCostVolume_cuda.cu:63-98 (forward),
+// :15-61 (bilinear rule), :152-205 (backward).  Design (not the reference's one-thread-per-
+// element gather): every CTA stages the few input rows it needs in shared memory ONCE and emits
+// all depth bins from there, so HBM sees one read of the features and one fully coalesced
+// 128-bit write stream of the volume.  Two layouts:
+//   * NCDHW fp32/fp64 -- the reference's output layout (drop-in for build_cost_volume);
+//   * NDHWC bf16      -- channels-last, exactly what the tcgen05 conv3d TMA-loads
+//                        (halves the dominant write stream).
+// Arithmetic is written with explicit round-to-nearest intrinsics so that the result is
+// bit-identical to the nvcc-compiled reference expression  w1*v1 + w2*v2 + w3*v3 + w4*v4
+// (-fmad=true => fma(w2,v2, w1*v1); the w3/w4 terms are exact zeros because y is an integer).
+#include "common.cuh"
+
+namespace snvc {
+namespace {
+
+template <typename T> struct Arith;
+template <> struct Arith<float> {
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+};
+template <> struct Arith<double> {
+  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+  static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+  static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+  static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+};
+
+// Sample position for output column pw at depth shift s (.cu:84-96, :26-49).
+// Returns false when the sample is outside the image (value 0).  x_low/x_high/lx as the reference.
+template <typename T>
+__device__ __forceinline__ bool sample_pos(int iw, T neg_shift, int img_w, int& x_low, int& x_high, T& lx) {
+  T x = Arith<T>::add((T)iw, neg_shift);
+  if (!(x >= (T)0 && x <= (T)(img_w - 1))) return false;
+  if (x <= (T)0) x = (T)0;
+  x_low = (int)x;
+  if (x_low >= img_w - 1) {
+    x_high = x_low = img_w - 1;
+    x = (T)x_low;
+  } else {
+    x_high = x_low + 1;
+  }
+  lx = Arith<T>::sub(x, (T)x_low);
+  return true;
+}
+
+template <typename T>
+__device__ __forceinline__ T interp(T lx, T v1, T v2) {
+  T hx = Arith<T>::sub((T)1, lx);
+  return Arith<T>::fma(lx, v2, Arith<T>::mul(hx, v1));
+}
+
+// ------------------------------------------------------------------------------------------
+// NCDHW.  grid = (h-tiles, N*C, d-splits);  smem: TH rows of left and right (+ shifts).
+// ------------------------------------------------------------------------------------------
+template <typename T, bool VEC4>
+__global__ void __launch_bounds__(256)
+cv_ncdhw_kernel(const T* __restrict__ left, const T* __restrict__ right, const T* __restrict__ shift,
+                T* __restrict__ cost, int C, int img_h, int img_w, int D, int H, int W, int ds, int TH,
+                int d_per_cta) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* sL = reinterpret_cast<T*>(smem_raw);
+  T* sR = sL + (size_t)TH * img_w;
+  T* sS = sR + (size_t)TH * img_w;
+
+  const int nc = blockIdx.y;
+  const int n = nc / C;
+  const int c = nc - n * C;
+  const int ph0 = blockIdx.x * TH;
+  const int th = min(TH, H - ph0);
+  const int d0 = blockIdx.z * d_per_cta;
+  const int dn = min(d_per_cta, D - d0);
+  if (dn <= 0) return;
+
+  const T* lplane = left + (int64_t)nc * img_h * img_w;
+  const T* rplane = right + (int64_t)nc * img_h * img_w;
+  for (int i = threadIdx.x; i < th * img_w; i += blockDim.x) {
+    int r = i / img_w, col = i - r * img_w;
+    int64_t g = (int64_t)(ph0 + r) * ds * img_w + col;
+    sL[r * img_w + col] = lplane[g];
+    sR[r * img_w + col] = rplane[g];
+  }
+  for (int i = threadIdx.x; i < dn; i += blockDim.x) sS[i] = -shift[(int64_t)n * D + d0 + i];
+  __syncthreads();
+
+  const int64_t plane = (int64_t)H * W;
+  T* outL = cost + (((int64_t)n * 2 * C + c) * D + d0) * plane + (int64_t)ph0 * W;
+  T* outR = outL + (int64_t)C * D * plane;
+
+  if (VEC4) {
+    // W % 4 == 0 and T == float: one float4 per thread-iteration
+    const int W4 = W >> 2;
+    const int per_d = th * W4;
+    const int total = dn * per_d;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+      int dd = idx / per_d;
+      int rem = idx - dd * per_d;
+      int r = rem / W4;
+      int pw = (rem - r * W4) << 2;
+      const T ns = sS[dd];
+      const T* rowL = sL + r * img_w;
+      const T* rowR = sR + r * img_w;
+      float4 vl, vr;
+      float* pl = reinterpret_cast<float*>(&vl);
+      float* pr = reinterpret_cast<float*>(&vr);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int iw = (pw + j) * ds;
+        pl[j] = (float)rowL[iw];
+        int xl, xh;
+        T lx;
+        pr[j] = sample_pos<T>(iw, ns, img_w, xl, xh, lx) ? (float)interp<T>(lx, rowR[xl], rowR[xh]) : 0.f;
+      }
+      int64_t o = (int64_t)dd * plane + (int64_t)r * W + pw;
+      st_cs_f4(reinterpret_cast<float*>(outL + o), vl);
+      st_cs_f4(reinterpret_cast<float*>(outR + o), vr);
+    }
+  } else {
+    const int per_d = th * W;
+    const int total = dn * per_d;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+      int dd = idx / per_d;
+      int rem = idx - dd * per_d;
+      int r = rem / W;
+      int pw = rem - r * W;
+      int iw = pw * ds;
+      int xl, xh;
+      T lx;
+      int64_t o = (int64_t)dd * plane + (int64_t)r * W + pw;
+      outL[o] = sL[r * img_w + iw];
+      outR[o] = sample_pos<T>(iw, sS[dd], img_w, xl, xh, lx)
+                    ? interp<T>(lx, sR[r * img_w + xl], sR[r * img_w + xh])
+                    : (T)0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// NDHWC bf16 (fp32 in).  grid = (H, N, d-splits * w-tiles).
+// smem holds one input row of every channel, transposed to [col][C] with a 16-byte XOR swizzle
+// (conflict-free float4 reads by 8-channel lanes, <=4-way conflicts on the one-off staging).
+// ------------------------------------------------------------------------------------------
+// 16-byte chunk q of column `col` lives at chunk (q ^ (col & mask)); mask = 2^k - 1 with 2^k | C/4.
+__device__ __forceinline__ int swz(int col, int c, int C, int mask) {
+  return col * C + ((((c >> 2) ^ (col & mask)) << 2) | (c & 3));
+}
+__device__ __forceinline__ const float4* chunk_ptr(const float* base, int col, int q, int C, int mask) {
+  return reinterpret_cast<const float4*>(base + col * C + ((q ^ (col & mask)) << 2));
+}
+
+__global__ void __launch_bounds__(256)
+cv_ndhwc_bf16_kernel(const float* __restrict__ left, const float* __restrict__ right,
+                     const float* __restrict__ shift, __nv_bfloat16* __restrict__ cost, int C, int img_h,
+                     int img_w, int D, int H, int W, int ds, int d_per_cta, int n_dsplit, int TW, int S, int mask) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int ph = blockIdx.x;
+  const int n = blockIdx.y;
+  const int dsplit = blockIdx.z % n_dsplit;
+  const int wtile = blockIdx.z / n_dsplit;
+  const int d0 = dsplit * d_per_cta;
+  const int dn = min(d_per_cta, D - d0);
+  const int pw0 = wtile * TW;
+  const int tw = min(TW, W - pw0);
+  if (dn <= 0 || tw <= 0) return;
+
+  // input column windows staged in smem
+  const int llo = pw0 * ds, lhi = (pw0 + tw - 1) * ds + 1;              // left: [llo, lhi)
+  const int rlo = max(0, llo - S), rhi = min(img_w, lhi + 1);            // right: [rlo, rhi)
+  const int lw = lhi - llo, rw = rhi - rlo;
+  float* sL = reinterpret_cast<float*>(smem_raw);
+  float* sR = sL + (size_t)lw * C;
+  float* sS = sR + (size_t)rw * C;
+
+  const int ih = ph * ds;
+  const float* lrow = left + ((int64_t)n * C * img_h + ih) * img_w;      // + c*img_h*img_w + col
+  const float* rrow = right + ((int64_t)n * C * img_h + ih) * img_w;
+  const int64_t cstride = (int64_t)img_h * img_w;
+  for (int i = threadIdx.x; i < C * lw; i += blockDim.x) {
+    int c = i / lw, col = i - c * lw;
+    sL[swz(col, c, C, mask)] = lrow[c * cstride + llo + col];
+  }
+  for (int i = threadIdx.x; i < C * rw; i += blockDim.x) {
+    int c = i / rw, col = i - c * rw;
+    sR[swz(col, c, C, mask)] = rrow[c * cstride + rlo + col];
+  }
+  for (int i = threadIdx.x; i < dn; i += blockDim.x) sS[i] = -shift[(int64_t)n * D + d0 + i];
+  __syncthreads();
+
+  const int CG = C >> 3;                // 8-channel groups per view
+  const int per_d = tw * CG;
+  const int total = dn * per_d;
+  const int C2 = 2 * C;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    int dd = idx / per_d;
+    int rem = idx - dd * per_d;
+    int wl = rem / CG;
+    int cg = rem - wl * CG;
+    int pw = pw0 + wl;
+    int iw = pw * ds;
+    __nv_bfloat16* o = cost + ((((int64_t)n * D + d0 + dd) * H + ph) * W + pw) * C2 + cg * 8;
+
+    // left half: broadcast copy
+    {
+      int col = iw - llo;
+      const float4 a = *chunk_ptr(sL, col, 2 * cg, C, mask);
+      const float4 b = *chunk_ptr(sL, col, 2 * cg + 1, C, mask);
+      uint4 v = {pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w)};
+      *reinterpret_cast<uint4*>(o) = v;
+    }
+    // right half: 1-D linear interpolation along the row
+    int xl, xh;
+    float lx;
+    uint4 v = {0u, 0u, 0u, 0u};
+    if (sample_pos<float>(iw, sS[dd], img_w, xl, xh, lx)) {
+      float r0[8], r1[8];
+      if (xl >= rlo) {
+        int c0 = xl - rlo, c1 = xh - rlo;
+        *reinterpret_cast<float4*>(r0) = *chunk_ptr(sR, c0, 2 * cg, C, mask);
+        *reinterpret_cast<float4*>(r0 + 4) = *chunk_ptr(sR, c0, 2 * cg + 1, C, mask);
+        *reinterpret_cast<float4*>(r1) = *chunk_ptr(sR, c1, 2 * cg, C, mask);
+        *reinterpret_cast<float4*>(r1 + 4) = *chunk_ptr(sR, c1, 2 * cg + 1, C, mask);
+      } else {
+        // sample left of the staged window (very large shift on a w-tiled row): read HBM directly
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          r0[j] = rrow[(int64_t)(cg * 8 + j) * cstride + xl];
+          r1[j] = rrow[(int64_t)(cg * 8 + j) * cstride + xh];
+        }
+      }
+      float r[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = interp<float>(lx, r0[j], r1[j]);
+      v = {pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7])};
+    }
+    *reinterpret_cast<uint4*>(o + C) = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Backward: gather formulation, one thread per input pixel, fixed summation order
+// (d ascending, then the <=2 output columns that touch this pixel) -> deterministic, no atomics.
+//   grad_left [n,c,ih,iw]  = sum_d grad[n, c, d, ih/ds, iw/ds]           (iw, ih multiples of ds)
+//   grad_right[n,c,ih,x]   = sum_d sum_{pw : x_low==x or x_high==x} w * grad[n, C+c, d, ih/ds, pw]
+// Semantics .cu:152-205 (weights below 1e-10 are skipped as in :195-202).
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+cv_bwd_kernel(const T* __restrict__ grad, const T* __restrict__ shift, T* __restrict__ gl, T* __restrict__ gr,
+              int C, int H, int W, int D, int ds, int64_t total) {
+  const int img_h = H * ds, img_w = W * ds;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int x = (int)(i % img_w);
+    int64_t t = i / img_w;
+    int ih = (int)(t % img_h);
+    int64_t nc = t / img_h;
+    int n = (int)(nc / C), c = (int)(nc - (int64_t)n * C);
+    T accL = (T)0, accR = (T)0;
+    if (ih % ds == 0) {
+      const int ph = ih / ds;
+      const T* gL = grad + (((int64_t)n * 2 * C + c) * D) * H * W + (int64_t)ph * W;
+      const T* gR = gL + (int64_t)C * D * H * W;
+      const int64_t plane = (int64_t)H * W;
+      const bool on_grid = (x % ds) == 0;
+      for (int d = 0; d < D; ++d) {
+        if (on_grid) accL += gL[d * plane + x / ds];
+        const T s = shift[(int64_t)n * D + d];
+        const T ns = -s;
+        // candidate output columns: iw - s in (x-1, x+1)  <=>  iw in (x-1+s, x+1+s)
+        T lo = (T)x - (T)1 + s, hi = (T)x + (T)1 + s;
+        int pw_lo = (int)floor((double)lo / ds) - 1;
+        int pw_hi = (int)ceil((double)hi / ds) + 1;
+        pw_lo = max(pw_lo, 0);
+        pw_hi = min(pw_hi, W - 1);
+        for (int pw = pw_lo; pw <= pw_hi; ++pw) {
+          int xl, xh;
+          T lx;
+          if (!sample_pos<T>(pw * ds, ns, img_w, xl, xh, lx)) continue;
+          if (xl != x && xh != x) continue;
+          T hx = Arith<T>::sub((T)1, lx);
+          // hy = 1, ly = 0 (integer y): w1 = hx, w2 = lx, w3 = w4 = 0
+          T g = gR[d * plane + pw];
+          if (xl == x && hx >= (T)1e-10) accR += g * hx;
+          if (xh == x && lx >= (T)1e-10) accR += g * lx;
+        }
+      }
+    }
+    gl[i] = accL;
+    gr[i] = accR;
+  }
+}
+
+__global__ void cv_xlow_kernel(const float* __restrict__ shift, int32_t* __restrict__ xlow, int64_t total, int D,
+                               int W, int ds) {
+  const int img_w = W * ds;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int pw = (int)(i % W);
+    int64_t nd = i / W;
+    int xl, xh;
+    float lx;
+    xlow[i] = sample_pos<float>(pw * ds, -shift[nd], img_w, xl, xh, lx) ? xl : -1;
+  }
+}
+
+}  // namespace
+}  // namespace snvc
+
+using namespace snvc;
+
+extern "C" int snvc_cost_volume_fwd(const void* left, const void* right, const void* shift, void* cost, int64_t N,
+                                    int64_t C, int64_t IH, int64_t IW, int64_t D, int32_t ds, int32_t dtype,
+                                    int32_t out_dtype, int32_t out_layout, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SNVC_CHECK_ARG(ds >= 1, "downsample must be >= 1 (got %d)", ds);
+  SNVC_CHECK_ARG(N >= 0 && C >= 0 && IH >= 0 && IW >= 0 && D >= 0, "negative dimension");
+  SNVC_CHECK_ARG(IH % ds == 0 && IW % ds == 0, "IH (%lld) and IW (%lld) must be multiples of downsample (%d)",
+                 (long long)IH, (long long)IW, ds);
+  const int64_t H = IH / ds, W = IW / ds;
+  if (N * C * D * H * W == 0) return 0;  // empty output returns early (.cu:235-238)
+  SNVC_CHECK_ARG(left && right && shift && cost, "null pointer");
+  SNVC_CHECK_ARG(IW < (1 << 24) && IH < (1 << 24) && D < (1 << 24) && N * C < (1ll << 31) && N < 65536,
+                 "dimension too large");
+
+  if (out_layout == SNVC_NCDHW) {
+    const bool f32 = dtype == SNVC_F32 && out_dtype == SNVC_F32;
+    const bool f64 = dtype == SNVC_F64 && out_dtype == SNVC_F64;
+    if (!f32 && !f64) return fail(SNVC_E_UNSUPPORTED, "NCDHW cost volume: supported types are f32->f32 and f64->f64");
+    const size_t es = f32 ? 4 : 8;
+    int TH = 4;
+    while (TH > 1 && (2 * TH * IW + D) * es > 96 * 1024) TH >>= 1;
+    size_t smem = (2 * (size_t)TH * IW + D) * es;
+    if (smem > 200 * 1024) return fail(SNVC_E_UNSUPPORTED, "image row too wide for the staged kernel (IW=%lld)", (long long)IW);
+    const int64_t htiles = ceil_div(H, TH);
+    SNVC_CHECK_ARG(N * C <= 65535 * 1ll, "N*C too large for one launch (%lld)", (long long)(N * C));
+    // enough CTAs for >= ~8 waves: split D when the (h-tile, n, c) grid is small
+    int64_t base = htiles * N * C;
+    int dsplit = 1;
+    const int64_t want = 8ll * 4 * sm_count();
+    while (base * dsplit < want && dsplit * 2 <= D) dsplit *= 2;
+    int d_per = (int)ceil_div(D, dsplit);
+    dsplit = (int)ceil_div(D, d_per);
+    dim3 grid((unsigned)htiles, (unsigned)(N * C), (unsigned)dsplit);
+    if (f32) {
+      const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(cost) & 15) == 0);
+      auto k = vec ? cv_ncdhw_kernel<float, true> : cv_ncdhw_kernel<float, false>;
+      if (smem > 48 * 1024) SNVC_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k<<<grid, 256, smem, stream>>>((const float*)left, (const float*)right, (const float*)shift, (float*)cost,
+                                     (int)C, (int)IH, (int)IW, (int)D, (int)H, (int)W, ds, TH, d_per);
+    } else {
+      auto k = cv_ncdhw_kernel<double, false>;
+      if (smem > 48 * 1024) SNVC_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k<<<grid, 256, smem, stream>>>((const double*)left, (const double*)right, (const double*)shift, (double*)cost,
+                                     (int)C, (int)IH, (int)IW, (int)D, (int)H, (int)W, ds, TH, d_per);
+    }
+    return launch_status("cv_ncdhw_kernel");
+  }
+
+  if (out_layout == SNVC_NDHWC) {
+    if (!(dtype == SNVC_F32 && out_dtype == SNVC_BF16))
+      return fail(SNVC_E_UNSUPPORTED, "NDHWC cost volume: supported types are f32 -> bf16");
+    SNVC_CHECK_ARG(C % 8 == 0, "NDHWC cost volume needs C %% 8 == 0 (got %lld)", (long long)C);
+    SNVC_CHECK_ARG((reinterpret_cast<uintptr_t>(cost) & 15) == 0, "cost must be 16-byte aligned");
+    SNVC_CHECK_ARG(H <= 2147483647ll && N <= 65535, "H/N too large");
+    // w-tiling: whole row when it fits (KITTI 1/4-res: 2*312*32*4 = 78 KB -> 2 CTAs/SM)
+    const size_t budget = 100 * 1024, hard = 200 * 1024;
+    int TW = (int)W, S = 0;
+    size_t row_bytes = (size_t)C * 4;
+    auto need = [&](int tw, int s) { return ((size_t)((tw - 1) * ds + 1) + (size_t)((tw - 1) * ds + 2 + s)) * row_bytes + (size_t)D * 4; };
+    if (need(TW, 0) > budget) {
+      int ntile = 2;
+      while (need((int)ceil_div(W, ntile), 0) > budget / 2 && ntile < W) ++ntile;
+      TW = (int)ceil_div(W, ntile);
+      // spend what is left of the hard budget on the left extension of the right window
+      size_t rest = hard - need(TW, 0);
+      S = (int)(rest / row_bytes);
+    }
+    const int wtiles = (int)ceil_div(W, TW);
+    size_t smem = need(TW, S);
+    if (smem > 220 * 1024) return fail(SNVC_E_UNSUPPORTED, "cost volume tile does not fit shared memory");
+    int64_t base = H * N * wtiles;
+    int dsplit = 1;
+    const int64_t want = 8ll * 2 * sm_count();
+    while (base * dsplit < want && dsplit < D) ++dsplit;
+    int d_per = (int)ceil_div(D, dsplit);
+    dsplit = (int)ceil_div(D, d_per);
+    SNVC_CHECK_ARG((int64_t)dsplit * wtiles <= 65535, "grid.z too large");
+    if (smem > 48 * 1024)
+      SNVC_CUDA_OK(cudaFuncSetAttribute(cv_ndhwc_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int mask = 1;  // largest 2^k - 1 (k <= 3) with 2^k | C/4
+    while (mask < 7 && ((C / 4) % (2 * (mask + 1))) == 0) mask = 2 * mask + 1;
+    dim3 grid((unsigned)H, (unsigned)N, (unsigned)(dsplit * wtiles));
+    cv_ndhwc_bf16_kernel<<<grid, 256, smem, stream>>>((const float*)left, (const float*)right, (const float*)shift,
+                                                       (__nv_bfloat16*)cost, (int)C, (int)IH, (int)IW, (int)D, (int)H,
+                                                       (int)W, ds, d_per, dsplit, TW, S, mask);
+    return launch_status("cv_ndhwc_bf16_kernel");
+  }
+  return fail(SNVC_E_BADARG, "unknown out_layout %d", out_layout);
+}
+
+extern "C" int snvc_cost_volume_bwd(const void* grad, const void* shift, void* grad_left, void* grad_right, int64_t N,
+                                    int64_t C, int64_t H, int64_t W, int64_t D, int32_t ds, int32_t dtype,
+                                    void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SNVC_CHECK_ARG(ds >= 1, "downsample must be >= 1");
+  SNVC_CHECK_ARG(dtype == SNVC_F32 || dtype == SNVC_F64, "dtype must be f32 or f64");
+  const int64_t total = N * C * H * ds * W * ds;
+  if (total == 0) return 0;
+  SNVC_CHECK_ARG(grad_left && grad_right && shift, "null pointer");
+  const size_t es = dtype == SNVC_F32 ? 4 : 8;
+  if (D == 0 || grad == nullptr) {  // empty gradient: zeros (.cu:270-285)
+    SNVC_CUDA_OK(cudaMemsetAsync(grad_left, 0, total * es, stream));
+    SNVC_CUDA_OK(cudaMemsetAsync(grad_right, 0, total * es, stream));
+    return 0;
+  }
+  int blocks = (int)std::min<int64_t>(ceil_div(total, 256), (int64_t)sm_count() * 16);
+  if (dtype == SNVC_F32)
+    cv_bwd_kernel<float><<<blocks, 256, 0, stream>>>((const float*)grad, (const float*)shift, (float*)grad_left,
+                                                     (float*)grad_right, (int)C, (int)H, (int)W, (int)D, ds, total);
+  else
+    cv_bwd_kernel<double><<<blocks, 256, 0, stream>>>((const double*)grad, (const double*)shift, (double*)grad_left,
+                                                      (double*)grad_right, (int)C, (int)H, (int)W, (int)D, ds, total);
+  return launch_status("cv_bwd_kernel");
+}
+
+extern "C" int snvc_cost_volume_xlow(const float* shift, int32_t* xlow, int64_t N, int64_t IW, int64_t D, int32_t ds,
+                                     void* stream_) {
+  SNVC_CHECK_ARG(ds >= 1 && IW % ds == 0, "bad downsample");
+  const int64_t W = IW / ds, total = N * D * W;
+  if (total == 0) return 0;
+  int blocks = (int)std::min<int64_t>(ceil_div(total, 256), (int64_t)sm_count() * 8);
+  cv_xlow_kernel<<<blocks, 256, 0, (cudaStream_t)stream_>>>(shift, xlow, total, (int)D, (int)W, ds);
+  return launch_status("cv_xlow_kernel");
+}

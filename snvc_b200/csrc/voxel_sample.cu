@@ -1,0 +1,448 @@
+// A3 / A4 -- gather kernels: instance ROI voxel sampling and the global frustum-to-voxel lift.
+//
+// Both reproduce torch's zero-padded (bi|tri)linear grid_sample (ATen/native/GridSampler.h:27-36
+// `grid_sampler_unnormalize`, GridSampler.cpp corner order and weight products) with explicit
+// round-to-nearest fp32 intrinsics and no FMA contraction, so corner indices and in-bounds masks
+// are bit-identical to oracle/grid_sample.py.  What changes vs the reference's call sequence
+// (vernier.py:332-346: permute+reshape copy, 6 elementwise normalisation kernels, 2 grid_sample,
+// cat) is the data movement: features are re-laid out channels-last once (tiny), every output
+// element is written exactly once, in the layout its consumer reads (NDHWC bf16 for the tcgen05
+// conv3d, or the reference's NCDHW fp32), with 128-bit accesses.
+#include "common.cuh"
+
+namespace snvc {
+namespace {
+
+// ---- shared coordinate arithmetic (bit-exact contract; see oracle/grid_sample.py) ---------
+__device__ __forceinline__ float unnormalize(float g, int size, bool align_corners) {
+  if (align_corners) return __fmul_rn(__fdiv_rn(__fadd_rn(g, 1.f), 2.f), (float)(size - 1));
+  return __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(g, 1.f), (float)size), 1.f), 2.f);
+}
+// vernier.py:335-338:  p / resolution * 2 - 1
+__device__ __forceinline__ float roi_normalize(float p, float res) {
+  return __fsub_rn(__fmul_rn(__fdiv_rn(p, res), 2.f), 1.f);
+}
+
+struct Bilinear {
+  int x0, y0;          // floor corner (nw)
+  float w[4];          // nw, ne, sw, se
+  unsigned mask;       // bit k set <=> corner k inside the feature map
+};
+
+__device__ __forceinline__ Bilinear bilinear_setup(float px, float py, float res_x, float res_y, int Wf, int Hf) {
+  Bilinear b;
+  float ix = unnormalize(roi_normalize(px, res_x), Wf, false);
+  float iy = unnormalize(roi_normalize(py, res_y), Hf, false);
+  float fx0 = floorf(ix), fy0 = floorf(iy);
+  // non-finite coordinates: no corner is in bounds (torch compares the float->int cast; here the
+  // range test on the float itself rejects NaN/inf before the cast)
+  bool finite = (fabsf(ix) < 1e9f) && (fabsf(iy) < 1e9f);
+  b.x0 = finite ? (int)fx0 : -2;
+  b.y0 = finite ? (int)fy0 : -2;
+  float fx1 = __fadd_rn(fx0, 1.f), fy1 = __fadd_rn(fy0, 1.f);
+  float dx1 = __fsub_rn(fx1, ix), dx0 = __fsub_rn(ix, fx0);
+  float dy1 = __fsub_rn(fy1, iy), dy0 = __fsub_rn(iy, fy0);
+  b.w[0] = __fmul_rn(dx1, dy1);
+  b.w[1] = __fmul_rn(dx0, dy1);
+  b.w[2] = __fmul_rn(dx1, dy0);
+  b.w[3] = __fmul_rn(dx0, dy0);
+  bool xin0 = b.x0 >= 0 && b.x0 < Wf, xin1 = b.x0 + 1 >= 0 && b.x0 + 1 < Wf;
+  bool yin0 = b.y0 >= 0 && b.y0 < Hf, yin1 = b.y0 + 1 >= 0 && b.y0 + 1 < Hf;
+  b.mask = (xin0 && yin0 ? 1u : 0u) | (xin1 && yin0 ? 2u : 0u) | (xin0 && yin1 ? 4u : 0u) | (xin1 && yin1 ? 8u : 0u);
+  return b;
+}
+
+// out = (((0 + v_nw*w_nw) + v_ne*w_ne) + v_sw*w_sw) + v_se*w_se, out-of-bounds corners skipped
+__device__ __forceinline__ float acc4(const Bilinear& b, float v0, float v1, float v2, float v3) {
+  float o = 0.f;
+  if (b.mask & 1u) o = __fadd_rn(o, __fmul_rn(v0, b.w[0]));
+  if (b.mask & 2u) o = __fadd_rn(o, __fmul_rn(v1, b.w[1]));
+  if (b.mask & 4u) o = __fadd_rn(o, __fmul_rn(v2, b.w[2]));
+  if (b.mask & 8u) o = __fadd_rn(o, __fmul_rn(v3, b.w[3]));
+  return o;
+}
+
+// NCHW fp32 -> NHWC fp32 (both views at once); tiny: N*C*Hf*Wf elements
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ oa,
+                                    float* __restrict__ ob, int C, int HW, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    // i indexes the NHWC output; read is strided but the whole map is L2 resident
+    int c = (int)(i % C);
+    int64_t t = i / C;
+    int p = (int)(t % HW);
+    int64_t n = t / HW;
+    int64_t src = (n * C + c) * HW + p;
+    oa[i] = a[src];
+    ob[i] = b[src];
+  }
+}
+
+// ---- A3, NDHWC output: 8 channels (16/32 B) per thread, lanes = (point, view, channel group) ----
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+roi_sample_ndhwc_kernel(const float* __restrict__ fl, const float* __restrict__ fr, const float* __restrict__ pl,
+                        const float* __restrict__ pr, OutT* __restrict__ out, int C, int Hf, int Wf, int64_t P,
+                        float res_x, float res_y, int64_t total /* N*P*(2C/8) */) {
+  const int CG = C >> 3;          // 8-channel groups per view
+  const int G = 2 * CG;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int g = (int)(i % G);
+    int64_t np = i / G;
+    int64_t n = np / P;
+    int64_t p = np - n * P;
+    const bool right = g >= CG;
+    const int cg = right ? g - CG : g;
+    const float* pts = (right ? pr : pl) + n * 2 * P;
+    const float* feat = (right ? fr : fl) + n * (int64_t)Hf * Wf * C + cg * 8;
+    Bilinear b = bilinear_setup(__ldg(pts + p), __ldg(pts + P + p), res_x, res_y, Wf, Hf);
+    float v[4][8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (b.mask & (1u << k)) {
+        const float* src = feat + ((int64_t)(b.y0 + (k >> 1)) * Wf + (b.x0 + (k & 1))) * C;
+        *reinterpret_cast<float4*>(v[k]) = __ldg(reinterpret_cast<const float4*>(src));
+        *reinterpret_cast<float4*>(v[k] + 4) = __ldg(reinterpret_cast<const float4*>(src + 4));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[k][j] = 0.f;
+      }
+    }
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = acc4(b, v[0][j], v[1][j], v[2][j], v[3][j]);
+    OutT* o = out + np * (2 * C) + g * 8;
+    if (sizeof(OutT) == 2) {
+      uint4 q = {pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7])};
+      *reinterpret_cast<uint4*>(o) = q;
+    } else {
+      *reinterpret_cast<float4*>(o) = make_float4(r[0], r[1], r[2], r[3]);
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(o) + 4) = make_float4(r[4], r[5], r[6], r[7]);
+    }
+  }
+}
+
+// ---- A3, NCDHW fp32 output (the reference's layout): one thread per (point, view); channel loop;
+//      stores are coalesced across the warp's consecutive points. -------------------------------
+__global__ void __launch_bounds__(256)
+roi_sample_ncdhw_kernel(const float* __restrict__ fl, const float* __restrict__ fr, const float* __restrict__ pl,
+                        const float* __restrict__ pr, float* __restrict__ out, int C, int Hf, int Wf, int64_t P,
+                        float res_x, float res_y) {
+  const int64_t n = blockIdx.z;
+  const bool right = blockIdx.y == 1;
+  const float* pts = (right ? pr : pl) + n * 2 * P;
+  const float* feat = (right ? fr : fl) + n * (int64_t)Hf * Wf * C;
+  float* o = out + (n * 2 * C + (right ? C : 0)) * P;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
+    Bilinear b = bilinear_setup(__ldg(pts + p), __ldg(pts + P + p), res_x, res_y, Wf, Hf);
+    const float* src[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      src[k] = feat + ((int64_t)(b.y0 + (k >> 1)) * Wf + (b.x0 + (k & 1))) * C;
+    for (int c = 0; c < C; c += 4) {
+      float4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        v[k] = (b.mask & (1u << k)) ? __ldg(reinterpret_cast<const float4*>(src[k] + c)) : make_float4(0, 0, 0, 0);
+      __stcs(o + (int64_t)(c + 0) * P + p, acc4(b, v[0].x, v[1].x, v[2].x, v[3].x));
+      __stcs(o + (int64_t)(c + 1) * P + p, acc4(b, v[0].y, v[1].y, v[2].y, v[3].y));
+      __stcs(o + (int64_t)(c + 2) * P + p, acc4(b, v[0].z, v[1].z, v[2].z, v[3].z));
+      __stcs(o + (int64_t)(c + 3) * P + p, acc4(b, v[0].w, v[1].w, v[2].w, v[3].w));
+    }
+  }
+}
+
+__global__ void roi_indices_kernel(const float* __restrict__ pts, int32_t* __restrict__ idx, uint8_t* __restrict__ mask,
+                                   int64_t N, int64_t P, int Hf, int Wf, float res_x, float res_y) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N * P; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t n = i / P, p = i - n * P;
+    Bilinear b = bilinear_setup(pts[n * 2 * P + p], pts[n * 2 * P + P + p], res_x, res_y, Wf, Hf);
+    idx[2 * i] = b.x0;
+    idx[2 * i + 1] = b.y0;
+    mask[i] = (uint8_t)b.mask;
+  }
+}
+
+// ---- A4: frustum-to-voxel lift --------------------------------------------------------------
+struct LiftGeom {
+  float cv[6];   // CV_X_MIN, CV_X_MAX, CV_Y_MIN, CV_Y_MAX, CV_Z_MIN, CV_Z_MAX
+  int D, H, W;   // volume extent (z-bins, rows, cols)
+  int Z, Y, X;   // voxel grid extent
+  int align_corners;
+};
+
+struct Trilinear {
+  int x0, y0, z0;
+  float wx[2], wy[2], wz[2];   // weight of the low / high corner per axis
+  bool valid;                  // all three normalised coordinates inside [-1, 1]
+};
+
+// oracle/global_branch.py `lift_grid`: 4-term dots left to right, then divide, normalise
+__device__ __forceinline__ Trilinear trilinear_setup(const float* __restrict__ Pm, float x, float y, float z,
+                                                     const LiftGeom& g) {
+  auto row = [&](int r) {
+    float a = __fmul_rn(Pm[4 * r + 0], x);
+    a = __fadd_rn(a, __fmul_rn(Pm[4 * r + 1], y));
+    a = __fadd_rn(a, __fmul_rn(Pm[4 * r + 2], z));
+    return __fadd_rn(a, Pm[4 * r + 3]);
+  };
+  float uh = row(0), vh = row(1), wh = row(2);
+  float u = __fdiv_rn(uh, wh), v = __fdiv_rn(vh, wh);
+  auto norm = [](float c, float lo, float hi) {
+    return __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(c, lo), __fsub_rn(hi, lo)), 2.f), 1.f);
+  };
+  float gx = norm(u, g.cv[0], g.cv[1]), gy = norm(v, g.cv[2], g.cv[3]), gz = norm(z, g.cv[4], g.cv[5]);
+  Trilinear t;
+  t.valid = (gx >= -1.f && gx <= 1.f && gy >= -1.f && gy <= 1.f && gz >= -1.f && gz <= 1.f);
+  if (!(fabsf(gx) < 1e9f) || !(fabsf(gy) < 1e9f) || !(fabsf(gz) < 1e9f)) { gx = gy = gz = -2.f; }  // oracle: non-finite -> -2
+  float ix = unnormalize(gx, g.W, g.align_corners);
+  float iy = unnormalize(gy, g.H, g.align_corners);
+  float iz = unnormalize(gz, g.D, g.align_corners);
+  float fx0 = floorf(ix), fy0 = floorf(iy), fz0 = floorf(iz);
+  t.x0 = (int)fx0; t.y0 = (int)fy0; t.z0 = (int)fz0;
+  t.wx[0] = __fsub_rn(__fadd_rn(fx0, 1.f), ix); t.wx[1] = __fsub_rn(ix, fx0);
+  t.wy[0] = __fsub_rn(__fadd_rn(fy0, 1.f), iy); t.wy[1] = __fsub_rn(iy, fy0);
+  t.wz[0] = __fsub_rn(__fadd_rn(fz0, 1.f), iz); t.wz[1] = __fsub_rn(iz, fz0);
+  return t;
+}
+
+// NDHWC bf16 volume; lanes = (voxel, 8-channel group).  Output NDHWC (bf16|f32) or NCDHW f32.
+template <typename OutT, bool OUT_NDHWC>
+__global__ void __launch_bounds__(256)
+lift_ndhwc_kernel(const __nv_bfloat16* __restrict__ vol, const float* __restrict__ proj, const float* __restrict__ zs,
+                  const float* __restrict__ ys, const float* __restrict__ xs, OutT* __restrict__ out,
+                  uint8_t* __restrict__ valid, int C, LiftGeom g, int64_t total /* N*Z*Y*X*(C/8) */) {
+  const int CG = C >> 3;
+  const int64_t ZYX = (int64_t)g.Z * g.Y * g.X;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int cg = (int)(i % CG);
+    int64_t nv = i / CG;
+    int64_t n = nv / ZYX;
+    int64_t vox = nv - n * ZYX;
+    int xi = (int)(vox % g.X);
+    int yi = (int)((vox / g.X) % g.Y);
+    int zi = (int)(vox / ((int64_t)g.X * g.Y));
+    Trilinear t = trilinear_setup(proj + n * 12, __ldg(xs + xi), __ldg(ys + yi), __ldg(zs + zi), g);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (t.valid) {
+      const __nv_bfloat16* base = vol + n * (int64_t)g.D * g.H * g.W * C + cg * 8;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {   // tnw,tne,tsw,tse,bnw,bne,bsw,bse
+        int xx = t.x0 + (k & 1), yy = t.y0 + ((k >> 1) & 1), zz = t.z0 + (k >> 2);
+        if (xx >= 0 && xx < g.W && yy >= 0 && yy < g.H && zz >= 0 && zz < g.D) {
+          float ww = __fmul_rn(__fmul_rn(t.wx[k & 1], t.wy[(k >> 1) & 1]), t.wz[k >> 2]);
+          uint4 q = __ldg(reinterpret_cast<const uint4*>(base + (((int64_t)zz * g.H + yy) * g.W + xx) * C));
+          acc[0] = __fadd_rn(acc[0], __fmul_rn(bf16_lo(q.x), ww));
+          acc[1] = __fadd_rn(acc[1], __fmul_rn(bf16_hi(q.x), ww));
+          acc[2] = __fadd_rn(acc[2], __fmul_rn(bf16_lo(q.y), ww));
+          acc[3] = __fadd_rn(acc[3], __fmul_rn(bf16_hi(q.y), ww));
+          acc[4] = __fadd_rn(acc[4], __fmul_rn(bf16_lo(q.z), ww));
+          acc[5] = __fadd_rn(acc[5], __fmul_rn(bf16_hi(q.z), ww));
+          acc[6] = __fadd_rn(acc[6], __fmul_rn(bf16_lo(q.w), ww));
+          acc[7] = __fadd_rn(acc[7], __fmul_rn(bf16_hi(q.w), ww));
+        }
+      }
+    }
+    if (valid && cg == 0) valid[nv] = t.valid ? 1 : 0;
+    if (OUT_NDHWC) {
+      OutT* o = out + nv * C + cg * 8;
+      if (sizeof(OutT) == 2) {
+        uint4 q = {pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                   pack_bf16x2(acc[6], acc[7])};
+        st_cs_v4(o, q);
+      } else {
+        st_cs_f4(reinterpret_cast<float*>(o), make_float4(acc[0], acc[1], acc[2], acc[3]));
+        st_cs_f4(reinterpret_cast<float*>(o) + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
+      }
+    } else {
+      float* o = reinterpret_cast<float*>(out) + (n * C + cg * 8) * ZYX + vox;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) __stcs(o + j * ZYX, acc[j]);
+    }
+  }
+}
+
+// NCDHW fp32 volume (the reference's layout) -> NCDHW fp32; one thread per voxel, channel loop.
+__global__ void __launch_bounds__(256)
+lift_ncdhw_kernel(const float* __restrict__ vol, const float* __restrict__ proj, const float* __restrict__ zs,
+                  const float* __restrict__ ys, const float* __restrict__ xs, float* __restrict__ out,
+                  uint8_t* __restrict__ valid, int C, LiftGeom g, int64_t total /* N*Z*Y*X */) {
+  const int64_t ZYX = (int64_t)g.Z * g.Y * g.X;
+  const int64_t DHW = (int64_t)g.D * g.H * g.W;
+  for (int64_t nv = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; nv < total; nv += (int64_t)gridDim.x * blockDim.x) {
+    int64_t n = nv / ZYX;
+    int64_t vox = nv - n * ZYX;
+    int xi = (int)(vox % g.X);
+    int yi = (int)((vox / g.X) % g.Y);
+    int zi = (int)(vox / ((int64_t)g.X * g.Y));
+    Trilinear t = trilinear_setup(proj + n * 12, __ldg(xs + xi), __ldg(ys + yi), __ldg(zs + zi), g);
+    int64_t off[8];
+    float ww[8];
+    unsigned m = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      int xx = t.x0 + (k & 1), yy = t.y0 + ((k >> 1) & 1), zz = t.z0 + (k >> 2);
+      bool in = t.valid && xx >= 0 && xx < g.W && yy >= 0 && yy < g.H && zz >= 0 && zz < g.D;
+      m |= in ? (1u << k) : 0u;
+      off[k] = in ? ((int64_t)zz * g.H + yy) * g.W + xx : 0;
+      ww[k] = __fmul_rn(__fmul_rn(t.wx[k & 1], t.wy[(k >> 1) & 1]), t.wz[k >> 2]);
+    }
+    if (valid) valid[nv] = t.valid ? 1 : 0;
+    const float* vb = vol + n * C * DHW;
+    float* o = out + n * C * ZYX + vox;
+    for (int c = 0; c < C; ++c) {
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (m & (1u << k)) a = __fadd_rn(a, __fmul_rn(__ldg(vb + c * DHW + off[k]), ww[k]));
+      __stcs(o + c * ZYX, a);
+    }
+  }
+}
+
+__global__ void lift_indices_kernel(const float* __restrict__ proj, const float* __restrict__ zs,
+                                    const float* __restrict__ ys, const float* __restrict__ xs, int32_t* __restrict__ idx,
+                                    uint8_t* __restrict__ valid, LiftGeom g, int64_t total) {
+  const int64_t ZYX = (int64_t)g.Z * g.Y * g.X;
+  for (int64_t nv = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; nv < total; nv += (int64_t)gridDim.x * blockDim.x) {
+    int64_t n = nv / ZYX;
+    int64_t vox = nv - n * ZYX;
+    int xi = (int)(vox % g.X);
+    int yi = (int)((vox / g.X) % g.Y);
+    int zi = (int)(vox / ((int64_t)g.X * g.Y));
+    Trilinear t = trilinear_setup(proj + n * 12, xs[xi], ys[yi], zs[zi], g);
+    idx[3 * nv] = t.x0;
+    idx[3 * nv + 1] = t.y0;
+    idx[3 * nv + 2] = t.z0;
+    valid[nv] = t.valid ? 1 : 0;
+  }
+}
+
+int grid_for(int64_t total, int per_sm = 8) {
+  return (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total, 256), (int64_t)sm_count() * per_sm));
+}
+
+}  // namespace
+}  // namespace snvc
+
+using namespace snvc;
+
+extern "C" int64_t snvc_roi_voxel_sample_workspace_bytes(int64_t N, int64_t C, int64_t Hf, int64_t Wf) {
+  return 2 * N * C * Hf * Wf * 4;
+}
+
+extern "C" int snvc_roi_voxel_sample_fwd(const float* feat_l, const float* feat_r, const float* pts_l,
+                                         const float* pts_r, void* out, void* workspace, int64_t N, int64_t C,
+                                         int64_t Hf, int64_t Wf, int64_t P, float res_x, float res_y,
+                                         int32_t out_dtype, int32_t out_layout, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SNVC_CHECK_ARG(N >= 0 && C > 0 && Hf > 0 && Wf > 0 && P >= 0, "bad dimensions");
+  if (N * P == 0) return 0;
+  SNVC_CHECK_ARG(feat_l && feat_r && pts_l && pts_r && out && workspace, "null pointer");
+  SNVC_CHECK_ARG(C % 4 == 0, "C must be a multiple of 4 (got %lld)", (long long)C);
+  SNVC_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                 "out / workspace must be 16-byte aligned");
+  float* wl = (float*)workspace;
+  float* wr = wl + N * C * Hf * Wf;
+  const int64_t nfeat = N * C * Hf * Wf;
+  nchw_to_nhwc_kernel<<<grid_for(nfeat), 256, 0, stream>>>(feat_l, feat_r, wl, wr, (int)C, (int)(Hf * Wf), nfeat);
+  if (int e = launch_status("nchw_to_nhwc_kernel")) return e;
+  if (out_layout == SNVC_NDHWC) {
+    SNVC_CHECK_ARG(C % 8 == 0, "NDHWC output needs C %% 8 == 0");
+    const int64_t total = N * P * (2 * C / 8);
+    if (out_dtype == SNVC_BF16)
+      roi_sample_ndhwc_kernel<__nv_bfloat16><<<grid_for(total, 16), 256, 0, stream>>>(
+          wl, wr, pts_l, pts_r, (__nv_bfloat16*)out, (int)C, (int)Hf, (int)Wf, P, res_x, res_y, total);
+    else if (out_dtype == SNVC_F32)
+      roi_sample_ndhwc_kernel<float><<<grid_for(total, 16), 256, 0, stream>>>(wl, wr, pts_l, pts_r, (float*)out, (int)C,
+                                                                              (int)Hf, (int)Wf, P, res_x, res_y, total);
+    else
+      return fail(SNVC_E_UNSUPPORTED, "roi sample: out_dtype must be bf16 or f32");
+    return launch_status("roi_sample_ndhwc_kernel");
+  }
+  if (out_layout == SNVC_NCDHW) {
+    if (out_dtype != SNVC_F32) return fail(SNVC_E_UNSUPPORTED, "roi sample NCDHW: out_dtype must be f32");
+    SNVC_CHECK_ARG(N <= 65535, "N too large");
+    dim3 grid((unsigned)std::min<int64_t>(ceil_div(P, 256), 4096), 2, (unsigned)N);
+    roi_sample_ncdhw_kernel<<<grid, 256, 0, stream>>>(wl, wr, pts_l, pts_r, (float*)out, (int)C, (int)Hf, (int)Wf, P,
+                                                      res_x, res_y);
+    return launch_status("roi_sample_ncdhw_kernel");
+  }
+  return fail(SNVC_E_BADARG, "unknown out_layout %d", out_layout);
+}
+
+extern "C" int snvc_roi_voxel_sample_indices(const float* pts, int32_t* idx, uint8_t* mask, int64_t N, int64_t P,
+                                             int64_t Hf, int64_t Wf, float res_x, float res_y, void* stream_) {
+  if (N * P == 0) return 0;
+  SNVC_CHECK_ARG(pts && idx && mask, "null pointer");
+  roi_indices_kernel<<<grid_for(N * P), 256, 0, (cudaStream_t)stream_>>>(pts, idx, mask, N, P, (int)Hf, (int)Wf, res_x,
+                                                                        res_y);
+  return launch_status("roi_indices_kernel");
+}
+
+static int make_geom(LiftGeom& g, const float* cv, int64_t D, int64_t H, int64_t W, int64_t Z, int64_t Y, int64_t X,
+                     int ac) {
+  SNVC_CHECK_ARG(cv != nullptr, "cv_range_host is null");
+  SNVC_CHECK_ARG(D > 0 && H > 0 && W > 0 && Z > 0 && Y > 0 && X > 0, "bad dimensions");
+  SNVC_CHECK_ARG(D < (1 << 20) && H < (1 << 20) && W < (1 << 20) && Z < (1 << 20) && Y < (1 << 20) && X < (1 << 20),
+                 "dimension too large");
+  for (int i = 0; i < 6; ++i) g.cv[i] = cv[i];
+  g.D = (int)D; g.H = (int)H; g.W = (int)W; g.Z = (int)Z; g.Y = (int)Y; g.X = (int)X;
+  g.align_corners = ac ? 1 : 0;
+  return 0;
+}
+
+extern "C" int snvc_frustum_lift_fwd(const void* vol, const float* proj, const float* zs, const float* ys,
+                                     const float* xs, const float* cv_range_host, void* out, uint8_t* valid, int64_t N,
+                                     int64_t C, int64_t D, int64_t H, int64_t W, int64_t Z, int64_t Y, int64_t X,
+                                     int32_t align_corners, int32_t in_dtype, int32_t in_layout, int32_t out_dtype,
+                                     int32_t out_layout, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (N == 0) return 0;
+  LiftGeom g;
+  if (int e = make_geom(g, cv_range_host, D, H, W, Z, Y, X, align_corners)) return e;
+  SNVC_CHECK_ARG(vol && proj && zs && ys && xs && out, "null pointer");
+  SNVC_CHECK_ARG(N > 0 && C > 0, "bad N / C");
+  const int64_t nvox = N * Z * Y * X;
+  if (in_layout == SNVC_NDHWC && in_dtype == SNVC_BF16) {
+    SNVC_CHECK_ARG(C % 8 == 0, "NDHWC lift needs C %% 8 == 0");
+    SNVC_CHECK_ARG((reinterpret_cast<uintptr_t>(vol) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                   "vol / out must be 16-byte aligned");
+    const int64_t total = nvox * (C / 8);
+    const int blocks = grid_for(total, 16);
+    if (out_layout == SNVC_NDHWC && out_dtype == SNVC_BF16)
+      lift_ndhwc_kernel<__nv_bfloat16, true><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)vol, proj, zs, ys, xs,
+                                                                         (__nv_bfloat16*)out, valid, (int)C, g, total);
+    else if (out_layout == SNVC_NDHWC && out_dtype == SNVC_F32)
+      lift_ndhwc_kernel<float, true><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)vol, proj, zs, ys, xs,
+                                                                 (float*)out, valid, (int)C, g, total);
+    else if (out_layout == SNVC_NCDHW && out_dtype == SNVC_F32)
+      lift_ndhwc_kernel<float, false><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)vol, proj, zs, ys, xs,
+                                                                  (float*)out, valid, (int)C, g, total);
+    else
+      return fail(SNVC_E_UNSUPPORTED, "lift: unsupported output type/layout for an NDHWC bf16 volume");
+    return launch_status("lift_ndhwc_kernel");
+  }
+  if (in_layout == SNVC_NCDHW && in_dtype == SNVC_F32) {
+    if (!(out_layout == SNVC_NCDHW && out_dtype == SNVC_F32))
+      return fail(SNVC_E_UNSUPPORTED, "lift: an NCDHW f32 volume lifts to NCDHW f32 only");
+    lift_ncdhw_kernel<<<grid_for(nvox, 16), 256, 0, stream>>>((const float*)vol, proj, zs, ys, xs, (float*)out, valid,
+                                                              (int)C, g, nvox);
+    return launch_status("lift_ncdhw_kernel");
+  }
+  return fail(SNVC_E_UNSUPPORTED, "lift: supported inputs are NDHWC bf16 and NCDHW f32");
+}
+
+extern "C" int snvc_frustum_lift_indices(const float* proj, const float* zs, const float* ys, const float* xs,
+                                         const float* cv_range_host, int32_t* idx, uint8_t* valid, int64_t N, int64_t D,
+                                         int64_t H, int64_t W, int64_t Z, int64_t Y, int64_t X, int32_t align_corners,
+                                         void* stream_) {
+  if (N == 0) return 0;
+  LiftGeom g;
+  if (int e = make_geom(g, cv_range_host, D, H, W, Z, Y, X, align_corners)) return e;
+  SNVC_CHECK_ARG(proj && zs && ys && xs && idx && valid, "null pointer");
+  const int64_t nvox = N * Z * Y * X;
+  lift_indices_kernel<<<grid_for(nvox), 256, 0, (cudaStream_t)stream_>>>(proj, zs, ys, xs, idx, valid, g, nvox);
+  return launch_status("lift_indices_kernel");
+}

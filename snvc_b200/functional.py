@@ -1,0 +1,144 @@
+"""Functional wrappers (torch tensors in/out) over the C ABI for the gather / layout kernels.
+
+Every function allocates its outputs with torch (the library never allocates), launches on
+torch's current stream of the tensors' device and raises RuntimeError on any failure."""
+import ctypes
+
+import numpy as np
+import torch
+
+from snvc_b200 import _lib
+
+_TORCH_DT = {_lib.F32: torch.float32, _lib.BF16: torch.bfloat16, _lib.F64: torch.float64}
+
+
+def _dt(t):
+    return {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16, torch.float64: _lib.F64}[t]
+
+
+# ------------------------------------------------------------------------------------ A3
+def roi_voxel_sample(left, right, l_pts, r_pts, resolution, out_dtype=torch.float32, layout="NCDHW"):
+    """VernierScale._sample_2d_feat(aggregate='concat') in one pass (vernier.py:323-349).
+
+    left, right [N,F,Hf,Wf] fp32; l_pts, r_pts [N,2,P] fp32 pixel coords; resolution = cfg.resolution.
+    Returns [N, 2F, P] (layout 'NCDHW', fp32) or [N, P, 2F] (layout 'NDHWC', bf16/fp32); the
+    caller reshapes P -> (nh, nw, nl).  The inputs are not modified."""
+    _lib.require_cuda(left, right, l_pts, r_pts)
+    left, right = left.contiguous().float(), right.contiguous().float()
+    l_pts, r_pts = l_pts.contiguous().float(), r_pts.contiguous().float()
+    N, C, Hf, Wf = left.shape
+    if right.shape != left.shape or l_pts.shape != r_pts.shape or l_pts.dim() != 3 or l_pts.size(1) != 2 \
+            or l_pts.size(0) != N:
+        raise RuntimeError("roi_voxel_sample: shape mismatch")
+    P = l_pts.size(2)
+    lay = _lib.NCDHW if layout == "NCDHW" else _lib.NDHWC
+    shape = (N, 2 * C, P) if lay == _lib.NCDHW else (N, P, 2 * C)
+    out = torch.empty(shape, dtype=out_dtype, device=left.device)
+    L = _lib.lib()
+    ws = torch.empty(max(16, L.snvc_roi_voxel_sample_workspace_bytes(N, C, Hf, Wf)), dtype=torch.uint8,
+                     device=left.device)
+    with torch.cuda.device(left.device):
+        st = L.snvc_roi_voxel_sample_fwd(left.data_ptr(), right.data_ptr(), l_pts.data_ptr(), r_pts.data_ptr(),
+                                         out.data_ptr(), ws.data_ptr(), N, C, Hf, Wf, P, float(resolution[1]),
+                                         float(resolution[0]), _dt(out_dtype), lay, _lib.stream_ptr())
+    _lib.check(st, "snvc_roi_voxel_sample_fwd")
+    return out
+
+
+def roi_voxel_sample_indices(pts, Hf, Wf, resolution):
+    """Debug: (idx [N,P,2] int32 (x_nw,y_nw), mask [N,P] uint8) from the kernel's own device code."""
+    _lib.require_cuda(pts)
+    pts = pts.contiguous().float()
+    N, _, P = pts.shape
+    idx = torch.empty((N, P, 2), dtype=torch.int32, device=pts.device)
+    mask = torch.empty((N, P), dtype=torch.uint8, device=pts.device)
+    with torch.cuda.device(pts.device):
+        st = _lib.lib().snvc_roi_voxel_sample_indices(pts.data_ptr(), idx.data_ptr(), mask.data_ptr(), N, P, Hf, Wf,
+                                                      float(resolution[1]), float(resolution[0]), _lib.stream_ptr())
+    _lib.check(st, "snvc_roi_voxel_sample_indices")
+    return idx, mask
+
+
+# ------------------------------------------------------------------------------------ A4
+def _cv(cv_range):
+    arr = (ctypes.c_float * 6)(*[float(v) for v in cv_range])
+    return arr
+
+
+def frustum_lift(vol, proj, zs, ys, xs, cv_range, align_corners=True, layout_in="NCDHW", out_dtype=None,
+                 layout_out=None, return_valid=False):
+    """Trilinear frustum -> world-voxel lift with the sampling grid computed in-kernel.
+
+    vol: [N,C,D,H,W] fp32 (layout_in 'NCDHW') or [N,D,H,W,C] bf16 ('NDHWC'); proj [N,3,4] fp32;
+    zs/ys/xs voxel-centre vectors; cv_range = (CV_X_MIN, CV_X_MAX, CV_Y_MIN, CV_Y_MAX, CV_Z_MIN, CV_Z_MAX).
+    Returns [N,C,Z,Y,X] ('NCDHW') or [N,Z,Y,X,C] ('NDHWC')."""
+    _lib.require_cuda(vol, proj, zs, ys, xs)
+    vol = vol.contiguous()
+    proj, zs, ys, xs = (t.contiguous().float() for t in (proj, zs, ys, xs))
+    lin = _lib.NCDHW if layout_in == "NCDHW" else _lib.NDHWC
+    layout_out = layout_out or layout_in
+    lout = _lib.NCDHW if layout_out == "NCDHW" else _lib.NDHWC
+    if lin == _lib.NCDHW:
+        N, C, D, H, W = vol.shape
+    else:
+        N, D, H, W, C = vol.shape
+    out_dtype = out_dtype or (torch.float32 if lout == _lib.NCDHW else vol.dtype)
+    Z, Y, X = zs.numel(), ys.numel(), xs.numel()
+    shape = (N, C, Z, Y, X) if lout == _lib.NCDHW else (N, Z, Y, X, C)
+    out = torch.empty(shape, dtype=out_dtype, device=vol.device)
+    valid = torch.empty((N, Z, Y, X), dtype=torch.uint8, device=vol.device) if return_valid else None
+    with torch.cuda.device(vol.device):
+        st = _lib.lib().snvc_frustum_lift_fwd(vol.data_ptr(), proj.data_ptr(), zs.data_ptr(), ys.data_ptr(),
+                                              xs.data_ptr(), _cv(cv_range), out.data_ptr(),
+                                              valid.data_ptr() if valid is not None else None, N, C, D, H, W, Z, Y, X,
+                                              int(bool(align_corners)), _dt(vol.dtype), lin, _dt(out_dtype), lout,
+                                              _lib.stream_ptr())
+    _lib.check(st, "snvc_frustum_lift_fwd")
+    return (out, valid) if return_valid else out
+
+
+def frustum_lift_indices(proj, zs, ys, xs, cv_range, vol_dhw, align_corners=True):
+    """Debug: (idx [N,Z,Y,X,3] int32 floor corners (x0,y0,z0), valid [N,Z,Y,X] uint8)."""
+    _lib.require_cuda(proj, zs, ys, xs)
+    proj, zs, ys, xs = (t.contiguous().float() for t in (proj, zs, ys, xs))
+    N = proj.size(0)
+    D, H, W = vol_dhw
+    Z, Y, X = zs.numel(), ys.numel(), xs.numel()
+    idx = torch.empty((N, Z, Y, X, 3), dtype=torch.int32, device=proj.device)
+    valid = torch.empty((N, Z, Y, X), dtype=torch.uint8, device=proj.device)
+    with torch.cuda.device(proj.device):
+        st = _lib.lib().snvc_frustum_lift_indices(proj.data_ptr(), zs.data_ptr(), ys.data_ptr(), xs.data_ptr(),
+                                                  _cv(cv_range), idx.data_ptr(), valid.data_ptr(), N, D, H, W, Z, Y, X,
+                                                  int(bool(align_corners)), _lib.stream_ptr())
+    _lib.check(st, "snvc_frustum_lift_indices")
+    return idx, valid
+
+
+# ------------------------------------------------------------------------------------ layouts
+def to_ndhwc_bf16(x):
+    """[N,C,D,H,W] fp32 -> [N,D,H,W,C] bf16."""
+    _lib.require_cuda(x)
+    x = x.contiguous().float()
+    N, C = x.shape[:2]
+    sp = tuple(x.shape[2:])
+    S = int(np.prod(sp))
+    out = torch.empty((N,) + sp + (C,), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        st = _lib.lib().snvc_ncdhw_f32_to_ndhwc_bf16(x.data_ptr(), out.data_ptr(), N, C, S, _lib.stream_ptr())
+    _lib.check(st, "snvc_ncdhw_f32_to_ndhwc_bf16")
+    return out
+
+
+def to_ncdhw_f32(x):
+    """[N,D,H,W,C] bf16 -> [N,C,D,H,W] fp32."""
+    _lib.require_cuda(x)
+    x = x.contiguous()
+    assert x.dtype == torch.bfloat16
+    N, C = x.shape[0], x.shape[-1]
+    sp = tuple(x.shape[1:-1])
+    S = int(np.prod(sp))
+    out = torch.empty((N, C) + sp, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        st = _lib.lib().snvc_ndhwc_bf16_to_ncdhw_f32(x.data_ptr(), out.data_ptr(), N, C, S, _lib.stream_ptr())
+    _lib.check(st, "snvc_ndhwc_bf16_to_ncdhw_f32")
+    return out

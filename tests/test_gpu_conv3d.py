@@ -1,0 +1,110 @@
+"""GPU parity: the tcgen05 implicit-GEMM conv3d (C ABI snvc_conv3d_fwd) vs the oracle arithmetic
+(torch CPU fp32 conv3d / conv_transpose3d + eval-BN affine, as in oracle/blocks.py).
+
+Inputs and weights are exactly representable in bf16 (tests/golden/synth.py), so with fp32
+output the only difference is fp32 summation order (tolerance 1e-4 of max|ref|); with bf16 output
+the additional error is one bf16 rounding (<= 2^-8 relative; north_star bar: 1e-2)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as TF
+
+import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _relerr(a, b):
+    return float(np.max(np.abs(a - b)) / max(1e-30, np.max(np.abs(b))))
+
+
+def _case(Cin, Cout, k, stride, pad, dil, transposed, dhw, N=1, relu=False, residual_mode=0, sigmoid=False, seed=0):
+    from snvc_b200 import functional as F
+    from snvc_b200.conv import PackedConv3d
+    D, H, W = dhw
+    x = synth.det_uniform((N, Cin, D, H, W), seed + 1)
+    wshape = (Cin, Cout, k, k, k) if transposed else (Cout, Cin, k, k, k)
+    taps = (k ** 3) / (8.0 if transposed else 1.0)
+    a = float(np.sqrt(3.0 / (Cin * taps)))
+    w = synth.det_uniform(wshape, seed + 2, -a, a)
+    scale = synth.det_uniform((Cout,), seed + 3, 0.6, 1.4, bf16=False)
+    bias = synth.det_uniform((Cout,), seed + 4, -0.2, 0.2, bf16=False)
+    tx, tw = torch.from_numpy(x), torch.from_numpy(w)
+    if transposed:
+        ref = TF.conv_transpose3d(tx, tw, stride=2, padding=1, output_padding=1)
+    else:
+        ref = TF.conv3d(tx, tw, stride=stride, padding=pad, dilation=dil)
+    ref = ref * torch.from_numpy(scale).view(1, -1, 1, 1, 1) + torch.from_numpy(bias).view(1, -1, 1, 1, 1)
+    res = None
+    if residual_mode:
+        res = synth.det_uniform(tuple(ref.shape), seed + 5)
+        if residual_mode == 1:
+            ref = ref + torch.from_numpy(res)
+    if relu:
+        ref = torch.relu(ref)
+    if residual_mode == 2:
+        ref = ref + torch.from_numpy(res)
+    if sigmoid:
+        ref = torch.sigmoid(ref)
+    ref = ref.numpy()
+
+    class _BN:  # folded affine expressed as an eval BatchNorm (weight=scale, bias=bias, mean=0, var=1-eps)
+        eps = 0.0
+        weight = torch.from_numpy(scale).cuda()
+        bias = torch.from_numpy(bias).cuda()
+        running_mean = torch.zeros(Cout, device="cuda")
+        running_var = torch.ones(Cout, device="cuda")
+
+    conv = PackedConv3d(tw.cuda(), _BN, transposed=transposed, stride=stride, pad=pad, dilation=dil)
+    x16 = F.to_ndhwc_bf16(tx.cuda())
+    r16 = F.to_ndhwc_bf16(torch.from_numpy(res).cuda()) if res is not None else None
+    outs = {}
+    for dt in (torch.float32, torch.bfloat16):
+        y = conv(x16, relu=relu, residual=r16, residual_mode=residual_mode, sigmoid=sigmoid, out_dtype=dt)
+        torch.cuda.synchronize()
+        outs[dt] = y.float().permute(0, 4, 1, 2, 3).cpu().numpy()
+    assert outs[torch.float32].shape == ref.shape
+    e32, e16 = _relerr(outs[torch.float32], ref), _relerr(outs[torch.bfloat16], ref)
+    assert e32 <= 1e-4, f"fp32-out rel err {e32}"
+    assert e16 <= 1e-2 and e16 <= 6e-3, f"bf16-out rel err {e16}"
+    return e32, e16
+
+
+def test_conv_tiny_first():
+    """Smallest possible launch: a protocol bug traps here (bounded waits) instead of later."""
+    _case(32, 32, 1, 1, 0, 1, False, (2, 8, 8))
+
+
+@pytest.mark.parametrize("Cin,Cout", [(32, 32), (64, 32), (64, 64), (32, 64), (16, 16)])
+def test_conv_3x3x3_s1(Cin, Cout):
+    _case(Cin, Cout, 3, 1, 1, 1, False, (6, 10, 20), N=2, relu=True)
+
+
+@pytest.mark.parametrize("dhw", [(8, 16, 24), (5, 7, 9), (12, 24, 78)])
+def test_conv_3x3x3_s2(dhw):
+    _case(32, 64, 3, 2, 1, 1, False, dhw, relu=True)
+    _case(64, 64, 3, 2, 1, 1, False, dhw, relu=True)
+
+
+@pytest.mark.parametrize("Cin,Cout,mode", [(64, 64, 1), (64, 32, 1), (64, 64, 0)])
+def test_deconv_k3_s2(Cin, Cout, mode):
+    _case(Cin, Cout, 3, 2, 1, 1, True, (3, 6, 10), N=2, relu=(mode == 1 and Cout == 64), residual_mode=mode)
+
+
+def test_conv_residual_modes_and_sigmoid():
+    _case(32, 32, 3, 1, 1, 1, False, (4, 8, 16), residual_mode=1)                      # dres1.1: bn + x
+    _case(32, 32, 3, 1, 1, 1, False, (4, 8, 16), relu=True, residual_mode=1)           # hourglass conv2 (+postsqu)
+    _case(32, 32, 5, 1, 2, 1, False, (6, 10, 12), relu=True, residual_mode=2)          # vernier conv2: relu(bn) + x
+    _case(32, 1, 3, 1, 1, 1, False, (4, 8, 16), sigmoid=True)                          # fg_cls_head.2 (Cout = 1)
+
+
+def test_conv_instance_kernels():
+    _case(64, 32, 1, 1, 0, 1, False, (4, 8, 16), relu=True)                            # vimg_feat 1^3
+    _case(64, 32, 7, 1, 3, 1, False, (8, 12, 16), relu=True)                           # conv1 7^3
+    _case(32, 32, 5, 1, 4, 2, False, (10, 12, 16), relu=True, residual_mode=2)         # conv3 5^3 dilation 2
+
+
+def test_conv_kitti_level_shapes():
+    """One slab of the global trunk's real W/H (W=312 is not a multiple of the tile)."""
+    _case(64, 32, 3, 1, 1, 1, False, (4, 96, 312), relu=True)
+    _case(32, 32, 3, 1, 1, 1, False, (3, 96, 312), relu=True, residual_mode=1)
