@@ -440,14 +440,8 @@ int launch_conv(const void* x, const void* w_packed, const float* scale, const f
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail((int)r, "cuTensorMapEncodeTiled(w) failed with CUresult %d", (int)r);
   }
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(conv3d_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  });
-  // (the attribute is per device; set it again cheaply when another device is current)
-  cudaFuncSetAttribute(conv3d_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  if (attr_err != cudaSuccess) return fail((int)attr_err, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
+  // opt in to the dynamic shared memory this launch needs (static smem counts against the 227 KB cap)
+  SNVC_CUDA_OK(cudaFuncSetAttribute(conv3d_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = std::min(p.num_tiles, sm_count());
   conv3d_tcgen05_kernel<<<grid, kThreads, smem, stream>>>(map_x, map_w, p);
   return launch_status("conv3d_tcgen05_kernel");

@@ -48,14 +48,11 @@ def _case(Cin, Cout, k, stride, pad, dil, transposed, dhw, N=1, relu=False, resi
         ref = torch.sigmoid(ref)
     ref = ref.numpy()
 
-    class _BN:  # folded affine expressed as an eval BatchNorm (weight=scale, bias=bias, mean=0, var=1-eps)
-        eps = 0.0
-        weight = torch.from_numpy(scale).cuda()
-        bias = torch.from_numpy(bias).cuda()
-        running_mean = torch.zeros(Cout, device="cuda")
-        running_var = torch.ones(Cout, device="cuda")
-
-    conv = PackedConv3d(tw.cuda(), _BN, transposed=transposed, stride=stride, pad=pad, dilation=dil)
+    import types
+    # folded affine expressed as an eval BatchNorm (weight=scale, bias=bias, mean=0, var=1, eps=0)
+    bn = types.SimpleNamespace(eps=0.0, weight=torch.from_numpy(scale).cuda(), bias=torch.from_numpy(bias).cuda(),
+                               running_mean=torch.zeros(Cout, device="cuda"), running_var=torch.ones(Cout, device="cuda"))
+    conv = PackedConv3d(tw.cuda(), bn, transposed=transposed, stride=stride, pad=pad, dilation=dil)
     x16 = F.to_ndhwc_bf16(tx.cuda())
     r16 = F.to_ndhwc_bf16(torch.from_numpy(res).cuda()) if res is not None else None
     outs = {}
