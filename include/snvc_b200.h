@@ -150,7 +150,9 @@ typedef struct snvc_conv3d_desc {
   int32_t out_coffset;       /* first channel written inside that stride */
   int32_t res_cstride;       /* same for the residual tensor; 0 -> Cout */
   int32_t res_coffset;
-  int32_t reserved[4];
+  int32_t in_cstride;        /* channel stride of x's innermost dim (>= Cin); 0 -> Cin */
+  int32_t in_coffset;        /* first channel read inside that stride (multiple of 8) */
+  int32_t reserved[2];
 } snvc_conv3d_desc;
 
 /* w: Conv3d [Cout,Cin,k,k,k] fp32 (transposed=0) or ConvTranspose3d [Cin,Cout,k,k,k] fp32

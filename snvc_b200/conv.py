@@ -50,12 +50,13 @@ class PackedConv3d:
         return N, f(Di), f(Hi), f(Wi)
 
     def __call__(self, x, *, relu=False, residual=None, residual_mode=0, sigmoid=False, out_dtype=torch.bfloat16,
-                 out=None, out_coffset=0, res_coffset=0):
-        """x [N,D,H,W,Cin] bf16 -> y [N,Do,Ho,Wo,Cout] (or the channel slice [out_coffset, +Cout) of `out`)."""
+                 out=None, out_coffset=0, res_coffset=0, in_coffset=0):
+        """x [N,D,H,W,Cin] bf16 -> y [N,Do,Ho,Wo,Cout] (or the channel slice [out_coffset, +Cout) of `out`).
+        `in_coffset` / `res_coffset` select channel slices of wider x / residual buffers."""
         _lib.require_cuda(x)
-        if x.dtype != torch.bfloat16 or not x.is_contiguous() or x.shape[-1] != self.cin:
-            raise RuntimeError(f"conv3d: x must be contiguous NDHWC bf16 with {self.cin} channels, got "
-                               f"{tuple(x.shape)} {x.dtype}")
+        if x.dtype != torch.bfloat16 or not x.is_contiguous() or x.shape[-1] < in_coffset + self.cin:
+            raise RuntimeError(f"conv3d: x must be contiguous NDHWC bf16 with >= {in_coffset + self.cin} channels, "
+                               f"got {tuple(x.shape)} {x.dtype}")
         N, Do, Ho, Wo = self.out_shape(x)
         if out is None:
             out = torch.empty((N, Do, Ho, Wo, self.cout), dtype=out_dtype, device=x.device)
@@ -73,7 +74,8 @@ class PackedConv3d:
                           residual_mode=int(residual_mode if residual is not None else 0), sigmoid=int(sigmoid),
                           out_dtype=_lib.BF16 if out.dtype == torch.bfloat16 else _lib.F32,
                           out_cstride=out.shape[-1], out_coffset=out_coffset,
-                          res_cstride=residual.shape[-1] if residual is not None else 0, res_coffset=res_coffset)
+                          res_cstride=residual.shape[-1] if residual is not None else 0, res_coffset=res_coffset,
+                          in_cstride=x.shape[-1], in_coffset=in_coffset)
         with torch.cuda.device(x.device):
             st = _lib.lib().snvc_conv3d_fwd(x.data_ptr(), self.packed.data_ptr(),
                                             self.scale.data_ptr() if self.scale is not None else None,

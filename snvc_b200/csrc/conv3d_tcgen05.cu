@@ -418,13 +418,15 @@ int launch_conv(const void* x, const void* w_packed, const float* scale, const f
   CUtensorMap map_x, map_w;
   {
     cuuint64_t dims[5] = {(cuuint64_t)p.Cin, (cuuint64_t)d.Wi, (cuuint64_t)d.Hi, (cuuint64_t)d.Di, (cuuint64_t)p.N};
-    cuuint64_t strides[4] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)d.Wi * p.Cin * 2, (cuuint64_t)d.Hi * d.Wi * p.Cin * 2,
-                             (cuuint64_t)d.Di * d.Hi * d.Wi * p.Cin * 2};
+    const cuuint64_t cs = (cuuint64_t)(d.in_cstride ? d.in_cstride : p.Cin) * 2;   // bytes between voxels
+    cuuint64_t strides[4] = {cs, (cuuint64_t)d.Wi * cs, (cuuint64_t)d.Hi * d.Wi * cs,
+                             (cuuint64_t)d.Di * d.Hi * d.Wi * cs};
     const int s = p.in_stride;
     cuuint32_t box[5] = {(cuuint32_t)p.Cin, (cuuint32_t)((p.TW - 1) * s + 1), (cuuint32_t)((p.TH - 1) * s + 1),
                          (cuuint32_t)((p.TD - 1) * s + 1), 1};
     cuuint32_t estr[5] = {1, (cuuint32_t)s, (cuuint32_t)s, (cuuint32_t)s, 1};
-    CUresult r = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box, estr,
+    const void* xbase = static_cast<const char*>(x) + (size_t)d.in_coffset * 2;
+    CUresult r = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(xbase), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_mode(p.swizzle_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail((int)r, "cuTensorMapEncodeTiled(x) failed with CUresult %d", (int)r);
@@ -480,6 +482,8 @@ extern "C" int snvc_conv3d_fwd(const void* x, const void* w_packed, const float*
   SNVC_CHECK_ARG(d.N >= 0 && d.Di > 0 && d.Hi > 0 && d.Wi > 0, "bad input extent");
   SNVC_CHECK_ARG(d.out_dtype == SNVC_BF16 || d.out_dtype == SNVC_F32, "out_dtype must be bf16 or f32");
   SNVC_CHECK_ARG(d.residual_mode == 0 || residual != nullptr, "residual_mode set but residual is null");
+  SNVC_CHECK_ARG(d.in_cstride == 0 || (d.in_cstride % 8 == 0 && d.in_coffset % 8 == 0 && d.in_coffset + d.Cin <= d.in_cstride),
+                 "bad input channel slice (in_cstride %d, in_coffset %d)", d.in_cstride, d.in_coffset);
   SNVC_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0 &&
                      (reinterpret_cast<uintptr_t>(y) & 15) == 0,
                  "x, w_packed and y must be 16-byte aligned");

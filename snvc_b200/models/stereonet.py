@@ -1,0 +1,61 @@
+"""Global branch hot path: plane-sweep cost volume -> 3-D trunk -> frustum-to-voxel lift.
+
+The reference does not ship its global model class (snvc/models/__init__.py:1-2 are commented-out
+imports of `StereoNet` / `NewStereoNet`); per SURVEY.md section 3.4 the composition below is
+restated from the DSGN lineage (README.md:68) out of the blocks the reference does ship:
+  build_cost_volume           snvc/extension/build_cost_volume/__init__.py:26
+  convbn_3d / hourglass       snvc/models/submodule.py:32-50, 85-168
+  projection / voxel centres  snvc/utils/torch_utils.py:36-45, 77-98
+  range key names             snvc/models/loss3d.py:15-20 (CV_*_MIN/MAX, *_MIN/MAX, VOXEL_*_SIZE)
+Wiring: dres0 = 2 x (convbn_3d + ReLU); dres1 = convbn_3d + ReLU + convbn_3d, out = dres1(x) + x;
+out = hourglass(out, None, None)[0] + out; voxels = grid_sample(out, project(voxel centres)) * valid.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from snvc_b200 import functional as SF
+from snvc_b200.extension.build_cost_volume import build_cost_volume_ndhwc_bf16
+from snvc_b200.models.submodule import _cbr, convbn_3d, hourglass
+
+
+def voxel_centres(lo, hi, step):
+    """snvc/utils/torch_utils.py:85-94: arange(MIN, MAX - sign(step)*1e-10, step) + step/2 (float32)."""
+    return torch.arange(lo, hi - np.sign(step) * 1e-10, step=step, dtype=torch.float32) + step / 2.0
+
+
+class GlobalHotPath(nn.Module):
+    """cfg: attribute-style object with the reference's key names (loss3d.py:15-20):
+    X_MIN, X_MAX, Y_MIN, Y_MAX, Z_MIN, Z_MAX, VOXEL_{X,Y,Z}_SIZE, CV_{X,Y,Z}_{MIN,MAX}; optional
+    `GN` (submodule.py:372) and `align_corners` (:375)."""
+
+    def __init__(self, cfg, feat_channels=32, trunk_channels=32):
+        super().__init__()
+        gn = bool(getattr(cfg, "GN", False))
+        cin, ch = 2 * feat_channels, trunk_channels
+        self.dres0 = nn.Sequential(_cbr(cin, ch, 3, 1, 1, gn=gn), _cbr(ch, ch, 3, 1, 1, gn=gn))
+        self.dres1 = nn.Sequential(_cbr(ch, ch, 3, 1, 1, gn=gn), convbn_3d(ch, ch, 3, 1, 1, gn=gn))
+        self.hg = hourglass(ch, gn=gn)
+        self.align_corners = bool(getattr(cfg, "align_corners", True))
+        self.cv_range = tuple(float(getattr(cfg, k)) for k in
+                              ("CV_X_MIN", "CV_X_MAX", "CV_Y_MIN", "CV_Y_MAX", "CV_Z_MIN", "CV_Z_MAX"))
+        self.register_buffer("zs", voxel_centres(cfg.Z_MIN, cfg.Z_MAX, cfg.VOXEL_Z_SIZE), persistent=False)
+        self.register_buffer("ys", voxel_centres(cfg.Y_MIN, cfg.Y_MAX, cfg.VOXEL_Y_SIZE), persistent=False)
+        self.register_buffer("xs", voxel_centres(cfg.X_MIN, cfg.X_MAX, cfg.VOXEL_X_SIZE), persistent=False)
+
+    # ---- stages on channels-last bf16 -----------------------------------------------------
+    def trunk(self, cost):
+        """cost [N,D,H,W,2F] bf16 -> [N,D,H,W,ch] bf16 (7 + 3*... fused conv launches)."""
+        x = self.dres0[1].fused(self.dres0[0].fused(cost))
+        x = self.dres1[1].fused(self.dres1[0].fused(x), residual=x, residual_mode=1)
+        return self.hg.fused(x, out_residual=x)[0]
+
+    def lift(self, vol, proj, out_dtype=torch.float32, layout_out="NCDHW"):
+        return SF.frustum_lift(vol, proj, self.zs, self.ys, self.xs, self.cv_range, self.align_corners,
+                               layout_in="NDHWC", out_dtype=out_dtype, layout_out=layout_out)
+
+    def forward(self, left_feat, right_feat, shift, proj, out_dtype=torch.float32, layout_out="NCDHW"):
+        """left_feat/right_feat [N,F,H,W] fp32, shift [N,D] fp32 (>= 0), proj [N,3,4] fp32
+        -> lifted voxels [N,ch,Z,Y,X] (layout_out 'NCDHW') or [N,Z,Y,X,ch] ('NDHWC')."""
+        cost = build_cost_volume_ndhwc_bf16(left_feat, right_feat, shift, 1)
+        return self.lift(self.trunk(cost), proj, out_dtype, layout_out)

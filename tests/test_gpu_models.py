@@ -1,0 +1,155 @@
+"""GPU parity of the drop-in module layer (snvc_b200.models) against
+  * the golden outputs produced by the reference's own modules (tests/golden/*.npz), and
+  * the CPU oracle (oracle/blocks.py, oracle/global_branch.py) on seeded inputs.
+bf16 tensor-core path: bar = max|a-b| / max|b| <= 1e-2 (BASELINE.json north_star), plus identical
+top-k ordering on the synthetic set."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import synth
+from oracle import blocks as oblocks
+from oracle import cost_volume as ocv
+from oracle import global_branch as ogb
+from oracle import grid_sample as ogs
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-2
+
+
+@pytest.fixture(autouse=True)
+def _no_grad():
+    with torch.no_grad():
+        yield
+
+
+def _relerr(a, b):
+    a, b = np.asarray(a, np.float32), np.asarray(b, np.float32)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float(np.max(np.abs(a - b)) / max(1e-30, np.max(np.abs(b))))
+
+
+@pytest.mark.parametrize("gn", [False, True])
+def test_hourglass_matches_reference_golden(golden, gn):
+    from snvc_b200.models.submodule import hourglass
+    g = golden("hourglass_gn" if gn else "hourglass_bn")
+    m = hourglass(32, gn=gn).eval()
+    m.load_state_dict(synth.det_state_dict(m, 11 + int(gn)), strict=True)     # same keys as the reference
+    m = m.cuda()
+    x = torch.from_numpy(synth.det_uniform((1, 32, 8, 16, 16), 101)).cuda()
+    out, pre, post = m(x, None, None)
+    assert out.dtype == torch.float32 and out.is_contiguous()                # reference-kind tensors back
+    for name, t in (("out", out), ("pre", pre), ("post", post)):
+        assert _relerr(t.cpu().numpy(), g[name]) <= TOL, name
+    out2, pre2, post2 = m(x, torch.from_numpy(g["pre"]).cuda(), torch.from_numpy(g["post"]).cuda())
+    for name, t in (("out2", out2), ("pre2", pre2), ("post2", post2)):
+        assert _relerr(t.cpu().numpy(), g[name]) <= TOL, name
+    # channels-last bf16 in -> channels-last bf16 out, same numbers
+    xcl = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
+    ocl = m(xcl, None, None)[0]
+    assert ocl.dtype == torch.bfloat16 and ocl.is_contiguous(memory_format=torch.channels_last_3d)
+    assert _relerr(ocl.float().cpu().numpy(), g["out"]) <= TOL
+
+
+def test_hg16_matches_reference_golden(golden):
+    from snvc_b200.models.submodule import hourglass_downsample_16
+    g = golden("hg16_bn")
+    m = hourglass_downsample_16(32).eval()
+    m.load_state_dict(synth.det_state_dict(m, 21), strict=True)
+    out = m.cuda()(torch.from_numpy(synth.det_uniform((1, 32, 16, 16, 16), 102)).cuda())
+    assert _relerr(out.cpu().numpy(), g["out"]) <= TOL
+
+
+def test_plan_cache_follows_load_state_dict():
+    from snvc_b200.models.submodule import convbn_3d
+    m = convbn_3d(32, 32, 3, 1, 1).eval().cuda()
+    x = torch.from_numpy(synth.det_uniform((1, 32, 4, 8, 8), 5)).cuda()
+    a = m(x)
+    m.load_state_dict(synth.det_state_dict(m, 77))
+    b = m(x)
+    ref = oblocks.convbn_3d(32, 32, 3, 1, 1).eval()
+    ref.load_state_dict(synth.det_state_dict(ref, 77))
+    assert not torch.equal(a, b)
+    assert _relerr(b.cpu().numpy(), ref(x.cpu()).numpy()) <= TOL
+    m.train()
+    with pytest.raises(RuntimeError):
+        m(x)
+
+
+def _vernier_cfg(grid=(16, 32, 48)):
+    ns = types.SimpleNamespace
+    return ns(vernier_type="BEV_type3", gn=False, hrfeat=ns(output_channel=32), num_parts=9, grid_resolution=list(grid),
+              n_sample_h=grid[0], n_sample_w=grid[1], n_sample_l=grid[2], resolution=[64, 64])
+
+
+def test_vernier_hot_path_matches_reference_golden(golden):
+    from snvc_b200.models.vernier import VernierHotPath
+    g = golden("vernier_bev3")
+    cfg = _vernier_cfg()
+    nh, nw, nl = cfg.grid_resolution
+    P = nh * nw * nl
+    m = VernierHotPath(cfg).eval()
+    m.load_state_dict(synth.det_state_dict(m, 31), strict=True)
+    m = m.cuda()
+    lf, rf = synth.det_uniform((1, 32, 16, 16), 201), synth.det_uniform((1, 32, 16, 16), 202)
+    gl = synth.det_uniform((1, 2, P), 203, -6.4, 70.4, bf16=False)
+    gr = synth.det_uniform((1, 2, P), 204, -6.4, 70.4, bf16=False)
+    bev, occ = m(*[torch.from_numpy(a).cuda() for a in (lf, rf, gl, gr)])
+    assert bev.shape == g["voxel_bev"].shape and occ.shape == g["occupancy"].shape
+    assert _relerr(bev.cpu().numpy(), g["voxel_bev"]) <= TOL
+    assert _relerr(occ.cpu().numpy(), g["occupancy"]) <= TOL
+
+
+def _small_global():
+    geom = ogb.GlobalGeometry(IH=64, IW=192, D=8, depth_min=2.0, depth_max=14.8, X_MIN=-6.0, X_MAX=6.0, Y_MIN=-1.0,
+                              Y_MAX=2.0, Z_MIN=2.0, Z_MAX=14.0, VOXEL_X_SIZE=0.4, VOXEL_Y_SIZE=0.5, VOXEL_Z_SIZE=0.5,
+                              align_corners=True,
+                              P=np.array([[110.0, 0, 96.0, 6.0], [0, 110.0, 30.0, 0.03], [0, 0, 1.0, 0.0003]], np.float32))
+    cv = geom.cv_ranges()
+    cfg = types.SimpleNamespace(X_MIN=geom.X_MIN, X_MAX=geom.X_MAX, Y_MIN=geom.Y_MIN, Y_MAX=geom.Y_MAX, Z_MIN=geom.Z_MIN,
+                                Z_MAX=geom.Z_MAX, VOXEL_X_SIZE=geom.VOXEL_X_SIZE, VOXEL_Y_SIZE=geom.VOXEL_Y_SIZE,
+                                VOXEL_Z_SIZE=geom.VOXEL_Z_SIZE, CV_X_MIN=cv[0], CV_X_MAX=cv[1], CV_Y_MIN=cv[2],
+                                CV_Y_MAX=cv[3], CV_Z_MIN=cv[4], CV_Z_MAX=cv[5], align_corners=True, GN=False)
+    return geom, cfg
+
+
+def test_global_hot_path_vs_oracle_and_topk():
+    """cost volume -> trunk -> lift, end to end, vs the fp32 CPU oracle (a scaled-down configs[0])."""
+    from snvc_b200.models.stereonet import GlobalHotPath
+    geom, cfg = _small_global()
+    N, Fc, H, W = 2, 32, geom.IH // 4, geom.IW // 4
+    lf, rf = synth.det_uniform((N, Fc, H, W), 301), synth.det_uniform((N, Fc, H, W), 302)
+    shift = np.ascontiguousarray(geom.shifts(N))
+    Ps = np.stack([geom.P, geom.P * np.float32([[1.0], [1.02], [1.0]])]).astype(np.float32)
+    # oracle
+    trunk = oblocks.GlobalTrunk(2 * Fc, 32).eval()
+    sd = synth.det_state_dict(trunk, 41)
+    trunk.load_state_dict(sd, strict=True)
+    cost = ocv.forward_c(lf, rf, shift, 1, fma_mode=1)
+    feat = trunk(torch.from_numpy(cost)).numpy()
+    want, _ = ogb.frustum_lift(feat, Ps, geom)
+    # product
+    m = GlobalHotPath(cfg).eval()
+    m.load_state_dict(sd, strict=True)                                       # same key names as the oracle trunk
+    m = m.cuda()
+    got = m(*[torch.from_numpy(a).cuda() for a in (lf, rf, shift, Ps)])
+    assert got.shape == want.shape
+    assert _relerr(got.cpu().numpy(), want) <= TOL
+    # top-k (k=100) BEV cells of a fixed random 1x1 head over the Y-pooled lifted volume
+    head = synth.det_uniform((want.shape[1],), 55, bf16=False)
+    def scores(v):
+        return np.einsum("nczyx,c->nzx", v, head).reshape(v.shape[0], -1) / v.shape[3]
+    s_ref, s_got = scores(want), scores(got.cpu().numpy())
+    for n in range(N):
+        top_ref = np.argsort(-s_ref[n], kind="stable")[:100]
+        top_got = np.argsort(-s_got[n], kind="stable")[:100]
+        assert set(top_ref[:50]) <= set(top_got) and set(top_got[:50]) <= set(top_ref)
+        # identical ordering wherever the reference scores are separated by more than the bf16 noise
+        gaps = np.abs(np.diff(s_ref[n][top_ref]))
+        noise = 2 * np.max(np.abs(s_ref[n] - s_got[n]))
+        k = 0
+        while k < 99 and gaps[k] > noise:
+            k += 1
+        assert np.array_equal(top_ref[:k + 1], top_got[:k + 1])

@@ -8,7 +8,12 @@ import torch
 import synth
 from oracle import blocks, grid_sample as gs
 
-torch.set_grad_enabled(False)
+
+
+@pytest.fixture(autouse=True)
+def _no_grad():
+    with torch.no_grad():
+        yield
 
 
 def _close(a, b, tol=2e-6):
