@@ -23,6 +23,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -131,6 +132,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// One lane of a converged warp.  The producer / MMA warps run their loops warp-wide (uniform
+// control flow -> addresses and descriptors live in uniform registers) and only the issue
+// instructions are predicated on the elected lane; a plain `if (lane == 0)` region makes ptxas
+// wrap every UTCHMMA / UTMALDG in an ELECT + BRA.U.ANY loop (~10 extra issue slots each).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint64_t desc64(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
 
 // K-major, swizzled operand tile: rows of `swizzle_bytes` bytes, 8-row atoms back to back.
 //   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major: 1) | [32,46) SBO>>4 = 8 rows
@@ -203,53 +214,56 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile(p, tile);
-        const int cd = tc.jd * p.in_stride, ch = tc.jh * p.in_stride, cw = tc.jw * p.in_stride;
-        for (int id = 0; id < p.nk[0]; ++id)
-          for (int ih = 0; ih < p.nk[1]; ++ih)
-            for (int iw = 0; iw < p.nk[2]; ++iw) {
-              mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+    // ===================== TMA producer (warp-wide loop, elected lane issues) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p, tile);
+      const int cd = tc.jd * p.in_stride, ch = tc.jh * p.in_stride, cw = tc.jw * p.in_stride;
+      for (int id = 0; id < p.nk[0]; ++id)
+        for (int ih = 0; ih < p.nk[1]; ++ih)
+          for (int iw = 0; iw < p.nk[2]; ++iw) {
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+            if (elect_one()) {
               const uint32_t fb = smem_u32(&full_bar[stage]);
               const uint32_t sa = smem_base + stage * stage_bytes;
               mbar_expect_tx(fb, (uint32_t)stage_bytes);
               tma_load_5d(sa, &map_x, fb, 0, cw + p.off[2][iw], ch + p.off[1][ih], cd + p.off[0][id], tc.n);
               const int slot = (p.kid[0][id] * p.K + p.kid[1][ih]) * p.K + p.kid[2][iw];
               tma_load_2d(sa + p.a_bytes, &map_w, fb, 0, slot * p.CoutPad);
-              if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
-      }
+            __syncwarp();
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(kTileM, p.CoutPad);
-      const int ksteps = p.Cin >> 4;
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        const uint32_t use = (uint32_t)(it >> 1);
-        mbar_wait(smem_u32(&tmem_empty_bar[buf]), (use & 1u) ^ 1u);
+    // ===================== MMA issuer (warp-wide loop, elected lane issues) =====================
+    const uint32_t idesc = make_idesc(kTileM, p.CoutPad);
+    const uint32_t desc_hi = (uint32_t)(make_smem_desc(0, p.swizzle_bytes) >> 32);
+    const int ksteps = p.Cin >> 4;
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      mbar_wait(smem_u32(&tmem_empty_bar[buf]), (use & 1u) ^ 1u);
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.CoutPad);
+      for (int t = 0; t < ntaps; ++t) {
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.CoutPad);
-        for (int t = 0; t < ntaps; ++t) {
-          mbar_wait(smem_u32(&full_bar[stage]), phase);
-          tcgen05_fence_after();
-          const uint32_t sa = smem_base + stage * stage_bytes;
-          const uint64_t adesc = make_smem_desc(sa, p.swizzle_bytes);
-          const uint64_t bdesc = make_smem_desc(sa + p.a_bytes, p.swizzle_bytes);
+        const uint32_t sa = smem_base + stage * stage_bytes;
+        const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | (1u << 16);
+        const uint32_t b_lo = (((sa + p.a_bytes) >> 4) & 0x3FFFu) | (1u << 16);
+        if (elect_one()) {
           for (int k = 0; k < ksteps; ++k)   // +32 B per K=16 step inside the swizzled row: +2 in the >>4 field
-            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (t | k) ? 1u : 0u);
+            umma_bf16(d_tmem, desc64(desc_hi, a_lo + 2 * k), desc64(desc_hi, b_lo + 2 * k), idesc, (t | k) ? 1u : 0u);
           umma_commit(smem_u32(&empty_bar[stage]));          // frees the smem slot once these MMAs retire
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          if (t == ntaps - 1) umma_commit(smem_u32(&tmem_full_bar[buf]));   // accumulator complete -> epilogue
         }
-        umma_commit(smem_u32(&tmem_full_bar[buf]));          // accumulator complete -> epilogue
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else {
@@ -336,6 +350,274 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   }
 
   // teardown: everyone done with TMEM before the allocating warp frees it
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+
+// ==========================================================================================
+// v2: plane-march kernel for stride-1 "same" convolutions (the layers that carry the FLOPs).
+//
+// The per-tap kernel above re-fetches every activation k^3 times through TMA (one 128-row box per
+// tap); the launch list shows it bound by the TMA row rate (~640 cycles per tap), not by bytes.
+// Here a CTA owns a column of the volume -- an (TH x TWv) patch of (h, w), all depth planes --
+// and marches along d:
+//   * each INPUT plane of the patch (+halo) is TMA-loaded ONCE into a ring of smem slots as a
+//     dense [(TH+hw) x WP] array of voxel rows (WP = row pitch 16/32/64, hw = (k-1)*dil);
+//   * because the tile width equals the pitch, output row r = h*WP + w of the 128-row MMA tile
+//     needs input row r + (kh*dil*WP + kw*dil) of plane d+kd*dil: every filter tap is the SAME
+//     smem tile read through a UMMA descriptor whose start address is shifted by whole rows --
+//     no data movement per tap at all.  Columns w >= TWv of each row wrap into the next row and
+//     are discarded by the epilogue (WP-hw of WP columns useful);
+//   * all k^3 weight tiles stay resident in smem for the CTA's lifetime (persistent grid);
+//   * swizzle phase of shifted windows: TMA and UMMA both swizzle on ABSOLUTE smem address bits
+//     (measured: descriptors with base offset 0 and a start address shifted by any number of
+//     rows reproduce the oracle for SWIZZLE_32B/64B/128B; tests/test_gpu_conv3d.py).
+// ==========================================================================================
+struct EpiParams {
+  int Cout, CoutPad;
+  int relu, residual_mode, sigmoid, out_f32;
+  int out_cstride, out_coffset, res_cstride, res_coffset;
+  const __nv_bfloat16* residual;
+  void* y;
+};
+
+// One accumulator row (this thread's TMEM lane) -> global memory.  taddr: lane/column base.
+__device__ __forceinline__ void epilogue_row(const EpiParams& e, uint32_t taddr, bool in_range, int64_t vox,
+                                             const float* s_scale, const float* s_bias) {
+  for (int c0 = 0; c0 < e.CoutPad; c0 += 16) {
+    uint32_t acc[16];
+    tmem_ld16(taddr + (uint32_t)c0, acc);
+    tmem_ld_wait();
+    if (!in_range) continue;
+    float v[16], r[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(acc[j]), s_scale[(c0 + j) & 63], s_bias[(c0 + j) & 63]);
+    const bool full = (c0 + 16 <= e.Cout);
+    if (e.residual_mode) {
+      const __nv_bfloat16* rp = e.residual + vox * e.res_cstride + e.res_coffset + c0;
+      if (full) {
+        uint4 q0 = __ldg(reinterpret_cast<const uint4*>(rp));
+        uint4 q1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
+        r[0] = bf16_lo(q0.x); r[1] = bf16_hi(q0.x); r[2] = bf16_lo(q0.y); r[3] = bf16_hi(q0.y);
+        r[4] = bf16_lo(q0.z); r[5] = bf16_hi(q0.z); r[6] = bf16_lo(q0.w); r[7] = bf16_hi(q0.w);
+        r[8] = bf16_lo(q1.x); r[9] = bf16_hi(q1.x); r[10] = bf16_lo(q1.y); r[11] = bf16_hi(q1.y);
+        r[12] = bf16_lo(q1.z); r[13] = bf16_hi(q1.z); r[14] = bf16_lo(q1.w); r[15] = bf16_hi(q1.w);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = (c0 + j < e.Cout) ? __bfloat162float(rp[j]) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float x = v[j];
+      if (e.residual_mode == 1) x += r[j];
+      if (e.relu) x = fmaxf(x, 0.f);
+      if (e.residual_mode == 2) x += r[j];
+      if (e.sigmoid) x = 1.f / (1.f + __expf(-x));
+      v[j] = x;
+    }
+    if (e.out_f32) {
+      float* o = reinterpret_cast<float*>(e.y) + vox * e.out_cstride + e.out_coffset + c0;
+      if (full && ((e.out_cstride | e.out_coffset) & 3) == 0) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (c0 + j < e.Cout) o[j] = v[j];
+      }
+    } else {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(e.y) + vox * e.out_cstride + e.out_coffset + c0;
+      if (full && ((e.out_cstride | e.out_coffset) & 7) == 0) {
+        uint4 q0 = {pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])};
+        uint4 q1 = {pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15])};
+        *reinterpret_cast<uint4*>(o) = q0;
+        *(reinterpret_cast<uint4*>(o) + 1) = q1;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (c0 + j < e.Cout) o[j] = __float2bfloat16_rn(v[j]);
+      }
+    }
+  }
+}
+
+constexpr int kMaxSlots = 12;
+
+struct HaloParams {
+  int N, Cin;
+  int D, H, W;                 // input == output extent
+  int K, dil, pad;             // pad == dil*(K-1)/2
+  int WP, TH, TWv;             // row pitch, tile rows (WP*TH == 128), valid columns per row = WP - hw
+  int tiles_h, tiles_w, num_cols;
+  int plane_bytes;             // TMA box bytes: (TH+hw)*WP*Cin*2
+  int slot_bytes, nslots;
+  int w_tap_bytes;             // CoutPad*Cin*2
+  int swizzle_bytes, bo_mode;
+  const float* scale;
+  const float* bias;
+  EpiParams epi;
+};
+
+template <int K, int KSTEPS>
+__global__ void __launch_bounds__(kThreads, 1)
+conv3d_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                   const __grid_constant__ HaloParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxSlots];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxSlots];
+  __shared__ __align__(8) uint64_t w_bar;
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ float s_scale[64], s_bias[64];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int K3 = p.K * p.K * p.K;
+  const int hw = (p.K - 1) * p.dil;
+  const uint32_t w_base = (smem_u32(smem) + 1023u) & ~1023u;
+  const uint32_t slots_base = w_base + (((uint32_t)(K3 * p.w_tap_bytes) + 1023u) & ~1023u);
+  const int row_bytes = p.Cin * 2;
+  const uint32_t tmem_cols = p.epi.CoutPad * 2 <= 32 ? 32u : (p.epi.CoutPad * 2 <= 64 ? 64u : 128u);
+  const int planes_per_col = p.D + hw;
+
+  if (threadIdx.x < 64) {
+    s_scale[threadIdx.x] = (p.scale && threadIdx.x < p.epi.Cout) ? p.scale[threadIdx.x] : 1.f;
+    s_bias[threadIdx.x] = (p.bias && threadIdx.x < p.epi.Cout) ? p.bias[threadIdx.x] : 0.f;
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    for (int s = 0; s < p.nslots; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(&w_bar), 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&tmem_full_bar[b]), 1);
+      mbar_init(smem_u32(&tmem_empty_bar[b]), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                 "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer (warp-wide loop, elected lane issues) =====================
+    const uint32_t wb = smem_u32(&w_bar);
+    if (elect_one()) {
+      mbar_expect_tx(wb, (uint32_t)(K3 * p.w_tap_bytes));
+      for (int t = 0; t < K3; ++t) tma_load_2d(w_base + t * p.w_tap_bytes, &map_w, wb, 0, t * p.epi.CoutPad);
+    }
+    __syncwarp();
+    uint32_t q = 0;
+    for (int col = blockIdx.x; col < p.num_cols; col += gridDim.x) {
+      int tw = col % p.tiles_w, rest = col / p.tiles_w;
+      int th = rest % p.tiles_h, n = rest / p.tiles_h;
+      const int w0 = tw * p.TWv - p.pad, h0 = th * p.TH - p.pad;
+      for (int ip = -p.pad; ip < p.D + hw - p.pad; ++ip, ++q) {
+        const uint32_t slot = q % (uint32_t)p.nslots, phase = (q / (uint32_t)p.nslots) & 1u;
+        mbar_wait(smem_u32(&empty_bar[slot]), phase ^ 1u);
+        if (elect_one()) {
+          const uint32_t fb = smem_u32(&full_bar[slot]);
+          mbar_expect_tx(fb, (uint32_t)p.plane_bytes);
+          tma_load_5d(slots_base + slot * p.slot_bytes, &map_x, fb, 0, w0, h0, ip, n);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (warp-wide loop, elected lane issues) =====================
+    const uint32_t idesc = make_idesc(kTileM, p.epi.CoutPad);
+    const uint32_t desc_hi = (uint32_t)(make_smem_desc(0, p.swizzle_bytes) >> 32);
+    const uint32_t lo_flags = 1u << 16;                                   // LBO field (ignored for swizzled K-major)
+    // descriptor offsets, in 16-byte units: filter tap (kh,kw) = whole-row shift of the plane tile
+    uint32_t off_hw[K * K];
+#pragma unroll
+    for (int kh = 0; kh < K; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < K; ++kw) off_hw[kh * K + kw] = (uint32_t)((kh * p.dil * p.WP + kw * p.dil) * row_bytes) >> 4;
+    const uint32_t b_lo0 = ((w_base >> 4) & 0x3FFFu) | lo_flags;
+    const uint32_t b_step = (uint32_t)p.w_tap_bytes >> 4;
+    mbar_wait(smem_u32(&w_bar), 0);
+    uint32_t q0 = 0, it = 0;
+    for (int col = blockIdx.x; col < p.num_cols; col += gridDim.x) {
+      for (int d = 0; d < p.D; ++d, ++it) {
+        for (int pl = (d == 0 ? 0 : hw); pl <= hw; ++pl) {     // planes newly needed by this output plane
+          const uint32_t qq = q0 + d + pl;
+          mbar_wait(smem_u32(&full_bar[qq % (uint32_t)p.nslots]), (qq / (uint32_t)p.nslots) & 1u);
+        }
+        const uint32_t buf = it & 1u;
+        mbar_wait(smem_u32(&tmem_empty_bar[buf]), ((it >> 1) & 1u) ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * (uint32_t)p.epi.CoutPad;
+        uint32_t plane_lo[K];
+#pragma unroll
+        for (int kd = 0; kd < K; ++kd) {
+          const uint32_t qq = q0 + d + kd * p.dil;
+          plane_lo[kd] = (((slots_base + (qq % (uint32_t)p.nslots) * p.slot_bytes) >> 4) & 0x3FFFu) | lo_flags;
+        }
+        if (elect_one()) {
+#pragma unroll
+          for (int kd = 0; kd < K; ++kd)
+#pragma unroll
+            for (int t2 = 0; t2 < K * K; ++t2) {
+              const uint32_t a_lo = plane_lo[kd] + off_hw[t2];
+              const uint32_t b_lo = b_lo0 + (uint32_t)(kd * K * K + t2) * b_step;
+#pragma unroll
+              for (int k = 0; k < KSTEPS; ++k)
+                umma_bf16(d_tmem, desc64(desc_hi, a_lo + 2 * k), desc64(desc_hi, b_lo + 2 * k), idesc,
+                          (kd | t2 | k) ? 1u : 0u);
+            }
+          umma_commit(smem_u32(&tmem_full_bar[buf]));
+          umma_commit(smem_u32(&empty_bar[(q0 + d) % (uint32_t)p.nslots]));   // input plane d is done
+        }
+        __syncwarp();
+      }
+      if (elect_one())
+        for (int pl = 0; pl < hw; ++pl) umma_commit(smem_u32(&empty_bar[(q0 + p.D + pl) % (uint32_t)p.nslots]));
+      __syncwarp();
+      q0 += (uint32_t)planes_per_col;
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int r_w = row % p.WP, r_h = row / p.WP;
+    uint32_t it = 0;
+    for (int col = blockIdx.x; col < p.num_cols; col += gridDim.x) {
+      int tw = col % p.tiles_w, rest = col / p.tiles_w;
+      int th = rest % p.tiles_h, n = rest / p.tiles_h;
+      const int ow = tw * p.TWv + r_w, oh = th * p.TH + r_h;
+      const bool in_range = r_w < p.TWv && ow < p.W && oh < p.H;
+      const int64_t vox0 = (((int64_t)n * p.D) * p.H + oh) * p.W + ow;
+      for (int d = 0; d < p.D; ++d, ++it) {
+        const uint32_t buf = it & 1u;
+        mbar_wait(smem_u32(&tmem_full_bar[buf]), (it >> 1) & 1u);
+        tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * (uint32_t)p.epi.CoutPad;
+        epilogue_row(p.epi, taddr, in_range, vox0 + (int64_t)d * p.H * p.W, s_scale, s_bias);
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[buf]));
+      }
+    }
+  }
+
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -449,6 +731,84 @@ int launch_conv(const void* x, const void* w_packed, const float* scale, const f
   return launch_status("conv3d_tcgen05_kernel");
 }
 
+
+// ---- v2 host side: returns 1 if this conv is not eligible (caller falls back to the per-tap kernel)
+int launch_halo(const void* x, const void* w_packed, const float* scale, const float* bias, const void* residual,
+                void* y, const snvc_conv3d_desc& d, const ConvParams& cp, cudaStream_t stream, int bo_mode) {
+  const int hw = (d.kernel - 1) * d.dilation;
+  if (d.transposed || d.stride != 1 || d.kernel != 3 || 2 * d.pad != hw) return 1;
+  if (d.Do != d.Di || d.Ho != d.Hi || d.Wo != d.Wi) return 1;
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return fail(SNVC_E_DRIVER, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  HaloParams p{};
+  p.N = d.N; p.Cin = d.Cin; p.D = d.Di; p.H = d.Hi; p.W = d.Wi;
+  p.K = d.kernel; p.dil = d.dilation; p.pad = d.pad;
+  p.scale = scale; p.bias = bias;
+  p.epi.Cout = cp.Cout; p.epi.CoutPad = cp.CoutPad; p.epi.relu = cp.relu; p.epi.residual_mode = cp.residual_mode;
+  p.epi.sigmoid = cp.sigmoid; p.epi.out_f32 = cp.out_f32; p.epi.out_cstride = cp.out_cstride;
+  p.epi.out_coffset = cp.out_coffset; p.epi.res_cstride = cp.res_cstride; p.epi.res_coffset = cp.res_coffset;
+  p.epi.residual = (const __nv_bfloat16*)residual; p.epi.y = y;
+  p.swizzle_bytes = d.Cin * 2;
+  p.bo_mode = bo_mode;
+  const int row_bytes = d.Cin * 2;
+  const int K3 = d.kernel * d.kernel * d.kernel;
+  p.w_tap_bytes = cp.CoutPad * d.Cin * 2;
+  const int w_total = round_up(K3 * p.w_tap_bytes, 1024);
+  const int budget = 225 * 1024 - 1024 - w_total;       // dynamic smem left for the plane ring
+  // pick the row pitch: maximise useful MMA rows, subject to the ring fitting (>= hw + 2 slots)
+  double best = -1;
+  for (int wp = 16; wp <= 64; wp <<= 1) {
+    const int twv = wp - hw, th = 128 / wp;
+    if (twv <= 0) continue;
+    const int slot = round_up(((th + hw) * wp + 16) * row_bytes, 1024);
+    if (budget < slot * (hw + 2)) continue;
+    double eff = ((double)d.Wi / (ceil_div(d.Wi, twv) * wp)) * ((double)d.Hi / (ceil_div(d.Hi, th) * th));
+    if (eff > best) { best = eff; p.WP = wp; p.TH = th; p.TWv = twv; p.slot_bytes = slot; }
+  }
+  if (best < 0) return 1;                                // weights + ring do not fit: per-tap kernel
+  p.nslots = std::min(kMaxSlots, budget / p.slot_bytes);
+  p.plane_bytes = (p.TH + hw) * p.WP * row_bytes;
+  p.tiles_h = (int)ceil_div(d.Hi, p.TH); p.tiles_w = (int)ceil_div(d.Wi, p.TWv);
+  const int64_t ncols = (int64_t)d.N * p.tiles_h * p.tiles_w;
+  SNVC_CHECK_ARG(ncols < (1ll << 31), "too many tile columns");
+  p.num_cols = (int)ncols;
+  const size_t smem = (size_t)w_total + (size_t)p.nslots * p.slot_bytes + 1024;
+
+  CUtensorMap map_x, map_w;
+  {
+    const cuuint64_t cs = (cuuint64_t)(d.in_cstride ? d.in_cstride : d.Cin) * 2;
+    cuuint64_t dims[5] = {(cuuint64_t)d.Cin, (cuuint64_t)d.Wi, (cuuint64_t)d.Hi, (cuuint64_t)d.Di, (cuuint64_t)d.N};
+    cuuint64_t strides[4] = {cs, (cuuint64_t)d.Wi * cs, (cuuint64_t)d.Hi * d.Wi * cs, (cuuint64_t)d.Di * d.Hi * d.Wi * cs};
+    cuuint32_t box[5] = {(cuuint32_t)d.Cin, (cuuint32_t)p.WP, (cuuint32_t)(p.TH + hw), 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const void* xbase = static_cast<const char*>(x) + (size_t)d.in_coffset * 2;
+    CUresult r = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(xbase), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_mode(p.swizzle_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail((int)r, "cuTensorMapEncodeTiled(x, halo) failed with CUresult %d", (int)r);
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)d.Cin, (cuuint64_t)K3 * cp.CoutPad};
+    cuuint64_t strides[1] = {(cuuint64_t)d.Cin * 2};
+    cuuint32_t box[2] = {(cuuint32_t)d.Cin, (cuuint32_t)cp.CoutPad};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_packed), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_mode(p.swizzle_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail((int)r, "cuTensorMapEncodeTiled(w, halo) failed with CUresult %d", (int)r);
+  }
+  void (*kern)(const CUtensorMap, const CUtensorMap, const HaloParams) = nullptr;
+  switch (d.Cin) {
+    case 16: kern = conv3d_halo_kernel<3, 1>; break;
+    case 32: kern = conv3d_halo_kernel<3, 2>; break;
+    case 64: kern = conv3d_halo_kernel<3, 4>; break;
+  }
+  SNVC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = std::min(p.num_cols, sm_count());
+  kern<<<grid, kThreads, smem, stream>>>(map_x, map_w, p);
+  return launch_status("conv3d_halo_kernel");
+}
+
 }  // namespace
 }  // namespace snvc
 
@@ -518,6 +878,14 @@ extern "C" int snvc_conv3d_fwd(const void* x, const void* w_packed, const float*
         p.off[a][j] = (signed char)(j * d.dilation - d.pad);
         p.kid[a][j] = (signed char)j;
       }
+    }
+    // SNVC_CONV_MODE=tap forces the per-tap kernel (A/B measurements).  Descriptor base offset stays 0:
+    // measured on B200, UMMA swizzles on absolute smem address bits, so row-shifted windows of a
+    // TMA-written tile need no base-offset correction (base offset = (addr>>7)&7 gives wrong results).
+    const char* mode = getenv("SNVC_CONV_MODE");
+    if (!(mode && mode[0] == 't')) {
+      int r = launch_halo(x, w_packed, scale, bias, residual, y, d, p, stream, 0);
+      if (r != 1) return r;
     }
     return launch_conv(x, w_packed, scale, bias, residual, y, d, p, stream);
   }
