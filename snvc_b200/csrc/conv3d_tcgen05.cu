@@ -156,6 +156,120 @@ __device__ __forceinline__ uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+struct EpiParams {
+  int Cout, CoutPad;
+  int relu, residual_mode, sigmoid, out_f32;
+  int out_cstride, out_coffset, res_cstride, res_coffset;
+  const __nv_bfloat16* residual;
+  void* y;
+};
+
+// Residual row prefetch: issued BEFORE waiting for the accumulator so the global-load latency
+// overlaps the MMAs of this tile (up to 64 channels = 8 x 16 B per row).
+struct ResidualRow { uint4 q[8]; };
+__device__ __forceinline__ void residual_prefetch(const EpiParams& e, bool in_range, int64_t vox, ResidualRow& rr) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) rr.q[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (!e.residual_mode || !in_range) return;
+  const __nv_bfloat16* rp = e.residual + vox * e.res_cstride + e.res_coffset;
+  // host guarantees: Cout % 16 == 0 and 16-byte aligned rows whenever a residual is given
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i * 8 < e.Cout) rr.q[i] = __ldg(reinterpret_cast<const uint4*>(rp) + i);
+}
+
+// ---- lean epilogue: the common case (bf16 out, Cout == CoutPad, 16-byte aligned channel rows, no
+// sigmoid) as ONE branch-free code path:  x = acc*scale + bias;  x += r*m1;  x = max(x, lo);  x += r*m2
+// with (m1, m2, lo) = (1,0,-inf | 0) residual-before-ReLU, (0,1,..) residual-after-ReLU, (0,0,..) none.
+// ncu showed the flag-driven generic version costing ~1800 issue slots per warp per 128-row tile:
+// the epilogue, not the tensor pipe, bounded every kernel variant.
+struct EpiFast { float m1, m2, lo; };
+
+__device__ __forceinline__ void epilogue_chunk16(const uint32_t* acc, int cc, const float* s_scale, const float* s_bias,
+                                                 const ResidualRow& rr, const EpiFast f, __nv_bfloat16* yrow) {
+  float v[16];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 sc = *reinterpret_cast<const float4*>(s_scale + cc + 4 * q);
+    const float4 bi = *reinterpret_cast<const float4*>(s_bias + cc + 4 * q);
+    v[4 * q + 0] = fmaf(__uint_as_float(acc[4 * q + 0]), sc.x, bi.x);
+    v[4 * q + 1] = fmaf(__uint_as_float(acc[4 * q + 1]), sc.y, bi.y);
+    v[4 * q + 2] = fmaf(__uint_as_float(acc[4 * q + 2]), sc.z, bi.z);
+    v[4 * q + 3] = fmaf(__uint_as_float(acc[4 * q + 3]), sc.w, bi.w);
+  }
+  const uint4 q0 = rr.q[cc >> 3], q1 = rr.q[(cc >> 3) + 1];
+  const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float r0 = bf16_lo(w[j]), r1 = bf16_hi(w[j]);
+    v[2 * j] = fmaf(r0, f.m2, fmaxf(fmaf(r0, f.m1, v[2 * j]), f.lo));
+    v[2 * j + 1] = fmaf(r1, f.m2, fmaxf(fmaf(r1, f.m1, v[2 * j + 1]), f.lo));
+  }
+  uint4* o = reinterpret_cast<uint4*>(yrow + cc);
+  o[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  o[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+}
+
+__device__ __forceinline__ void epilogue_row_fast(int CoutPad, uint32_t taddr, bool in_range, __nv_bfloat16* yrow,
+                                                  const float* s_scale, const float* s_bias, const ResidualRow& rr,
+                                                  const EpiFast f) {
+#pragma unroll
+  for (int ci = 0; ci < 2; ++ci) {
+    const int c0 = ci * 32;
+    if (c0 >= CoutPad) break;
+    uint32_t acc[32];
+    const bool two = c0 + 16 < CoutPad;
+    tmem_ld16(taddr + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[16]>(acc));
+    if (two) tmem_ld16(taddr + (uint32_t)c0 + 16u, *reinterpret_cast<uint32_t(*)[16]>(acc + 16));
+    tmem_ld_wait();
+    if (in_range) {
+      epilogue_chunk16(acc, c0, s_scale, s_bias, rr, f, yrow);
+      if (two) epilogue_chunk16(acc + 16, c0 + 16, s_scale, s_bias, rr, f, yrow);
+    }
+  }
+}
+
+// generic (slow) path: partial channel counts (Cout = 1), sigmoid, unaligned rows
+__device__ __noinline__ void epilogue_row_generic(const EpiParams& e, uint32_t taddr, bool in_range, int64_t vox,
+                                                  const float* s_scale, const float* s_bias) {
+  for (int c0 = 0; c0 < e.CoutPad; c0 += 16) {
+    uint32_t acc[16];
+    tmem_ld16(taddr + (uint32_t)c0, acc);
+    tmem_ld_wait();
+    if (!in_range) continue;
+    for (int j = 0; j < 16; ++j) {
+      const int c = c0 + j;
+      if (c >= e.Cout) break;
+      float x = fmaf(__uint_as_float(acc[j]), s_scale[c & 63], s_bias[c & 63]);
+      float r = 0.f;
+      if (e.residual_mode) r = __bfloat162float(e.residual[vox * e.res_cstride + e.res_coffset + c]);
+      if (e.residual_mode == 1) x += r;
+      if (e.relu) x = fmaxf(x, 0.f);
+      if (e.residual_mode == 2) x += r;
+      if (e.sigmoid) x = 1.f / (1.f + __expf(-x));
+      if (e.out_f32) reinterpret_cast<float*>(e.y)[vox * e.out_cstride + e.out_coffset + c] = x;
+      else reinterpret_cast<__nv_bfloat16*>(e.y)[vox * e.out_cstride + e.out_coffset + c] = __float2bfloat16_rn(x);
+    }
+  }
+}
+
+// variant: 1 = fast path eligible
+__device__ __forceinline__ int epilogue_variant(const EpiParams& e) {
+  return (e.Cout == e.CoutPad && !e.sigmoid && !e.out_f32 && ((e.out_cstride | e.out_coffset) & 7) == 0) ? 1 : 0;
+}
+
+// One accumulator row (this thread's TMEM lane) -> global memory.  taddr: lane/column base.
+__device__ __forceinline__ void epilogue_row(const EpiParams& e, int variant, uint32_t taddr, bool in_range, int64_t vox,
+                                             const float* s_scale, const float* s_bias, const ResidualRow& rr) {
+  if (!variant) { epilogue_row_generic(e, taddr, in_range, vox, s_scale, s_bias); return; }
+  EpiFast f;
+  f.m1 = e.residual_mode == 1 ? 1.f : 0.f;
+  f.m2 = e.residual_mode == 2 ? 1.f : 0.f;
+  f.lo = e.relu ? 0.f : -INFINITY;
+  epilogue_row_fast(e.CoutPad, taddr, in_range, reinterpret_cast<__nv_bfloat16*>(e.y) + vox * e.out_cstride + e.out_coffset,
+                    s_scale, s_bias, rr, f);
+}
+
 struct TileCoord { int n, jd, jh, jw; };
 __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) {
   TileCoord t;
@@ -175,7 +289,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ float s_scale[64], s_bias[64];
+  __shared__ __align__(16) float s_scale[64], s_bias[64];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -270,6 +384,11 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     // ===================== epilogue (warps 2..5) =====================
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;          // accumulator row == box-linear voxel index
+    EpiParams epi;
+    epi.Cout = p.Cout; epi.CoutPad = p.CoutPad; epi.relu = p.relu; epi.residual_mode = p.residual_mode;
+    epi.sigmoid = p.sigmoid; epi.out_f32 = p.out_f32; epi.out_cstride = p.out_cstride; epi.out_coffset = p.out_coffset;
+    epi.res_cstride = p.res_cstride; epi.res_coffset = p.res_coffset; epi.residual = p.residual; epi.y = p.y;
+    const int variant = epilogue_variant(epi);
     const int r_w = row % p.TW, r_h = (row / p.TW) % p.TH, r_d = row / (p.TW * p.TH);
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -281,68 +400,12 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
       const int od = jd * p.out_stride + p.out_off_d, oh = jh * p.out_stride + p.out_off_h,
                 ow = jw * p.out_stride + p.out_off_w;
       const int64_t vox = (((int64_t)tc.n * p.Do + od) * p.Ho + oh) * p.Wo + ow;
+      ResidualRow rr;
+      residual_prefetch(epi, in_range, vox, rr);
       mbar_wait(smem_u32(&tmem_full_bar[buf]), use & 1u);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.CoutPad);
-      for (int c0 = 0; c0 < p.CoutPad; c0 += 16) {
-        uint32_t acc[16];
-        tmem_ld16(taddr + (uint32_t)c0, acc);
-        tmem_ld_wait();
-        if (in_range) {
-          float v[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(acc[j]), s_scale[(c0 + j) & 63], s_bias[(c0 + j) & 63]);
-          float r[16];
-          const bool full = (c0 + 16 <= p.Cout);
-          if (p.residual_mode) {
-            const __nv_bfloat16* rp = p.residual + vox * p.res_cstride + p.res_coffset + c0;
-            if (full) {
-              uint4 q0 = __ldg(reinterpret_cast<const uint4*>(rp));
-              uint4 q1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
-              r[0] = bf16_lo(q0.x); r[1] = bf16_hi(q0.x); r[2] = bf16_lo(q0.y); r[3] = bf16_hi(q0.y);
-              r[4] = bf16_lo(q0.z); r[5] = bf16_hi(q0.z); r[6] = bf16_lo(q0.w); r[7] = bf16_hi(q0.w);
-              r[8] = bf16_lo(q1.x); r[9] = bf16_hi(q1.x); r[10] = bf16_lo(q1.y); r[11] = bf16_hi(q1.y);
-              r[12] = bf16_lo(q1.z); r[13] = bf16_hi(q1.z); r[14] = bf16_lo(q1.w); r[15] = bf16_hi(q1.w);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) r[j] = (c0 + j < p.Cout) ? __bfloat162float(rp[j]) : 0.f;
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float x = v[j];
-            if (p.residual_mode == 1) x += r[j];
-            if (p.relu) x = fmaxf(x, 0.f);
-            if (p.residual_mode == 2) x += r[j];
-            if (p.sigmoid) x = 1.f / (1.f + __expf(-x));
-            v[j] = x;
-          }
-          if (p.out_f32) {
-            float* o = reinterpret_cast<float*>(p.y) + vox * p.out_cstride + p.out_coffset + c0;
-            if (full && ((p.out_cstride | p.out_coffset) & 3) == 0) {
-#pragma unroll
-              for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (c0 + j < p.Cout) o[j] = v[j];
-            }
-          } else {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.y) + vox * p.out_cstride + p.out_coffset + c0;
-            if (full && ((p.out_cstride | p.out_coffset) & 7) == 0) {
-              uint4 q0 = {pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])};
-              uint4 q1 = {pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
-                          pack_bf16x2(v[14], v[15])};
-              *reinterpret_cast<uint4*>(o) = q0;
-              *(reinterpret_cast<uint4*>(o) + 1) = q1;
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (c0 + j < p.Cout) o[j] = __float2bfloat16_rn(v[j]);
-            }
-          }
-        }
-      }
+      epilogue_row(epi, variant, taddr, in_range, vox, s_scale, s_bias, rr);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[buf]));
@@ -378,75 +441,6 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
 //     (measured: descriptors with base offset 0 and a start address shifted by any number of
 //     rows reproduce the oracle for SWIZZLE_32B/64B/128B; tests/test_gpu_conv3d.py).
 // ==========================================================================================
-struct EpiParams {
-  int Cout, CoutPad;
-  int relu, residual_mode, sigmoid, out_f32;
-  int out_cstride, out_coffset, res_cstride, res_coffset;
-  const __nv_bfloat16* residual;
-  void* y;
-};
-
-// One accumulator row (this thread's TMEM lane) -> global memory.  taddr: lane/column base.
-__device__ __forceinline__ void epilogue_row(const EpiParams& e, uint32_t taddr, bool in_range, int64_t vox,
-                                             const float* s_scale, const float* s_bias) {
-  for (int c0 = 0; c0 < e.CoutPad; c0 += 16) {
-    uint32_t acc[16];
-    tmem_ld16(taddr + (uint32_t)c0, acc);
-    tmem_ld_wait();
-    if (!in_range) continue;
-    float v[16], r[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(acc[j]), s_scale[(c0 + j) & 63], s_bias[(c0 + j) & 63]);
-    const bool full = (c0 + 16 <= e.Cout);
-    if (e.residual_mode) {
-      const __nv_bfloat16* rp = e.residual + vox * e.res_cstride + e.res_coffset + c0;
-      if (full) {
-        uint4 q0 = __ldg(reinterpret_cast<const uint4*>(rp));
-        uint4 q1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
-        r[0] = bf16_lo(q0.x); r[1] = bf16_hi(q0.x); r[2] = bf16_lo(q0.y); r[3] = bf16_hi(q0.y);
-        r[4] = bf16_lo(q0.z); r[5] = bf16_hi(q0.z); r[6] = bf16_lo(q0.w); r[7] = bf16_hi(q0.w);
-        r[8] = bf16_lo(q1.x); r[9] = bf16_hi(q1.x); r[10] = bf16_lo(q1.y); r[11] = bf16_hi(q1.y);
-        r[12] = bf16_lo(q1.z); r[13] = bf16_hi(q1.z); r[14] = bf16_lo(q1.w); r[15] = bf16_hi(q1.w);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) r[j] = (c0 + j < e.Cout) ? __bfloat162float(rp[j]) : 0.f;
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      float x = v[j];
-      if (e.residual_mode == 1) x += r[j];
-      if (e.relu) x = fmaxf(x, 0.f);
-      if (e.residual_mode == 2) x += r[j];
-      if (e.sigmoid) x = 1.f / (1.f + __expf(-x));
-      v[j] = x;
-    }
-    if (e.out_f32) {
-      float* o = reinterpret_cast<float*>(e.y) + vox * e.out_cstride + e.out_coffset + c0;
-      if (full && ((e.out_cstride | e.out_coffset) & 3) == 0) {
-#pragma unroll
-        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (c0 + j < e.Cout) o[j] = v[j];
-      }
-    } else {
-      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(e.y) + vox * e.out_cstride + e.out_coffset + c0;
-      if (full && ((e.out_cstride | e.out_coffset) & 7) == 0) {
-        uint4 q0 = {pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])};
-        uint4 q1 = {pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15])};
-        *reinterpret_cast<uint4*>(o) = q0;
-        *(reinterpret_cast<uint4*>(o) + 1) = q1;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (c0 + j < e.Cout) o[j] = __float2bfloat16_rn(v[j]);
-      }
-    }
-  }
-}
-
 constexpr int kMaxSlots = 12;
 
 struct HaloParams {
@@ -455,16 +449,20 @@ struct HaloParams {
   int K, dil, pad;             // pad == dil*(K-1)/2
   int WP, TH, TWv;             // row pitch, tile rows (WP*TH == 128), valid columns per row = WP - hw
   int tiles_h, tiles_w, num_cols;
-  int plane_bytes;             // TMA box bytes: (TH+hw)*WP*Cin*2
+  int plane_bytes;             // TMA bytes per plane: (TH+hw)*WP*Cin*2
   int slot_bytes, nslots;
   int w_tap_bytes;             // CoutPad*Cin*2
-  int swizzle_bytes, bo_mode;
+  // K-split: a plane / weight tile is stored as `nsub` sub-tiles whose rows are `sub_row_bytes` long
+  // (Cin=64: one 128-B-row SWIZZLE_128B tile; Cin=32: two 32-B-row SWIZZLE_32B tiles -- a 64-B-row
+  // SWIZZLE_64B tile read in 32-byte K-slices is 2-way bank conflicted, measured 89 vs 57 cycles/MMA)
+  int sub_row_bytes, nsub, sub_tile_bytes, w_sub_bytes;
+  int bo_mode;
   const float* scale;
   const float* bias;
   EpiParams epi;
 };
 
-template <int K, int KSTEPS>
+template <int K, int KSTEPS, int SUBROW>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3d_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                    const __grid_constant__ HaloParams p) {
@@ -475,7 +473,7 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ float s_scale[64], s_bias[64];
+  __shared__ __align__(16) float s_scale[64], s_bias[64];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -483,9 +481,9 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   const int hw = (p.K - 1) * p.dil;
   const uint32_t w_base = (smem_u32(smem) + 1023u) & ~1023u;
   const uint32_t slots_base = w_base + (((uint32_t)(K3 * p.w_tap_bytes) + 1023u) & ~1023u);
-  const int row_bytes = p.Cin * 2;
   const uint32_t tmem_cols = p.epi.CoutPad * 2 <= 32 ? 32u : (p.epi.CoutPad * 2 <= 64 ? 64u : 128u);
   const int planes_per_col = p.D + hw;
+  constexpr int KPS = SUBROW / 32;            // K=16 steps per sub-tile row
 
   if (threadIdx.x < 64) {
     s_scale[threadIdx.x] = (p.scale && threadIdx.x < p.epi.Cout) ? p.scale[threadIdx.x] : 1.f;
@@ -521,7 +519,9 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     const uint32_t wb = smem_u32(&w_bar);
     if (elect_one()) {
       mbar_expect_tx(wb, (uint32_t)(K3 * p.w_tap_bytes));
-      for (int t = 0; t < K3; ++t) tma_load_2d(w_base + t * p.w_tap_bytes, &map_w, wb, 0, t * p.epi.CoutPad);
+      for (int t = 0; t < K3; ++t)
+        for (int sb = 0; sb < p.nsub; ++sb)
+          tma_load_2d(w_base + t * p.w_tap_bytes + sb * p.w_sub_bytes, &map_w, wb, sb * (SUBROW / 2), t * p.epi.CoutPad);
     }
     __syncwarp();
     uint32_t q = 0;
@@ -535,7 +535,8 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         if (elect_one()) {
           const uint32_t fb = smem_u32(&full_bar[slot]);
           mbar_expect_tx(fb, (uint32_t)p.plane_bytes);
-          tma_load_5d(slots_base + slot * p.slot_bytes, &map_x, fb, 0, w0, h0, ip, n);
+          for (int sb = 0; sb < p.nsub; ++sb)
+            tma_load_5d(slots_base + slot * p.slot_bytes + sb * p.sub_tile_bytes, &map_x, fb, sb * (SUBROW / 2), w0, h0, ip, n);
         }
         __syncwarp();
       }
@@ -543,14 +544,15 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   } else if (warp == 1) {
     // ===================== MMA issuer (warp-wide loop, elected lane issues) =====================
     const uint32_t idesc = make_idesc(kTileM, p.epi.CoutPad);
-    const uint32_t desc_hi = (uint32_t)(make_smem_desc(0, p.swizzle_bytes) >> 32);
+    const uint32_t desc_hi = (uint32_t)(make_smem_desc(0, SUBROW) >> 32);
     const uint32_t lo_flags = 1u << 16;                                   // LBO field (ignored for swizzled K-major)
+    const uint32_t a_sub = (uint32_t)p.sub_tile_bytes >> 4, b_sub = (uint32_t)p.w_sub_bytes >> 4;
     // descriptor offsets, in 16-byte units: filter tap (kh,kw) = whole-row shift of the plane tile
     uint32_t off_hw[K * K];
 #pragma unroll
     for (int kh = 0; kh < K; ++kh)
 #pragma unroll
-      for (int kw = 0; kw < K; ++kw) off_hw[kh * K + kw] = (uint32_t)((kh * p.dil * p.WP + kw * p.dil) * row_bytes) >> 4;
+      for (int kw = 0; kw < K; ++kw) off_hw[kh * K + kw] = (uint32_t)((kh * p.dil * p.WP + kw * p.dil) * SUBROW) >> 4;
     const uint32_t b_lo0 = ((w_base >> 4) & 0x3FFFu) | lo_flags;
     const uint32_t b_step = (uint32_t)p.w_tap_bytes >> 4;
     mbar_wait(smem_u32(&w_bar), 0);
@@ -579,9 +581,11 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
               const uint32_t a_lo = plane_lo[kd] + off_hw[t2];
               const uint32_t b_lo = b_lo0 + (uint32_t)(kd * K * K + t2) * b_step;
 #pragma unroll
-              for (int k = 0; k < KSTEPS; ++k)
-                umma_bf16(d_tmem, desc64(desc_hi, a_lo + 2 * k), desc64(desc_hi, b_lo + 2 * k), idesc,
-                          (kd | t2 | k) ? 1u : 0u);
+              for (int k = 0; k < KSTEPS; ++k) {
+                const uint32_t ka = (uint32_t)(k / KPS) * a_sub + 2u * (uint32_t)(k % KPS);
+                const uint32_t kb = (uint32_t)(k / KPS) * b_sub + 2u * (uint32_t)(k % KPS);
+                umma_bf16(d_tmem, desc64(desc_hi, a_lo + ka), desc64(desc_hi, b_lo + kb), idesc, (kd | t2 | k) ? 1u : 0u);
+              }
             }
           umma_commit(smem_u32(&tmem_full_bar[buf]));
           umma_commit(smem_u32(&empty_bar[(q0 + d) % (uint32_t)p.nslots]));   // input plane d is done
@@ -598,6 +602,7 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const int r_w = row % p.WP, r_h = row / p.WP;
+    const int variant = epilogue_variant(p.epi);
     uint32_t it = 0;
     for (int col = blockIdx.x; col < p.num_cols; col += gridDim.x) {
       int tw = col % p.tiles_w, rest = col / p.tiles_w;
@@ -607,10 +612,13 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       const int64_t vox0 = (((int64_t)n * p.D) * p.H + oh) * p.W + ow;
       for (int d = 0; d < p.D; ++d, ++it) {
         const uint32_t buf = it & 1u;
+        const int64_t vox = vox0 + (int64_t)d * p.H * p.W;
+        ResidualRow rr;
+        residual_prefetch(p.epi, in_range, vox, rr);
         mbar_wait(smem_u32(&tmem_full_bar[buf]), (it >> 1) & 1u);
         tcgen05_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * (uint32_t)p.epi.CoutPad;
-        epilogue_row(p.epi, taddr, in_range, vox0 + (int64_t)d * p.H * p.W, s_scale, s_bias);
+        epilogue_row(p.epi, variant, taddr, in_range, vox, s_scale, s_bias, rr);
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[buf]));
@@ -623,6 +631,221 @@ conv3d_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+
+// ==========================================================================================
+// v3: kd-fused plane march (3x3x3, stride 1, "same" padding) -- the kernel the trunk runs on.
+//
+// Measured with ncu on v2 (profiles/r01_conv_halo_v2.ncu-rep): every M=128,N=32,K=16 MMA occupies
+// the tensor pipe for 64 cycles (16 would be peak) -- with both operands in shared memory the
+// 128x16 A slice (4 KB) is the cost, whatever N is.  So N must grow.  Here the three depth taps
+// are fused into ONE instruction: for input plane p and in-plane tap (kh,kw)
+//     D[128, 3*Cout] += A_p(kh,kw)[128, Cin] * [W(0,kh,kw) | W(1,kh,kw) | W(2,kh,kw)]
+// whose three column blocks are the accumulators of output planes p+1, p, p-1.  Accumulators
+// live in a RING of R = 512/Cout TMEM blocks, block(g) = (-g) mod R for accumulator plane g, so
+// the three blocks an input plane updates are always adjacent columns (one MMA; split in two
+// where the ring wraps).  Each input plane is read from HBM/L2 once, read from smem 9x (not 27x)
+// and each output plane has R-2 planes of slack before its TMEM block is reused, so the
+// epilogue (which drains a block, stores it, and zero-fills it with tcgen05.st for its next
+// use; all MMAs accumulate) is off the critical path.
+// ==========================================================================================
+constexpr int kMaxBlocks = 32;
+
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};"
+      ::"r"(taddr), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <int KSTEPS, int SUBROW>
+__global__ void __launch_bounds__(kThreads, 1)
+conv3d_kdfuse_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                     const __grid_constant__ HaloParams p) {
+  constexpr int K = 3;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxSlots];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxSlots];
+  __shared__ __align__(8) uint64_t w_bar;
+  __shared__ __align__(8) uint64_t acc_full_bar[kMaxBlocks];
+  __shared__ __align__(8) uint64_t acc_empty_bar[kMaxBlocks];
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(16) float s_scale[64], s_bias[64];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr int K3 = 27;
+  const int CP = p.epi.CoutPad;
+  const uint32_t R = 512u / (uint32_t)CP;                 // accumulator blocks in the TMEM ring
+  const uint32_t w_base = (smem_u32(smem) + 1023u) & ~1023u;
+  const uint32_t slots_base = w_base + (((uint32_t)(K3 * p.w_tap_bytes) + 1023u) & ~1023u);
+  const uint32_t acc_per_col = (uint32_t)p.D + 2u;        // accumulator planes per column: out[-1] .. out[D]
+
+  if (threadIdx.x < 64) {
+    s_scale[threadIdx.x] = (p.scale && threadIdx.x < p.epi.Cout) ? p.scale[threadIdx.x] : 1.f;
+    s_bias[threadIdx.x] = (p.bias && threadIdx.x < p.epi.Cout) ? p.bias[threadIdx.x] : 0.f;
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    for (int s = 0; s < p.nslots; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(&w_bar), 1);
+    for (uint32_t b = 0; b < R; ++b) {
+      mbar_init(smem_u32(&acc_full_bar[b]), 1);
+      mbar_init(smem_u32(&acc_empty_bar[b]), 4);          // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  if (warp >= 2) {                                        // zero the whole accumulator ring once
+    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    for (uint32_t c = 0; c < 512u; c += 16u) tmem_st16_zero(lane_base + c);
+    tmem_st_wait();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    const uint32_t wb = smem_u32(&w_bar);
+    if (elect_one()) {
+      mbar_expect_tx(wb, (uint32_t)(K3 * p.w_tap_bytes));
+      // smem order [(kh,kw)][kd]: the three depth taps of one in-plane tap are adjacent -> one B operand of 3*Cout rows
+      for (int t2 = 0; t2 < K * K; ++t2)
+        for (int kd = 0; kd < K; ++kd)
+          tma_load_2d(w_base + (t2 * K + kd) * p.w_tap_bytes, &map_w, wb, 0, (kd * K * K + t2) * CP);
+    }
+    __syncwarp();
+    uint32_t q = 0;
+    for (int col = blockIdx.x; col < p.num_cols; col += gridDim.x) {
+      int tw = col % p.tiles_w, rest = col / p.tiles_w;
+      int th = rest % p.tiles_h, n = rest / p.tiles_h;
+      const int w0 = tw * p.TWv - p.pad, h0 = th * p.TH - p.pad;
+      for (int ip = 0; ip < p.D; ++ip, ++q) {             // only real planes: the zero planes -1 and D contribute nothing
+        const uint32_t slot = q % (uint32_t)p.nslots, phase = (q / (uint32_t)p.nslots) & 1u;
+        mbar_wait(smem_u32(&empty_bar[slot]), phase ^ 1u);
+        if (elect_one()) {
+          const uint32_t fb = smem_u32(&full_bar[slot]);
+          mbar_expect_tx(fb, (uint32_t)p.plane_bytes);
+          tma_load_5d(slots_base + slot * p.slot_bytes, &map_x, fb, 0, w0, h0, ip, n);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc1 = make_idesc(kTileM, CP), idesc2 = make_idesc(kTileM, 2 * CP), idesc3 = make_idesc(kTileM, 3 * CP);
+    const uint32_t desc_hi = (uint32_t)(make_smem_desc(0, SUBROW) >> 32);
+    const uint32_t lo_flags = 1u << 16;
+    uint32_t off_hw[K * K];
+#pragma unroll
+    for (int kh = 0; kh < K; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < K; ++kw) off_hw[kh * K + kw] = (uint32_t)((kh * p.WP + kw) * SUBROW) >> 4;
+    const uint32_t b_lo0 = ((w_base >> 4) & 0x3FFFu) | lo_flags;
+    const uint32_t b_tap = (uint32_t)p.w_tap_bytes >> 4;             // one (kd) tile
+    mbar_wait(smem_u32(&w_bar), 0);
+    uint32_t q = 0, G0 = 0;
+    for (int col = blockIdx.x; col < p.num_cols; col += gridDim.x, G0 += acc_per_col) {
+      for (int pl = 0; pl < p.D; ++pl, ++q) {
+        const uint32_t slot = q % (uint32_t)p.nslots;
+        mbar_wait(smem_u32(&full_bar[slot]), (q / (uint32_t)p.nslots) & 1u);
+        // accumulator planes touched: g+2 (kd=0, out[pl+1]), g+1 (kd=1), g (kd=2, out[pl-1]);  g = G0 + pl
+        const uint32_t g = G0 + (uint32_t)pl;
+        for (uint32_t gn = (pl == 0 ? g : g + 2u); gn <= g + 2u; ++gn) {      // blocks entering the window
+          const uint32_t use = gn / R;
+          mbar_wait(smem_u32(&acc_empty_bar[(R - gn % R) % R]), (use & 1u) ^ 1u);
+        }
+        tcgen05_fence_after();
+        const uint32_t b0 = (R - (g + 2u) % R) % R;                            // block of kd = 0
+        const uint32_t n0 = min(3u, R - b0);                                   // blocks before the ring wraps
+        const uint32_t a_plane = (((slots_base + slot * p.slot_bytes) >> 4) & 0x3FFFu) | lo_flags;
+        const uint32_t d0 = tmem_base + b0 * (uint32_t)CP;
+        if (elect_one()) {
+          if (n0 == 3u) {
+#pragma unroll
+            for (int t2 = 0; t2 < K * K; ++t2)
+#pragma unroll
+              for (int k = 0; k < KSTEPS; ++k)
+                umma_bf16(d0, desc64(desc_hi, a_plane + off_hw[t2] + 2u * k),
+                          desc64(desc_hi, b_lo0 + (uint32_t)(t2 * K) * b_tap + 2u * k), idesc3, 1u);
+          } else {
+            const uint32_t ia = n0 == 1u ? idesc1 : idesc2, ib = n0 == 1u ? idesc2 : idesc1;
+#pragma unroll
+            for (int t2 = 0; t2 < K * K; ++t2)
+#pragma unroll
+              for (int k = 0; k < KSTEPS; ++k) {
+                const uint64_t ad = desc64(desc_hi, a_plane + off_hw[t2] + 2u * k);
+                const uint32_t bl = b_lo0 + (uint32_t)(t2 * K) * b_tap + 2u * k;
+                umma_bf16(d0, ad, desc64(desc_hi, bl), ia, 1u);                            // kd in [0, n0)
+                umma_bf16(tmem_base, ad, desc64(desc_hi, bl + n0 * b_tap), ib, 1u);        // kd in [n0, 3) at block 0
+              }
+          }
+          umma_commit(smem_u32(&empty_bar[slot]));                                          // plane consumed
+          umma_commit(smem_u32(&acc_full_bar[(R - g % R) % R]));                            // out[pl-1] complete
+          if (pl == p.D - 1) {                                                              // column tail: out[D-1], out[D]
+            umma_commit(smem_u32(&acc_full_bar[(R - (g + 1u) % R) % R]));
+            umma_commit(smem_u32(&acc_full_bar[(R - (g + 2u) % R) % R]));
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int r_w = row % p.WP, r_h = row / p.WP;
+    const int variant = epilogue_variant(p.epi);
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    uint32_t G0 = 0;
+    for (int col = blockIdx.x; col < p.num_cols; col += gridDim.x, G0 += acc_per_col) {
+      int tw = col % p.tiles_w, rest = col / p.tiles_w;
+      int th = rest % p.tiles_h, n = rest / p.tiles_h;
+      const int ow = tw * p.TWv + r_w, oh = th * p.TH + r_h;
+      const bool in_range = r_w < p.TWv && ow < p.W && oh < p.H;
+      const int64_t vox0 = (((int64_t)n * p.D) * p.H + oh) * p.W + ow;
+      for (uint32_t a = 0; a < acc_per_col; ++a) {          // accumulator plane a <-> output plane a - 1
+        const uint32_t g = G0 + a;
+        const uint32_t blk = (R - g % R) % R;
+        const bool real = a >= 1u && a <= (uint32_t)p.D;
+        const int64_t vox = vox0 + (int64_t)((int)a - 1) * p.H * p.W;
+        ResidualRow rr;
+        residual_prefetch(p.epi, in_range && real, vox, rr);
+        mbar_wait(smem_u32(&acc_full_bar[blk]), (g / R) & 1u);
+        tcgen05_fence_after();
+        const uint32_t taddr = lane_base + blk * (uint32_t)CP;
+        if (real) epilogue_row(p.epi, variant, taddr, in_range, vox, s_scale, s_bias, rr);
+        for (int c = 0; c < CP; c += 16) tmem_st16_zero(taddr + (uint32_t)c);   // ready for its next output plane
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&acc_empty_bar[blk]));
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -748,8 +971,9 @@ int launch_halo(const void* x, const void* w_packed, const float* scale, const f
   p.epi.sigmoid = cp.sigmoid; p.epi.out_f32 = cp.out_f32; p.epi.out_cstride = cp.out_cstride;
   p.epi.out_coffset = cp.out_coffset; p.epi.res_cstride = cp.res_cstride; p.epi.res_coffset = cp.res_coffset;
   p.epi.residual = (const __nv_bfloat16*)residual; p.epi.y = y;
-  p.swizzle_bytes = d.Cin * 2;
   p.bo_mode = bo_mode;
+  p.sub_row_bytes = d.Cin * 2;   // single sub-tile (a 2 x SWIZZLE_32B K-split measured no faster than SWIZZLE_64B)
+  p.nsub = d.Cin * 2 / p.sub_row_bytes;
   const int row_bytes = d.Cin * 2;
   const int K3 = d.kernel * d.kernel * d.kernel;
   p.w_tap_bytes = cp.CoutPad * d.Cin * 2;
@@ -760,13 +984,15 @@ int launch_halo(const void* x, const void* w_packed, const float* scale, const f
   for (int wp = 16; wp <= 64; wp <<= 1) {
     const int twv = wp - hw, th = 128 / wp;
     if (twv <= 0) continue;
-    const int slot = round_up(((th + hw) * wp + 16) * row_bytes, 1024);
+    const int slot = p.nsub * round_up(((th + hw) * wp + 16) * p.sub_row_bytes, 1024);
     if (budget < slot * (hw + 2)) continue;
     double eff = ((double)d.Wi / (ceil_div(d.Wi, twv) * wp)) * ((double)d.Hi / (ceil_div(d.Hi, th) * th));
     if (eff > best) { best = eff; p.WP = wp; p.TH = th; p.TWv = twv; p.slot_bytes = slot; }
   }
   if (best < 0) return 1;                                // weights + ring do not fit: per-tap kernel
   p.nslots = std::min(kMaxSlots, budget / p.slot_bytes);
+  p.sub_tile_bytes = p.slot_bytes / p.nsub;
+  p.w_sub_bytes = cp.CoutPad * p.sub_row_bytes;
   p.plane_bytes = (p.TH + hw) * p.WP * row_bytes;
   p.tiles_h = (int)ceil_div(d.Hi, p.TH); p.tiles_w = (int)ceil_div(d.Wi, p.TWv);
   const int64_t ncols = (int64_t)d.N * p.tiles_h * p.tiles_w;
@@ -779,29 +1005,31 @@ int launch_halo(const void* x, const void* w_packed, const float* scale, const f
     const cuuint64_t cs = (cuuint64_t)(d.in_cstride ? d.in_cstride : d.Cin) * 2;
     cuuint64_t dims[5] = {(cuuint64_t)d.Cin, (cuuint64_t)d.Wi, (cuuint64_t)d.Hi, (cuuint64_t)d.Di, (cuuint64_t)d.N};
     cuuint64_t strides[4] = {cs, (cuuint64_t)d.Wi * cs, (cuuint64_t)d.Hi * d.Wi * cs, (cuuint64_t)d.Di * d.Hi * d.Wi * cs};
-    cuuint32_t box[5] = {(cuuint32_t)d.Cin, (cuuint32_t)p.WP, (cuuint32_t)(p.TH + hw), 1, 1};
+    cuuint32_t box[5] = {(cuuint32_t)(p.sub_row_bytes / 2), (cuuint32_t)p.WP, (cuuint32_t)(p.TH + hw), 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     const void* xbase = static_cast<const char*>(x) + (size_t)d.in_coffset * 2;
     CUresult r = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(xbase), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_mode(p.swizzle_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_mode(p.sub_row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail((int)r, "cuTensorMapEncodeTiled(x, halo) failed with CUresult %d", (int)r);
   }
   {
     cuuint64_t dims[2] = {(cuuint64_t)d.Cin, (cuuint64_t)K3 * cp.CoutPad};
     cuuint64_t strides[1] = {(cuuint64_t)d.Cin * 2};
-    cuuint32_t box[2] = {(cuuint32_t)d.Cin, (cuuint32_t)cp.CoutPad};
+    cuuint32_t box[2] = {(cuuint32_t)(p.sub_row_bytes / 2), (cuuint32_t)cp.CoutPad};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_packed), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_mode(p.swizzle_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_mode(p.sub_row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail((int)r, "cuTensorMapEncodeTiled(w, halo) failed with CUresult %d", (int)r);
   }
   void (*kern)(const CUtensorMap, const CUtensorMap, const HaloParams) = nullptr;
+  const char* mode = getenv("SNVC_CONV_MODE");
+  const bool kdfuse = d.dilation == 1 && !(mode && mode[0] == 'h');     // SNVC_CONV_MODE=halo: v2 (A/B runs)
   switch (d.Cin) {
-    case 16: kern = conv3d_halo_kernel<3, 1>; break;
-    case 32: kern = conv3d_halo_kernel<3, 2>; break;
-    case 64: kern = conv3d_halo_kernel<3, 4>; break;
+    case 16: kern = kdfuse ? conv3d_kdfuse_kernel<1, 32> : conv3d_halo_kernel<3, 1, 32>; break;
+    case 32: kern = kdfuse ? conv3d_kdfuse_kernel<2, 64> : conv3d_halo_kernel<3, 2, 64>; break;
+    case 64: kern = kdfuse ? conv3d_kdfuse_kernel<4, 128> : conv3d_halo_kernel<3, 4, 128>; break;
   }
   SNVC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = std::min(p.num_cols, sm_count());
@@ -842,6 +1070,9 @@ extern "C" int snvc_conv3d_fwd(const void* x, const void* w_packed, const float*
   SNVC_CHECK_ARG(d.N >= 0 && d.Di > 0 && d.Hi > 0 && d.Wi > 0, "bad input extent");
   SNVC_CHECK_ARG(d.out_dtype == SNVC_BF16 || d.out_dtype == SNVC_F32, "out_dtype must be bf16 or f32");
   SNVC_CHECK_ARG(d.residual_mode == 0 || residual != nullptr, "residual_mode set but residual is null");
+  SNVC_CHECK_ARG(d.residual_mode == 0 || (d.Cout % 16 == 0 && (d.res_cstride % 8) == 0 && (d.res_coffset % 8) == 0 &&
+                                          (reinterpret_cast<uintptr_t>(residual) & 15) == 0),
+                 "a residual needs Cout %% 16 == 0 and 16-byte aligned channel rows");
   SNVC_CHECK_ARG(d.in_cstride == 0 || (d.in_cstride % 8 == 0 && d.in_coffset % 8 == 0 && d.in_coffset + d.Cin <= d.in_cstride),
                  "bad input channel slice (in_cstride %d, in_coffset %d)", d.in_cstride, d.in_coffset);
   SNVC_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0 &&
