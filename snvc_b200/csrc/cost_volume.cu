@@ -11,6 +11,8 @@
 // Arithmetic is written with explicit round-to-nearest intrinsics so that the result is
 // bit-identical to the nvcc-compiled reference expression  w1*v1 + w2*v2 + w3*v3 + w4*v4
 // (-fmad=true => fma(w2,v2, w1*v1); the w3/w4 terms are exact zeros because y is an integer).
+#include <cmath>
+
 #include "common.cuh"
 
 namespace snvc {
@@ -152,7 +154,16 @@ __device__ __forceinline__ const float4* chunk_ptr(const float* base, int col, i
   return reinterpret_cast<const float4*>(base + col * C + ((q ^ (col & mask)) << 2));
 }
 
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src)
+               : "memory");
+}
+
+// Each thread owns (output column, 8-channel group) pairs and walks the depth bins: the left half is
+// packed once and re-stored per bin, the right half costs one sample_pos + 4 LDS.128 + 8 FMAs per bin.
+// Staging uses 4-byte cp.async (no register round trip, all loads in flight at once).
+__global__ void __launch_bounds__(512)
 cv_ndhwc_bf16_kernel(const float* __restrict__ left, const float* __restrict__ right,
                      const float* __restrict__ shift, __nv_bfloat16* __restrict__ cost, int C, int img_h,
                      int img_w, int D, int H, int W, int ds, int d_per_cta, int n_dsplit, int TW, int S, int mask) {
@@ -181,62 +192,60 @@ cv_ndhwc_bf16_kernel(const float* __restrict__ left, const float* __restrict__ r
   const int64_t cstride = (int64_t)img_h * img_w;
   for (int i = threadIdx.x; i < C * lw; i += blockDim.x) {
     int c = i / lw, col = i - c * lw;
-    sL[swz(col, c, C, mask)] = lrow[c * cstride + llo + col];
+    cp_async_4(&sL[swz(col, c, C, mask)], lrow + c * cstride + llo + col);
   }
   for (int i = threadIdx.x; i < C * rw; i += blockDim.x) {
     int c = i / rw, col = i - c * rw;
-    sR[swz(col, c, C, mask)] = rrow[c * cstride + rlo + col];
+    cp_async_4(&sR[swz(col, c, C, mask)], rrow + c * cstride + rlo + col);
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
   for (int i = threadIdx.x; i < dn; i += blockDim.x) sS[i] = -shift[(int64_t)n * D + d0 + i];
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
   const int CG = C >> 3;                // 8-channel groups per view
-  const int per_d = tw * CG;
-  const int total = dn * per_d;
   const int C2 = 2 * C;
-  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-    int dd = idx / per_d;
-    int rem = idx - dd * per_d;
-    int wl = rem / CG;
-    int cg = rem - wl * CG;
-    int pw = pw0 + wl;
-    int iw = pw * ds;
-    __nv_bfloat16* o = cost + ((((int64_t)n * D + d0 + dd) * H + ph) * W + pw) * C2 + cg * 8;
-
-    // left half: broadcast copy
+  const int64_t dstride = (int64_t)H * W * C2;
+  for (int pair = threadIdx.x; pair < tw * CG; pair += blockDim.x) {
+    const int wl = pair / CG, cg = pair - wl * CG;
+    const int pw = pw0 + wl, iw = pw * ds;
+    __nv_bfloat16* o = cost + ((((int64_t)n * D + d0) * H + ph) * W + pw) * C2 + cg * 8;
+    uint4 vl;
     {
-      int col = iw - llo;
+      const int col = iw - llo;
       const float4 a = *chunk_ptr(sL, col, 2 * cg, C, mask);
       const float4 b = *chunk_ptr(sL, col, 2 * cg + 1, C, mask);
-      uint4 v = {pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w)};
-      *reinterpret_cast<uint4*>(o) = v;
+      vl = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
     }
-    // right half: 1-D linear interpolation along the row
-    int xl, xh;
-    float lx;
-    uint4 v = {0u, 0u, 0u, 0u};
-    if (sample_pos<float>(iw, sS[dd], img_w, xl, xh, lx)) {
-      float r0[8], r1[8];
-      if (xl >= rlo) {
-        int c0 = xl - rlo, c1 = xh - rlo;
-        *reinterpret_cast<float4*>(r0) = *chunk_ptr(sR, c0, 2 * cg, C, mask);
-        *reinterpret_cast<float4*>(r0 + 4) = *chunk_ptr(sR, c0, 2 * cg + 1, C, mask);
-        *reinterpret_cast<float4*>(r1) = *chunk_ptr(sR, c1, 2 * cg, C, mask);
-        *reinterpret_cast<float4*>(r1 + 4) = *chunk_ptr(sR, c1, 2 * cg + 1, C, mask);
-      } else {
-        // sample left of the staged window (very large shift on a w-tiled row): read HBM directly
+    for (int dd = 0; dd < dn; ++dd, o += dstride) {
+      *reinterpret_cast<uint4*>(o) = vl;                       // left half: broadcast over depth
+      int xl, xh;
+      float lx;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (sample_pos<float>(iw, sS[dd], img_w, xl, xh, lx)) {  // right half: 1-D interpolation along the row
+        float r0[8], r1[8];
+        if (xl >= rlo) {
+          const int c0 = xl - rlo, c1 = xh - rlo;
+          *reinterpret_cast<float4*>(r0) = *chunk_ptr(sR, c0, 2 * cg, C, mask);
+          *reinterpret_cast<float4*>(r0 + 4) = *chunk_ptr(sR, c0, 2 * cg + 1, C, mask);
+          *reinterpret_cast<float4*>(r1) = *chunk_ptr(sR, c1, 2 * cg, C, mask);
+          *reinterpret_cast<float4*>(r1 + 4) = *chunk_ptr(sR, c1, 2 * cg + 1, C, mask);
+        } else {
+          // sample left of the staged window (very large shift on a w-tiled row): read HBM directly
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          r0[j] = rrow[(int64_t)(cg * 8 + j) * cstride + xl];
-          r1[j] = rrow[(int64_t)(cg * 8 + j) * cstride + xh];
+          for (int j = 0; j < 8; ++j) {
+            r0[j] = rrow[(int64_t)(cg * 8 + j) * cstride + xl];
+            r1[j] = rrow[(int64_t)(cg * 8 + j) * cstride + xh];
+          }
         }
-      }
-      float r[8];
+        const float hx = __fsub_rn(1.f, lx);
+        float r[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) r[j] = interp<float>(lx, r0[j], r1[j]);
-      v = {pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7])};
+        for (int j = 0; j < 8; ++j) r[j] = __fmaf_rn(lx, r1[j], __fmul_rn(hx, r0[j]));
+        v = make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7]));
+      }
+      *reinterpret_cast<uint4*>(o + C) = v;
     }
-    *reinterpret_cast<uint4*>(o + C) = v;
   }
 }
 
@@ -380,10 +389,16 @@ extern "C" int snvc_cost_volume_fwd(const void* left, const void* right, const v
     const int wtiles = (int)ceil_div(W, TW);
     size_t smem = need(TW, S);
     if (smem > 220 * 1024) return fail(SNVC_E_UNSUPPORTED, "cost volume tile does not fit shared memory");
-    int64_t base = H * N * wtiles;
+    // split D so the grid fills whole waves (2 CTAs/SM at ~80 KB smem): few splits = little re-staging
+    const int64_t base = H * N * wtiles;
+    const double wave = 2.0 * sm_count();
     int dsplit = 1;
-    const int64_t want = 8ll * 2 * sm_count();
-    while (base * dsplit < want && dsplit < D) ++dsplit;
+    double best_eff = -1;
+    for (int cand = 1; cand <= 8 && cand <= D; ++cand) {
+      const double x = base * (double)ceil_div(D, ceil_div(D, cand)) / wave;
+      const double eff = x / ceil(x) - 0.01 * cand;
+      if (eff > best_eff + 1e-9) { best_eff = eff; dsplit = cand; }
+    }
     int d_per = (int)ceil_div(D, dsplit);
     dsplit = (int)ceil_div(D, d_per);
     SNVC_CHECK_ARG((int64_t)dsplit * wtiles <= 65535, "grid.z too large");
@@ -392,7 +407,7 @@ extern "C" int snvc_cost_volume_fwd(const void* left, const void* right, const v
     int mask = 1;  // largest 2^k - 1 (k <= 3) with 2^k | C/4
     while (mask < 7 && ((C / 4) % (2 * (mask + 1))) == 0) mask = 2 * mask + 1;
     dim3 grid((unsigned)H, (unsigned)N, (unsigned)(dsplit * wtiles));
-    cv_ndhwc_bf16_kernel<<<grid, 256, smem, stream>>>((const float*)left, (const float*)right, (const float*)shift,
+    cv_ndhwc_bf16_kernel<<<grid, 512, smem, stream>>>((const float*)left, (const float*)right, (const float*)shift,
                                                        (__nv_bfloat16*)cost, (int)C, (int)IH, (int)IW, (int)D, (int)H,
                                                        (int)W, ds, d_per, dsplit, TW, S, mask);
     return launch_status("cv_ndhwc_bf16_kernel");

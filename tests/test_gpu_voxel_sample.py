@@ -111,8 +111,10 @@ def test_lift_vs_oracle(ac):
                           layout_out="NDHWC")
     assert np.array_equal(got3.permute(0, 4, 1, 2, 3).cpu().numpy(), want)
     got4 = F.frustum_lift(v16, tp, zs, ys, xs, geom.cv_ranges(), ac, layout_in="NDHWC")
-    assert got4.dtype == torch.bfloat16
-    assert np.array_equal(got4.float().permute(0, 4, 1, 2, 3).cpu().numpy(), synth.bf16_round(want))
+    assert got4.dtype == torch.bfloat16          # product path: FMA accumulation, then one bf16 rounding
+    g4 = got4.float().permute(0, 4, 1, 2, 3).cpu().numpy()
+    assert np.max(np.abs(g4 - want)) <= 2.0 ** -8 * np.max(np.abs(want)) + 1e-6
+    assert np.array_equal(g4 == 0, want == 0)    # identical support (validity mask + zero padding)
 
 
 @pytest.mark.parametrize("ac", [True, False])
