@@ -457,6 +457,7 @@ struct HaloParams {
   // SWIZZLE_64B tile read in 32-byte K-slices is 2-way bank conflicted, measured 89 vs 57 cycles/MMA)
   int sub_row_bytes, nsub, sub_tile_bytes, w_sub_bytes;
   int bo_mode;
+  int w_rows_per_tap, w_row0;  // packed-weight rows per tap (full CoutPad) and first row of this launch's Cout slice
   const float* scale;
   const float* bias;
   EpiParams epi;
@@ -661,8 +662,10 @@ __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-template <int KSTEPS, int SUBROW>
-__global__ void __launch_bounds__(kThreads, 1)
+// TCOLS = TMEM columns this CTA allocates: 512 (one CTA per SM) or 256 (two co-resident CTAs per SM:
+// while one CTA's MMA warp does its per-plane bookkeeping the other CTA's MMAs keep the tensor pipe busy).
+template <int KSTEPS, int SUBROW, int CP, int TCOLS>
+__global__ void __launch_bounds__(kThreads, TCOLS == 512 ? 1 : 2)
 conv3d_kdfuse_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                      const __grid_constant__ HaloParams p) {
   constexpr int K = 3;
@@ -678,8 +681,11 @@ conv3d_kdfuse_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   constexpr int K3 = 27;
-  const int CP = p.epi.CoutPad;
-  const uint32_t R = 512u / (uint32_t)CP;                 // accumulator blocks in the TMEM ring
+  constexpr uint32_t R = (uint32_t)TCOLS / (uint32_t)CP;  // accumulator blocks in the TMEM ring (power of two, >= 8)
+  constexpr uint32_t RMASK = R - 1u;
+  constexpr uint32_t LOGR = R == 32u ? 5u : (R == 16u ? 4u : 3u);
+  static_assert(CP == 16 || CP == 32 || CP == 64, "CoutPad must be 16, 32 or 64");
+  static_assert(R == 8u || R == 16u || R == 32u, "accumulator ring must hold 8, 16 or 32 blocks");
   const uint32_t w_base = (smem_u32(smem) + 1023u) & ~1023u;
   const uint32_t slots_base = w_base + (((uint32_t)(K3 * p.w_tap_bytes) + 1023u) & ~1023u);
   const uint32_t acc_per_col = (uint32_t)p.D + 2u;        // accumulator planes per column: out[-1] .. out[D]
@@ -704,7 +710,7 @@ conv3d_kdfuse_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
-                 "r"(512u)
+                 "r"((uint32_t)TCOLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -714,13 +720,18 @@ conv3d_kdfuse_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   const uint32_t tmem_base = tmem_base_smem;
   if (warp >= 2) {                                        // zero the whole accumulator ring once
     const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    for (uint32_t c = 0; c < 512u; c += 16u) tmem_st16_zero(lane_base + c);
+    for (uint32_t c = 0; c < (uint32_t)TCOLS; c += 16u) tmem_st16_zero(lane_base + c);
     tmem_st_wait();
   }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
 
+  // All ring positions below are carried incrementally (wrap by compare / power-of-two mask): the
+  // first version recomputed `q % nslots`, `g % R`, `g / R` per plane with run-time divisors, and the
+  // ncu source page showed the MMA warp spending ~75 % of its issue slots in that integer code
+  // (MUFU.RCP division sequences) while the tensor-pipe queue (about 6 UTCHMMA deep) ran dry:
+  // ~1200 idle cycles per plane on top of the MMA time.
   if (warp == 0) {
     // ===================== TMA producer =====================
     const uint32_t wb = smem_u32(&w_bar);
@@ -729,53 +740,60 @@ conv3d_kdfuse_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
       // smem order [(kh,kw)][kd]: the three depth taps of one in-plane tap are adjacent -> one B operand of 3*Cout rows
       for (int t2 = 0; t2 < K * K; ++t2)
         for (int kd = 0; kd < K; ++kd)
-          tma_load_2d(w_base + (t2 * K + kd) * p.w_tap_bytes, &map_w, wb, 0, (kd * K * K + t2) * CP);
+          tma_load_2d(w_base + (t2 * K + kd) * p.w_tap_bytes, &map_w, wb, 0, (kd * K * K + t2) * p.w_rows_per_tap + p.w_row0);
     }
     __syncwarp();
-    uint32_t q = 0;
+    uint32_t slot = 0, phase = 0;
+    uint32_t slot_addr = slots_base;
+    int tw = blockIdx.x % p.tiles_w, rest = blockIdx.x / p.tiles_w;
     for (int col = blockIdx.x; col < p.num_cols; col += gridDim.x) {
-      int tw = col % p.tiles_w, rest = col / p.tiles_w;
-      int th = rest % p.tiles_h, n = rest / p.tiles_h;
+      const int th = rest % p.tiles_h, n = rest / p.tiles_h;
       const int w0 = tw * p.TWv - p.pad, h0 = th * p.TH - p.pad;
-      for (int ip = 0; ip < p.D; ++ip, ++q) {             // only real planes: the zero planes -1 and D contribute nothing
-        const uint32_t slot = q % (uint32_t)p.nslots, phase = (q / (uint32_t)p.nslots) & 1u;
+      for (int ip = 0; ip < p.D; ++ip) {                  // only real planes: the zero planes -1 and D contribute nothing
         mbar_wait(smem_u32(&empty_bar[slot]), phase ^ 1u);
         if (elect_one()) {
           const uint32_t fb = smem_u32(&full_bar[slot]);
           mbar_expect_tx(fb, (uint32_t)p.plane_bytes);
-          tma_load_5d(slots_base + slot * p.slot_bytes, &map_x, fb, 0, w0, h0, ip, n);
+          tma_load_5d(slot_addr, &map_x, fb, 0, w0, h0, ip, n);
         }
         __syncwarp();
+        slot_addr += (uint32_t)p.slot_bytes;
+        if (++slot == (uint32_t)p.nslots) { slot = 0; phase ^= 1u; slot_addr = slots_base; }
       }
+      const int nc = col + (int)gridDim.x;                // next column's (tw, rest) -- one division per column
+      tw = nc % p.tiles_w; rest = nc / p.tiles_w;
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    const uint32_t idesc1 = make_idesc(kTileM, CP), idesc2 = make_idesc(kTileM, 2 * CP), idesc3 = make_idesc(kTileM, 3 * CP);
+    constexpr uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CP >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    constexpr uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * CP) >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    constexpr uint32_t idesc3 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((3 * CP) >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
     const uint32_t desc_hi = (uint32_t)(make_smem_desc(0, SUBROW) >> 32);
-    const uint32_t lo_flags = 1u << 16;
+    constexpr uint32_t lo_flags = 1u << 16;
     uint32_t off_hw[K * K];
 #pragma unroll
     for (int kh = 0; kh < K; ++kh)
 #pragma unroll
       for (int kw = 0; kw < K; ++kw) off_hw[kh * K + kw] = (uint32_t)((kh * p.WP + kw) * SUBROW) >> 4;
     const uint32_t b_lo0 = ((w_base >> 4) & 0x3FFFu) | lo_flags;
-    const uint32_t b_tap = (uint32_t)p.w_tap_bytes >> 4;             // one (kd) tile
+    constexpr uint32_t b_tap = (uint32_t)(CP * KSTEPS * 32) >> 4;     // one (kd) tile: CP rows x Cin*2 bytes
+    const uint32_t a_lo0 = ((slots_base >> 4) & 0x3FFFu) | lo_flags;
+    const uint32_t a_step = (uint32_t)p.slot_bytes >> 4;
     mbar_wait(smem_u32(&w_bar), 0);
-    uint32_t q = 0, G0 = 0;
-    for (int col = blockIdx.x; col < p.num_cols; col += gridDim.x, G0 += acc_per_col) {
-      for (int pl = 0; pl < p.D; ++pl, ++q) {
-        const uint32_t slot = q % (uint32_t)p.nslots;
-        mbar_wait(smem_u32(&full_bar[slot]), (q / (uint32_t)p.nslots) & 1u);
-        // accumulator planes touched: g+2 (kd=0, out[pl+1]), g+1 (kd=1), g (kd=2, out[pl-1]);  g = G0 + pl
-        const uint32_t g = G0 + (uint32_t)pl;
-        for (uint32_t gn = (pl == 0 ? g : g + 2u); gn <= g + 2u; ++gn) {      // blocks entering the window
-          const uint32_t use = gn / R;
-          mbar_wait(smem_u32(&acc_empty_bar[(R - gn % R) % R]), (use & 1u) ^ 1u);
+    uint32_t slot = 0, phase = 0, a_plane = a_lo0;
+    uint32_t g = 0;                                       // accumulator plane index of out[pl-1] (global over columns)
+    for (int col = blockIdx.x; col < p.num_cols; col += gridDim.x) {
+      for (int pl = 0; pl < p.D; ++pl, ++g) {
+        mbar_wait(smem_u32(&full_bar[slot]), phase);
+        // accumulator planes touched: g+2 (kd=0, out[pl+1]), g+1 (kd=1), g (kd=2, out[pl-1])
+        if (pl == 0) {
+          mbar_wait(smem_u32(&acc_empty_bar[(0u - g) & RMASK]), ((g >> LOGR) & 1u) ^ 1u);
+          mbar_wait(smem_u32(&acc_empty_bar[(0u - (g + 1u)) & RMASK]), (((g + 1u) >> LOGR) & 1u) ^ 1u);
         }
+        mbar_wait(smem_u32(&acc_empty_bar[(0u - (g + 2u)) & RMASK]), (((g + 2u) >> LOGR) & 1u) ^ 1u);
         tcgen05_fence_after();
-        const uint32_t b0 = (R - (g + 2u) % R) % R;                            // block of kd = 0
+        const uint32_t b0 = (0u - (g + 2u)) & RMASK;                           // block of kd = 0
         const uint32_t n0 = min(3u, R - b0);                                   // blocks before the ring wraps
-        const uint32_t a_plane = (((slots_base + slot * p.slot_bytes) >> 4) & 0x3FFFu) | lo_flags;
         const uint32_t d0 = tmem_base + b0 * (uint32_t)CP;
         if (elect_one()) {
           if (n0 == 3u) {
@@ -798,14 +816,17 @@ conv3d_kdfuse_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
               }
           }
           umma_commit(smem_u32(&empty_bar[slot]));                                          // plane consumed
-          umma_commit(smem_u32(&acc_full_bar[(R - g % R) % R]));                            // out[pl-1] complete
+          umma_commit(smem_u32(&acc_full_bar[(0u - g) & RMASK]));                           // out[pl-1] complete
           if (pl == p.D - 1) {                                                              // column tail: out[D-1], out[D]
-            umma_commit(smem_u32(&acc_full_bar[(R - (g + 1u) % R) % R]));
-            umma_commit(smem_u32(&acc_full_bar[(R - (g + 2u) % R) % R]));
+            umma_commit(smem_u32(&acc_full_bar[(0u - (g + 1u)) & RMASK]));
+            umma_commit(smem_u32(&acc_full_bar[(0u - (g + 2u)) & RMASK]));
           }
         }
         __syncwarp();
+        a_plane += a_step;
+        if (++slot == (uint32_t)p.nslots) { slot = 0; phase ^= 1u; a_plane = a_lo0; }
       }
+      g += 2u;                                            // acc_per_col = D + 2
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
@@ -814,30 +835,32 @@ conv3d_kdfuse_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     const int r_w = row % p.WP, r_h = row / p.WP;
     const int variant = epilogue_variant(p.epi);
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
-    uint32_t G0 = 0;
-    for (int col = blockIdx.x; col < p.num_cols; col += gridDim.x, G0 += acc_per_col) {
-      int tw = col % p.tiles_w, rest = col / p.tiles_w;
-      int th = rest % p.tiles_h, n = rest / p.tiles_h;
+    const int64_t plane_vox = (int64_t)p.H * p.W;
+    uint32_t g = 0;
+    int tw = blockIdx.x % p.tiles_w, rest = blockIdx.x / p.tiles_w;
+    for (int col = blockIdx.x; col < p.num_cols; col += gridDim.x) {
+      const int th = rest % p.tiles_h, n = rest / p.tiles_h;
       const int ow = tw * p.TWv + r_w, oh = th * p.TH + r_h;
       const bool in_range = r_w < p.TWv && ow < p.W && oh < p.H;
-      const int64_t vox0 = (((int64_t)n * p.D) * p.H + oh) * p.W + ow;
-      for (uint32_t a = 0; a < acc_per_col; ++a) {          // accumulator plane a <-> output plane a - 1
-        const uint32_t g = G0 + a;
-        const uint32_t blk = (R - g % R) % R;
+      int64_t vox = (((int64_t)n * p.D) * p.H + oh) * p.W + ow - plane_vox;       // accumulator plane a <-> output plane a - 1
+      for (uint32_t a = 0; a < acc_per_col; ++a, ++g, vox += plane_vox) {
+        const uint32_t blk = (0u - g) & RMASK;
         const bool real = a >= 1u && a <= (uint32_t)p.D;
-        const int64_t vox = vox0 + (int64_t)((int)a - 1) * p.H * p.W;
         ResidualRow rr;
         residual_prefetch(p.epi, in_range && real, vox, rr);
-        mbar_wait(smem_u32(&acc_full_bar[blk]), (g / R) & 1u);
+        mbar_wait(smem_u32(&acc_full_bar[blk]), (g >> LOGR) & 1u);
         tcgen05_fence_after();
         const uint32_t taddr = lane_base + blk * (uint32_t)CP;
         if (real) epilogue_row(p.epi, variant, taddr, in_range, vox, s_scale, s_bias, rr);
+#pragma unroll
         for (int c = 0; c < CP; c += 16) tmem_st16_zero(taddr + (uint32_t)c);   // ready for its next output plane
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&acc_empty_bar[blk]));
       }
+      const int nc = col + (int)gridDim.x;
+      tw = nc % p.tiles_w; rest = nc / p.tiles_w;
     }
   }
 
@@ -845,7 +868,7 @@ conv3d_kdfuse_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TCOLS) : "memory");
   }
 }
 
@@ -956,8 +979,17 @@ int launch_conv(const void* x, const void* w_packed, const float* scale, const f
 
 
 // ---- v2 host side: returns 1 if this conv is not eligible (caller falls back to the per-tap kernel)
+// [cout0, cout0 + ncout) : the slice of output channels this launch computes (ncout = 0: all of them)
 int launch_halo(const void* x, const void* w_packed, const float* scale, const float* bias, const void* residual,
-                void* y, const snvc_conv3d_desc& d, const ConvParams& cp, cudaStream_t stream, int bo_mode) {
+                void* y, const snvc_conv3d_desc& d, const ConvParams& cp_full, cudaStream_t stream, int bo_mode,
+                int cout0 = 0, int ncout = 0) {
+  ConvParams cp = cp_full;
+  if (ncout > 0) {
+    cp.Cout = ncout; cp.CoutPad = round_up(ncout, 16);
+    cp.out_coffset += cout0; cp.res_coffset += cout0;
+    if (scale) scale += cout0;
+    if (bias) bias += cout0;
+  }
   const int hw = (d.kernel - 1) * d.dilation;
   if (d.transposed || d.stride != 1 || d.kernel != 3 || 2 * d.pad != hw) return 1;
   if (d.Do != d.Di || d.Ho != d.Hi || d.Wo != d.Wi) return 1;
@@ -972,6 +1004,7 @@ int launch_halo(const void* x, const void* w_packed, const float* scale, const f
   p.epi.out_coffset = cp.out_coffset; p.epi.res_cstride = cp.res_cstride; p.epi.res_coffset = cp.res_coffset;
   p.epi.residual = (const __nv_bfloat16*)residual; p.epi.y = y;
   p.bo_mode = bo_mode;
+  p.w_rows_per_tap = cp_full.CoutPad; p.w_row0 = cout0;
   p.sub_row_bytes = d.Cin * 2;   // single sub-tile (a 2 x SWIZZLE_32B K-split measured no faster than SWIZZLE_64B)
   p.nsub = d.Cin * 2 / p.sub_row_bytes;
   const int row_bytes = d.Cin * 2;
@@ -998,7 +1031,7 @@ int launch_halo(const void* x, const void* w_packed, const float* scale, const f
   const int64_t ncols = (int64_t)d.N * p.tiles_h * p.tiles_w;
   SNVC_CHECK_ARG(ncols < (1ll << 31), "too many tile columns");
   p.num_cols = (int)ncols;
-  const size_t smem = (size_t)w_total + (size_t)p.nslots * p.slot_bytes + 1024;
+  size_t smem = (size_t)w_total + (size_t)p.nslots * p.slot_bytes + 1024;
 
   CUtensorMap map_x, map_w;
   {
@@ -1014,7 +1047,7 @@ int launch_halo(const void* x, const void* w_packed, const float* scale, const f
     if (r != CUDA_SUCCESS) return fail((int)r, "cuTensorMapEncodeTiled(x, halo) failed with CUresult %d", (int)r);
   }
   {
-    cuuint64_t dims[2] = {(cuuint64_t)d.Cin, (cuuint64_t)K3 * cp.CoutPad};
+    cuuint64_t dims[2] = {(cuuint64_t)d.Cin, (cuuint64_t)K3 * cp_full.CoutPad};
     cuuint64_t strides[1] = {(cuuint64_t)d.Cin * 2};
     cuuint32_t box[2] = {(cuuint32_t)(p.sub_row_bytes / 2), (cuuint32_t)cp.CoutPad};
     cuuint32_t estr[2] = {1, 1};
@@ -1026,13 +1059,40 @@ int launch_halo(const void* x, const void* w_packed, const float* scale, const f
   void (*kern)(const CUtensorMap, const CUtensorMap, const HaloParams) = nullptr;
   const char* mode = getenv("SNVC_CONV_MODE");
   const bool kdfuse = d.dilation == 1 && !(mode && mode[0] == 'h');     // SNVC_CONV_MODE=halo: v2 (A/B runs)
+  if (!kdfuse && ncout > 0) return 1;                                   // Cout slicing is implemented by the kd-fused kernel only
   switch (d.Cin) {
-    case 16: kern = kdfuse ? conv3d_kdfuse_kernel<1, 32> : conv3d_halo_kernel<3, 1, 32>; break;
-    case 32: kern = kdfuse ? conv3d_kdfuse_kernel<2, 64> : conv3d_halo_kernel<3, 2, 64>; break;
-    case 64: kern = kdfuse ? conv3d_kdfuse_kernel<4, 128> : conv3d_halo_kernel<3, 4, 128>; break;
+    case 16: kern = conv3d_halo_kernel<3, 1, 32>; break;
+    case 32: kern = conv3d_halo_kernel<3, 2, 64>; break;
+    case 64: kern = conv3d_halo_kernel<3, 4, 128>; break;
+  }
+  int ctas_per_sm = 1;
+  if (kdfuse) {
+    // two CTAs per SM when weights + a 4-slot plane ring fit in half the shared memory (Cin = Cout = 32 does)
+    const size_t half_budget = (233472 - 2 * 1024) / 2 - 2048 /* static */ - 1024 /* alignment */;
+    const char* occ = getenv("SNVC_CONV_OCC");
+    if (cp.CoutPad <= 32 && (size_t)w_total + 4 * (size_t)p.slot_bytes <= half_budget && !(occ && occ[0] == '1')) {
+      ctas_per_sm = 2;
+      p.nslots = (int)std::min<size_t>(kMaxSlots, (half_budget - w_total) / p.slot_bytes);
+      smem = (size_t)w_total + (size_t)p.nslots * p.slot_bytes + 1024;
+    }
+#define SNVC_KDFUSE_T(KS, SR, T)                                                                         \
+    kern = cp.CoutPad == 16 ? conv3d_kdfuse_kernel<KS, SR, 16, T>                                        \
+                            : (cp.CoutPad == 32 ? conv3d_kdfuse_kernel<KS, SR, 32, T> : nullptr)
+#define SNVC_KDFUSE(KS, SR)                                                                              \
+    if (ctas_per_sm == 2) { SNVC_KDFUSE_T(KS, SR, 256); }                                                \
+    else if (cp.CoutPad == 64) kern = conv3d_kdfuse_kernel<KS, SR, 64, 512>;                             \
+    else { SNVC_KDFUSE_T(KS, SR, 512); }
+    switch (d.Cin) {
+      case 16: SNVC_KDFUSE(1, 32); break;
+      case 32: SNVC_KDFUSE(2, 64); break;
+      case 64: SNVC_KDFUSE(4, 128); break;
+    }
+#undef SNVC_KDFUSE
+#undef SNVC_KDFUSE_T
+    if (!kern) return 1;                                  // CoutPad 48: per-tap kernel
   }
   SNVC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = std::min(p.num_cols, sm_count());
+  const int grid = std::min(p.num_cols, ctas_per_sm * sm_count());
   kern<<<grid, kThreads, smem, stream>>>(map_x, map_w, p);
   return launch_status("conv3d_halo_kernel");
 }
@@ -1117,6 +1177,14 @@ extern "C" int snvc_conv3d_fwd(const void* x, const void* w_packed, const float*
     if (!(mode && mode[0] == 't')) {
       int r = launch_halo(x, w_packed, scale, bias, residual, y, d, p, stream, 0);
       if (r != 1) return r;
+      // 64 -> 64: all 27 weight tiles (221 KB) do not fit next to the plane ring; run the plane march twice on
+      // 32-channel output slices (the input, at most half resolution on this path, is read twice from L2/HBM)
+      if (p.CoutPad == 64 && d.Cout == 64 && d.dilation == 1 && d.kernel == 3 && d.stride == 1 &&
+          ((p.out_cstride | p.out_coffset) & 7) == 0) {
+        r = launch_halo(x, w_packed, scale, bias, residual, y, d, p, stream, 0, 0, 32);
+        if (r == 0) r = launch_halo(x, w_packed, scale, bias, residual, y, d, p, stream, 0, 32, 32);
+        if (r != 1) return r;
+      }
     }
     return launch_conv(x, w_packed, scale, bias, residual, y, d, p, stream);
   }
