@@ -116,6 +116,16 @@ int snvc_frustum_lift_fwd(const void* vol, const float* proj, const float* zs, c
                           int64_t N, int64_t C, int64_t D, int64_t H, int64_t W, int64_t Z, int64_t Y,
                           int64_t X, int32_t align_corners, int32_t in_dtype, int32_t in_layout,
                           int32_t out_dtype, int32_t out_layout, void* stream);
+/* Depth-slab variant (multi-GPU stress configuration): `vol` holds only planes
+ * [d_base, d_base + D) of a D_total-plane volume (d_base may be negative: leading halo planes);
+ * coordinates are normalised against D_total, corners outside the slab contribute zero -- the
+ * caller partitions the voxel z-range so that every needed plane is inside its slab. */
+int snvc_frustum_lift_slab_fwd(const void* vol, const float* proj, const float* zs, const float* ys,
+                               const float* xs, const float* cv_range_host, void* out, uint8_t* valid,
+                               int64_t N, int64_t C, int64_t D, int64_t H, int64_t W, int64_t Z, int64_t Y,
+                               int64_t X, int32_t align_corners, int32_t in_dtype, int32_t in_layout,
+                               int32_t out_dtype, int32_t out_layout, int64_t D_total, int64_t d_base,
+                               void* stream);
 /* Debug: floor corner (x0,y0,z0) per voxel: idx [N,Z,Y,X,3] int32, valid [N,Z,Y,X] uint8. */
 int snvc_frustum_lift_indices(const float* proj, const float* zs, const float* ys, const float* xs,
                               const float* cv_range_host, int32_t* idx, uint8_t* valid, int64_t N,

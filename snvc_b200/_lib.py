@@ -31,6 +31,8 @@ _SIGS = {
     "snvc_roi_voxel_sample_fwd": ([_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _f, _f, _i32, _i32, _p], _i32),
     "snvc_roi_voxel_sample_indices": ([_p, _p, _p, _i64, _i64, _i64, _i64, _f, _f, _p], _i32),
     "snvc_frustum_lift_fwd": ([_p, _p, _p, _p, _p, ctypes.POINTER(_f), _p, _p] + [_i64] * 8 + [_i32] * 5 + [_p], _i32),
+    "snvc_frustum_lift_slab_fwd": ([_p, _p, _p, _p, _p, ctypes.POINTER(_f), _p, _p] + [_i64] * 8 + [_i32] * 5 + [_i64, _i64, _p],
+                                   _i32),
     "snvc_frustum_lift_indices": ([_p, _p, _p, _p, ctypes.POINTER(_f), _p, _p] + [_i64] * 7 + [_i32, _p], _i32),
     "snvc_conv3d_packed_weight_bytes": ([_i32, _i32, _i32], _i64),
     "snvc_conv3d_pack_weights": ([_p, _p, _i32, _i32, _i32, _i32, _p], _i32),

@@ -166,7 +166,8 @@ __global__ void roi_indices_kernel(const float* __restrict__ pts, int32_t* __res
 // ---- A4: frustum-to-voxel lift --------------------------------------------------------------
 struct LiftGeom {
   float cv[6];   // CV_X_MIN, CV_X_MAX, CV_Y_MIN, CV_Y_MAX, CV_Z_MIN, CV_Z_MAX
-  int D, H, W;   // volume extent (z-bins, rows, cols)
+  int D, H, W;   // extent of the volume tensor passed in (z-bins, rows, cols)
+  int Dt, d_base;// depth-slab mode: the tensor holds planes [d_base, d_base + D) of a Dt-plane volume (else Dt = D, 0)
   int Z, Y, X;   // voxel grid extent
   int align_corners;
 };
@@ -197,7 +198,7 @@ __device__ __forceinline__ Trilinear trilinear_setup(const float* __restrict__ P
   if (!(fabsf(gx) < 1e9f) || !(fabsf(gy) < 1e9f) || !(fabsf(gz) < 1e9f)) { gx = gy = gz = -2.f; }  // oracle: non-finite -> -2
   float ix = unnormalize(gx, g.W, g.align_corners);
   float iy = unnormalize(gy, g.H, g.align_corners);
-  float iz = unnormalize(gz, g.D, g.align_corners);
+  float iz = unnormalize(gz, g.Dt, g.align_corners);
   float fx0 = floorf(ix), fy0 = floorf(iy), fz0 = floorf(iz);
   t.x0 = (int)fx0; t.y0 = (int)fy0; t.z0 = (int)fz0;
   t.wx[0] = __fsub_rn(__fadd_rn(fx0, 1.f), ix); t.wx[1] = __fsub_rn(ix, fx0);
@@ -232,7 +233,7 @@ lift_ndhwc_kernel(const __nv_bfloat16* __restrict__ vol, const float* __restrict
     unsigned m = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {   // tnw,tne,tsw,tse,bnw,bne,bsw,bse
-      const int xx = t.x0 + (k & 1), yy = t.y0 + ((k >> 1) & 1), zz = t.z0 + (k >> 2);
+      const int xx = t.x0 + (k & 1), yy = t.y0 + ((k >> 1) & 1), zz = t.z0 + (k >> 2) - g.d_base;
       const bool in = t.valid && xx >= 0 && xx < g.W && yy >= 0 && yy < g.H && zz >= 0 && zz < g.D;
       m |= in ? (1u << k) : 0u;
       off[k] = in ? (((int64_t)zz * g.H + yy) * g.W + xx) * C : 0;
@@ -302,7 +303,7 @@ lift_ncdhw_kernel(const float* __restrict__ vol, const float* __restrict__ proj,
     unsigned m = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      int xx = t.x0 + (k & 1), yy = t.y0 + ((k >> 1) & 1), zz = t.z0 + (k >> 2);
+      int xx = t.x0 + (k & 1), yy = t.y0 + ((k >> 1) & 1), zz = t.z0 + (k >> 2) - g.d_base;
       bool in = t.valid && xx >= 0 && xx < g.W && yy >= 0 && yy < g.H && zz >= 0 && zz < g.D;
       m |= in ? (1u << k) : 0u;
       off[k] = in ? ((int64_t)zz * g.H + yy) * g.W + xx : 0;
@@ -409,19 +410,22 @@ static int make_geom(LiftGeom& g, const float* cv, int64_t D, int64_t H, int64_t
                  "dimension too large");
   for (int i = 0; i < 6; ++i) g.cv[i] = cv[i];
   g.D = (int)D; g.H = (int)H; g.W = (int)W; g.Z = (int)Z; g.Y = (int)Y; g.X = (int)X;
+  g.Dt = (int)D; g.d_base = 0;
   g.align_corners = ac ? 1 : 0;
   return 0;
 }
 
-extern "C" int snvc_frustum_lift_fwd(const void* vol, const float* proj, const float* zs, const float* ys,
-                                     const float* xs, const float* cv_range_host, void* out, uint8_t* valid, int64_t N,
-                                     int64_t C, int64_t D, int64_t H, int64_t W, int64_t Z, int64_t Y, int64_t X,
-                                     int32_t align_corners, int32_t in_dtype, int32_t in_layout, int32_t out_dtype,
-                                     int32_t out_layout, void* stream_) {
+static int lift_fwd_impl(const void* vol, const float* proj, const float* zs, const float* ys, const float* xs,
+                         const float* cv_range_host, void* out, uint8_t* valid, int64_t N, int64_t C, int64_t D,
+                         int64_t H, int64_t W, int64_t Z, int64_t Y, int64_t X, int32_t align_corners, int32_t in_dtype,
+                         int32_t in_layout, int32_t out_dtype, int32_t out_layout, int64_t D_total, int64_t d_base,
+                         void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (N == 0) return 0;
+  if (N == 0 || Z == 0) return 0;
   LiftGeom g;
   if (int e = make_geom(g, cv_range_host, D, H, W, Z, Y, X, align_corners)) return e;
+  SNVC_CHECK_ARG(D_total > 0 && D_total < (1 << 20) && d_base > -(1 << 20) && d_base < (1 << 20), "bad depth-slab range");
+  g.Dt = (int)D_total; g.d_base = (int)d_base;
   SNVC_CHECK_ARG(vol && proj && zs && ys && xs && out, "null pointer");
   SNVC_CHECK_ARG(N > 0 && C > 0, "bad N / C");
   const int64_t nvox = N * Z * Y * X;
@@ -451,6 +455,25 @@ extern "C" int snvc_frustum_lift_fwd(const void* vol, const float* proj, const f
     return launch_status("lift_ncdhw_kernel");
   }
   return fail(SNVC_E_UNSUPPORTED, "lift: supported inputs are NDHWC bf16 and NCDHW f32");
+}
+
+extern "C" int snvc_frustum_lift_fwd(const void* vol, const float* proj, const float* zs, const float* ys,
+                                     const float* xs, const float* cv_range_host, void* out, uint8_t* valid, int64_t N,
+                                     int64_t C, int64_t D, int64_t H, int64_t W, int64_t Z, int64_t Y, int64_t X,
+                                     int32_t align_corners, int32_t in_dtype, int32_t in_layout, int32_t out_dtype,
+                                     int32_t out_layout, void* stream_) {
+  return lift_fwd_impl(vol, proj, zs, ys, xs, cv_range_host, out, valid, N, C, D, H, W, Z, Y, X, align_corners, in_dtype,
+                       in_layout, out_dtype, out_layout, D, 0, stream_);
+}
+
+extern "C" int snvc_frustum_lift_slab_fwd(const void* vol, const float* proj, const float* zs, const float* ys,
+                                          const float* xs, const float* cv_range_host, void* out, uint8_t* valid,
+                                          int64_t N, int64_t C, int64_t D, int64_t H, int64_t W, int64_t Z, int64_t Y,
+                                          int64_t X, int32_t align_corners, int32_t in_dtype, int32_t in_layout,
+                                          int32_t out_dtype, int32_t out_layout, int64_t D_total, int64_t d_base,
+                                          void* stream_) {
+  return lift_fwd_impl(vol, proj, zs, ys, xs, cv_range_host, out, valid, N, C, D, H, W, Z, Y, X, align_corners, in_dtype,
+                       in_layout, out_dtype, out_layout, D_total, d_base, stream_);
 }
 
 extern "C" int snvc_frustum_lift_indices(const float* proj, const float* zs, const float* ys, const float* xs,

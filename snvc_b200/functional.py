@@ -66,12 +66,13 @@ def _cv(cv_range):
 
 
 def frustum_lift(vol, proj, zs, ys, xs, cv_range, align_corners=True, layout_in="NCDHW", out_dtype=None,
-                 layout_out=None, return_valid=False):
+                 layout_out=None, return_valid=False, d_total=None, d_base=0):
     """Trilinear frustum -> world-voxel lift with the sampling grid computed in-kernel.
 
     vol: [N,C,D,H,W] fp32 (layout_in 'NCDHW') or [N,D,H,W,C] bf16 ('NDHWC'); proj [N,3,4] fp32;
     zs/ys/xs voxel-centre vectors; cv_range = (CV_X_MIN, CV_X_MAX, CV_Y_MIN, CV_Y_MAX, CV_Z_MIN, CV_Z_MAX).
-    Returns [N,C,Z,Y,X] ('NCDHW') or [N,Z,Y,X,C] ('NDHWC')."""
+    Returns [N,C,Z,Y,X] ('NCDHW') or [N,Z,Y,X,C] ('NDHWC').
+    Depth-slab mode: `vol` holds planes [d_base, d_base + D) of a `d_total`-plane volume."""
     _lib.require_cuda(vol, proj, zs, ys, xs)
     vol = vol.contiguous()
     proj, zs, ys, xs = (t.contiguous().float() for t in (proj, zs, ys, xs))
@@ -88,12 +89,13 @@ def frustum_lift(vol, proj, zs, ys, xs, cv_range, align_corners=True, layout_in=
     out = torch.empty(shape, dtype=out_dtype, device=vol.device)
     valid = torch.empty((N, Z, Y, X), dtype=torch.uint8, device=vol.device) if return_valid else None
     with torch.cuda.device(vol.device):
-        st = _lib.lib().snvc_frustum_lift_fwd(vol.data_ptr(), proj.data_ptr(), zs.data_ptr(), ys.data_ptr(),
-                                              xs.data_ptr(), _cv(cv_range), out.data_ptr(),
-                                              valid.data_ptr() if valid is not None else None, N, C, D, H, W, Z, Y, X,
-                                              int(bool(align_corners)), _dt(vol.dtype), lin, _dt(out_dtype), lout,
-                                              _lib.stream_ptr())
-    _lib.check(st, "snvc_frustum_lift_fwd")
+        st = _lib.lib().snvc_frustum_lift_slab_fwd(vol.data_ptr(), proj.data_ptr(), zs.data_ptr(), ys.data_ptr(),
+                                                   xs.data_ptr(), _cv(cv_range), out.data_ptr(),
+                                                   valid.data_ptr() if valid is not None else None, N, C, D, H, W, Z,
+                                                   Y, X, int(bool(align_corners)), _dt(vol.dtype), lin, _dt(out_dtype),
+                                                   lout, D if d_total is None else int(d_total), int(d_base),
+                                                   _lib.stream_ptr())
+    _lib.check(st, "snvc_frustum_lift_slab_fwd")
     return (out, valid) if return_valid else out
 
 

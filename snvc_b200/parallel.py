@@ -1,0 +1,216 @@
+"""Multi-GPU partitioning of the hot path: one process per GPU (torchrun), torch.distributed plumbing.
+
+The reference's only parallelism is single-process `nn.DataParallel` over the batch dimension
+(tools/inference_agnostic.py:472: scatter proposals, replicate the model, gather on GPU 0).  Here:
+
+* pairs (global branch) and proposals (instance branch) are independent units -> each rank takes a
+  contiguous block (`shard_range`), weights are replicated, NO collective on the data path;
+  `gather_outputs` reproduces DataParallel's gather for callers that want it;
+* the single-volume stress case splits the DEPTH axis into slabs (`DepthSlab`): cost-volume bins are
+  independent (BuildCostVolume_cuda.cu:84), every 3x3x3 conv needs neighbour planes, exchanged with
+  point-to-point sends between ranks r-1 / r+1 (`exchange_depth_halo`; NCCL over NVLink on GPUs,
+  gloo in the CPU tests), the lift is partitioned by the world-z range each slab covers.
+
+`SlabTrunk` drives any module tree with the layer interface of snvc_b200.models.submodule
+(`.fused(x, relu=, residual=, residual_mode=, out=)` on NDHWC tensors), so the slab algebra is
+testable on CPU with a plain-torch layer executor (tests/test_parallel_gloo.py).
+"""
+import torch
+import torch.distributed as dist
+
+HALO = 2   # halo planes kept on each side of a slab (1 is needed by a 3^3 conv; 2 keeps stride-2 levels aligned)
+
+
+# ------------------------------------------------------------------------------------ batch sharding
+def shard_range(n, world, rank):
+    """Contiguous block [lo, hi) of `n` units for `rank`: the first n % world ranks get one extra."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError(f"bad world/rank {world}/{rank}")
+    base, extra = divmod(int(n), world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_batch(tensors, world, rank):
+    """Slice every tensor of `tensors` (all with the same leading dim) to this rank's block."""
+    n = tensors[0].shape[0]
+    lo, hi = shard_range(n, world, rank)
+    return [t[lo:hi] for t in tensors]
+
+
+def gather_outputs(local, n_total, group=None):
+    """all_gather ragged leading-dim shards (as produced by `shard_range`) -> [n_total, ...] on every rank."""
+    world = dist.get_world_size(group)
+    sizes = [shard_range(n_total, world, r) for r in range(world)]
+    width = max(hi - lo for lo, hi in sizes)
+    pad = torch.zeros((width,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    return torch.cat([b[:hi - lo] for b, (lo, hi) in zip(bufs, sizes)], dim=0)
+
+
+# ------------------------------------------------------------------------------------ depth slabs
+class DepthSlab:
+    """Rank `rank`'s slab of a D-plane volume split over `world` ranks.
+
+    Slab boundaries are multiples of 4 (two stride-2 levels below the full resolution), every slab
+    has at least 4*HALO planes so the 1/4-resolution level still owns HALO real planes to send."""
+
+    def __init__(self, D, world, rank):
+        if D % (4 * world) != 0:
+            raise ValueError(f"depth {D} must be a multiple of 4*world ({4 * world})")
+        self.D, self.world, self.rank = D, world, rank
+        self.Dl = D // world
+        if world > 1 and self.Dl < 4 * HALO:
+            raise ValueError(f"slab of {self.Dl} planes is thinner than {4 * HALO}")
+        self.d0 = rank * self.Dl
+
+    @property
+    def first(self):
+        return self.rank == 0
+
+    @property
+    def last(self):
+        return self.rank == self.world - 1
+
+    def ext_bins(self):
+        """Global plane indices of the extended slab [d0-HALO, d0+Dl+HALO) (may fall outside [0, D))."""
+        return list(range(self.d0 - HALO, self.d0 + self.Dl + HALO))
+
+
+def exchange_depth_halo(x, slab, group=None):
+    """x: [1, Dl_level + 2*HALO, H, W, C] extended slab at any pyramid level (in place).
+
+    Sends the first / last HALO real planes to the previous / next rank, receives their halos; at the
+    global boundary the halo planes are zeroed (they stand for the convolution's zero padding)."""
+    h = HALO
+    if x.shape[1] < 3 * h:
+        raise ValueError("slab too thin for the halo exchange")
+    ops, recv_lo, recv_hi = [], None, None
+    # gloo moves host memory only: stage through the CPU there (tests); NCCL sends device buffers over NVLink
+    stage = slab.world > 1 and x.is_cuda and dist.get_backend(group) == "gloo"
+    if slab.world > 1:
+        if not slab.first:
+            send_lo = x[:, h:2 * h].contiguous()
+            if stage:
+                send_lo = send_lo.cpu()
+            recv_lo = torch.empty_like(send_lo)
+            ops += [dist.P2POp(dist.isend, send_lo, _peer(slab.rank - 1, group), group),
+                    dist.P2POp(dist.irecv, recv_lo, _peer(slab.rank - 1, group), group)]
+        if not slab.last:
+            send_hi = x[:, -2 * h:-h].contiguous()
+            if stage:
+                send_hi = send_hi.cpu()
+            recv_hi = torch.empty_like(send_hi)
+            ops += [dist.P2POp(dist.isend, send_hi, _peer(slab.rank + 1, group), group),
+                    dist.P2POp(dist.irecv, recv_hi, _peer(slab.rank + 1, group), group)]
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    if recv_lo is not None:
+        x[:, :h] = recv_lo.to(x.device)
+    else:
+        x[:, :h] = 0
+    if recv_hi is not None:
+        x[:, -h:] = recv_hi.to(x.device)
+    else:
+        x[:, -h:] = 0
+    return x
+
+
+def _peer(rank_in_group, group):
+    return dist.get_global_rank(group, rank_in_group) if group is not None else rank_in_group
+
+
+class SlabTrunk:
+    """The global trunk (dres0 / dres1 / hourglass, models/stereonet.py) on one depth slab, with a halo
+    exchange after every layer.  `model` needs attributes dres0, dres1, hg with the fused-layer
+    interface; tensors are NDHWC with N == 1 (depth slices of an N=1 volume are contiguous views)."""
+
+    def __init__(self, model, slab, group=None):
+        self.m, self.slab, self.group = model, slab, group
+
+    def _xchg(self, x):
+        return exchange_depth_halo(x, self.slab, self.group)
+
+    def _s1(self, layer, x, **kw):
+        return self._xchg(layer.fused(x, **kw))
+
+    def _s2(self, layer, x, **kw):
+        """stride-2 conv: ext [1, Dl+4, ...] -> ext [1, Dl/2+4, ...]; the conv output (Dl/2+2 planes, plane o
+        centred on ext input plane 2o) is written into planes [1, -1) of the half-resolution slab."""
+        N, De, H, W, _ = x.shape
+        assert N == 1 and (De - 2 * HALO) % 2 == 0
+        Do = (De - 2 * HALO) // 2 + 2 * HALO
+        cout = getattr(layer, "cout", None) or layer[0][0].out_channels
+        out = torch.zeros((1, Do, (H + 1) // 2, (W + 1) // 2, cout), dtype=x.dtype, device=x.device)
+        layer.fused(x, out=out[:, 1:-1], **kw)
+        return self._xchg(out)
+
+    def _up(self, layer, x, **kw):
+        """transposed conv (k3,s2,p1,op1): input planes [1, -1) of the ext slab -> ext slab at 2x resolution."""
+        return self._xchg(layer.fused(x[:, 1:-1], **kw))
+
+    def __call__(self, cost):
+        """cost: extended cost-volume slab [1, Dl+2*HALO, H, W, 2F] (halo planes already valid or zero)."""
+        m = self.m
+        x = self._s1(m.dres0[0], cost)
+        x = self._s1(m.dres0[1], x)
+        y = self._s1(m.dres1[0], x)
+        x = self._s1(m.dres1[1], y, residual=x, residual_mode=1)
+        hg = m.hg
+        o = self._s2(hg.conv1, x)
+        pre = self._s1(hg.conv2, o, relu=True)
+        o = self._s2(hg.conv3, pre)
+        o = self._s1(hg.conv4, o)
+        post = self._up(hg.conv5, o, relu=True, residual=pre, residual_mode=1)
+        return self._up(hg.conv6, post, residual=x, residual_mode=1)
+
+
+def slab_z_range(zs, cv_z_min, cv_z_max, D, slab, align_corners=True):
+    """Voxel z-indices [zlo, zhi) whose lower depth-plane index floor(iz) falls into this slab
+    (host float64 estimate; the slab's HALO planes absorb any fp32 disagreement with the kernel).
+    Voxels in front of / behind the volume go to the first / last slab."""
+    import numpy as np
+    z = np.asarray(zs, dtype=np.float64)
+    g = (z - cv_z_min) / (cv_z_max - cv_z_min) * 2 - 1
+    iz = (g + 1) / 2 * (D - 1) if align_corners else ((g + 1) * D - 1) / 2
+    plane = np.clip(np.floor(iz), 0, D - 1).astype(np.int64)
+    owner = np.minimum(plane // slab.Dl, slab.world - 1)
+    idx = np.nonzero(owner == slab.rank)[0]
+    if idx.size == 0:
+        return 0, 0
+    assert np.all(np.diff(idx) == 1), "voxel z centres must be monotonic in depth"
+    return int(idx[0]), int(idx[-1]) + 1
+
+
+def slab_global_forward(model, left_feat, right_feat, shift, proj, slab, group=None, out_dtype=torch.float32,
+                        layout_out="NCDHW"):
+    """Depth-slab-parallel GlobalHotPath.forward for ONE pair (N == 1).
+
+    Every rank passes the same (replicated) inputs and returns (voxels[:, zlo:zhi] slice, (zlo, zhi)):
+    its slice of the lifted voxel grid along Z (layout as `GlobalHotPath.forward`)."""
+    from snvc_b200 import functional as SF
+    from snvc_b200.extension.build_cost_volume import build_cost_volume_ndhwc_bf16
+    if left_feat.shape[0] != 1:
+        raise RuntimeError("slab_global_forward handles one pair (the stress configuration)")
+    D = shift.shape[1]
+    if D != slab.D:
+        raise RuntimeError("shift / slab depth mismatch")
+    bins = slab.ext_bins()
+    keep = [b for b in bins if 0 <= b < D]
+    cost_in = build_cost_volume_ndhwc_bf16(left_feat, right_feat, shift[:, keep[0]:keep[-1] + 1].contiguous(), 1)
+    lo_pad, hi_pad = keep[0] - bins[0], bins[-1] - keep[-1]
+    if lo_pad or hi_pad:
+        cost = torch.zeros((1, len(bins)) + tuple(cost_in.shape[2:]), dtype=cost_in.dtype, device=cost_in.device)
+        cost[:, lo_pad:lo_pad + len(keep)] = cost_in
+    else:
+        cost = cost_in
+    feat = SlabTrunk(model, slab, group)(cost)                        # [1, Dl+2*HALO, H, W, ch]
+    zlo, zhi = slab_z_range(model.zs.cpu().numpy(), model.cv_range[4], model.cv_range[5], D, slab,
+                            model.align_corners)
+    vox = SF.frustum_lift(feat, proj, model.zs[zlo:zhi].contiguous(), model.ys, model.xs, model.cv_range,
+                          model.align_corners, layout_in="NDHWC", out_dtype=out_dtype, layout_out=layout_out,
+                          d_total=D, d_base=bins[0])
+    return vox, (zlo, zhi)
