@@ -872,6 +872,299 @@ conv3d_kdfuse_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   }
 }
 
+// ==========================================================================================
+// v4: fused transposed convolution (k3, s2, p1, output_padding 1) -- all 8 output-parity classes
+// of an input tile in ONE kernel (the per-tap path above launches 8 kernels, each re-reading the
+// input through per-tap TMA boxes and writing a stride-2 quarter of the output).
+//
+//   out[2j+p] (per dim) = p == 0 ?  x[j] * W[1]  :  x[j] * W[2] + x[j+1] * W[0]
+//
+// A CTA marches along the INPUT depth of a (TH x TWv) patch; plane j (and j+1) sit in the same
+// kind of dense-row shared-memory ring as the plane-march conv kernels, so the +1 shifts in h / w
+// are UMMA descriptor row offsets (TWv = WP - 1 valid columns) and the +1 shift in d is "the next
+// ring slot".  For a shift s = (sd,sh,sw) the classes p >= s (componentwise) all read the same A
+// window; classes that are adjacent in TMEM (class c = pd*4 + ph*2 + pw at columns c*32) are fused
+// into one instruction: N = 256 (s=000), 128 (s=100), 64, 32 ... -- 14 MMAs per K=16 step instead of
+// 27.  All 27 weight tiles (32 output channels) stay resident; 2 x 256 TMEM columns double-buffer
+// the 8 class accumulators so the epilogue of tile-step j overlaps the MMAs of j+1.  Eight
+// epilogue warps (two per TMEM lane quadrant, four classes each) prefetch their residual rows
+// before waiting for the accumulator and write each output voxel row (64 B) exactly once.
+// Cout = 64 runs as two 32-channel output slices (weights 2 x 110 KB).
+// ==========================================================================================
+constexpr int kDeconvThreads = 320;      // producer, MMA issuer, 8 epilogue warps
+constexpr int kDeconvCP = 32;
+
+struct DeconvParams {
+  int N, Cin;
+  int Di, Hi, Wi;              // input extent (output is 2x)
+  int WP, TH, TWv;             // row pitch, tile rows (WP*TH == 128), valid columns = WP - 1
+  int tiles_h, tiles_w;
+  int DC, nchunk;              // depth chunk per work unit
+  int num_units;
+  int plane_bytes, slot_bytes, nslots;
+  int w_tap_bytes;             // 32 * Cin * 2
+  int w_rows_per_tap, w_row0;
+  const float* scale;
+  const float* bias;
+  EpiParams epi;
+};
+
+// static fusion schedule: shift s = sd*4 + sh*2 + sw; classes(s) = {c : (c & s) == s} ascending
+struct DeconvRun { unsigned char s, c0, len, tile0; };
+__device__ constexpr DeconvRun kDeconvRuns[14] = {
+    {0, 0, 8, 0},
+    {1, 1, 1, 8}, {1, 3, 1, 9}, {1, 5, 1, 10}, {1, 7, 1, 11},
+    {2, 2, 2, 12}, {2, 6, 2, 14},
+    {3, 3, 1, 16}, {3, 7, 1, 17},
+    {4, 4, 4, 18},
+    {5, 5, 1, 22}, {5, 7, 1, 23},
+    {6, 6, 2, 24},
+    {7, 7, 1, 26}};
+// smem tile t -> (s, c); kernel tap per dim: shift 1 -> k = 0; shift 0 -> k = (class bit ? 2 : 1)
+__device__ constexpr unsigned char kDeconvTileS[27] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3,
+                                                       4, 4, 4, 4, 5, 5, 6, 6, 7};
+__device__ constexpr unsigned char kDeconvTileC[27] = {0, 1, 2, 3, 4, 5, 6, 7, 1, 3, 5, 7, 2, 3, 6, 7, 3, 7,
+                                                       4, 5, 6, 7, 5, 7, 6, 7, 7};
+__device__ __forceinline__ int deconv_tap_of_tile(int t) {
+  const int s = kDeconvTileS[t], c = kDeconvTileC[t];
+  int tap = 0;
+#pragma unroll
+  for (int dim = 2; dim >= 0; --dim) {        // dim 2 = d (bit 2), 1 = h, 0 = w
+    const int sb = (s >> dim) & 1, cb = (c >> dim) & 1;
+    tap = tap * 3 + (sb ? 0 : (cb ? 2 : 1));
+  }
+  return tap;
+}
+
+struct ResidualRow32 { uint4 q[4]; };
+
+__device__ __forceinline__ void epilogue_chunk16_r32(const uint32_t* acc, int cc, const float* s_scale, const float* s_bias,
+                                                     const ResidualRow32& rr, const EpiFast f, __nv_bfloat16* yrow) {
+  float v[16];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 sc = *reinterpret_cast<const float4*>(s_scale + cc + 4 * q);
+    const float4 bi = *reinterpret_cast<const float4*>(s_bias + cc + 4 * q);
+    v[4 * q + 0] = fmaf(__uint_as_float(acc[4 * q + 0]), sc.x, bi.x);
+    v[4 * q + 1] = fmaf(__uint_as_float(acc[4 * q + 1]), sc.y, bi.y);
+    v[4 * q + 2] = fmaf(__uint_as_float(acc[4 * q + 2]), sc.z, bi.z);
+    v[4 * q + 3] = fmaf(__uint_as_float(acc[4 * q + 3]), sc.w, bi.w);
+  }
+  const uint4 q0 = rr.q[cc >> 3], q1 = rr.q[(cc >> 3) + 1];
+  const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float r0 = bf16_lo(w[j]), r1 = bf16_hi(w[j]);
+    v[2 * j] = fmaf(r0, f.m2, fmaxf(fmaf(r0, f.m1, v[2 * j]), f.lo));
+    v[2 * j + 1] = fmaf(r1, f.m2, fmaxf(fmaf(r1, f.m1, v[2 * j + 1]), f.lo));
+  }
+  uint4* o = reinterpret_cast<uint4*>(yrow + cc);
+  o[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  o[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+}
+
+template <int KSTEPS, int SUBROW>
+__global__ void __launch_bounds__(kDeconvThreads, 1)
+conv3d_deconv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                     const __grid_constant__ DeconvParams p) {
+  constexpr int CP = kDeconvCP;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxSlots];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxSlots];
+  __shared__ __align__(8) uint64_t w_bar;
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(16) float s_scale[32], s_bias[32];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t w_base = (smem_u32(smem) + 1023u) & ~1023u;
+  const uint32_t slots_base = w_base + (((uint32_t)(27 * p.w_tap_bytes) + 1023u) & ~1023u);
+
+  if (threadIdx.x < 32) {
+    s_scale[threadIdx.x] = p.scale ? p.scale[threadIdx.x] : 1.f;
+    s_bias[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    for (int s = 0; s < p.nslots; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(&w_bar), 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&tmem_full_bar[b]), 1);
+      mbar_init(smem_u32(&tmem_empty_bar[b]), 8);          // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  // work unit -> (n, th, tw, depth chunk); planes j0 .. j0+nj-1 are tile-steps, plane j0+nj is loaded if it exists
+  auto decode = [&](int unit, int& n, int& h0, int& w0, int& j0, int& nj) {
+    const int ch = unit % p.nchunk; unit /= p.nchunk;
+    const int tw = unit % p.tiles_w; unit /= p.tiles_w;
+    const int th = unit % p.tiles_h; n = unit / p.tiles_h;
+    h0 = th * p.TH; w0 = tw * p.TWv; j0 = ch * p.DC; nj = min(p.DC, p.Di - j0);
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    const uint32_t wb = smem_u32(&w_bar);
+    if (elect_one()) {
+      mbar_expect_tx(wb, (uint32_t)(27 * p.w_tap_bytes));
+      for (int t = 0; t < 27; ++t)
+        tma_load_2d(w_base + t * p.w_tap_bytes, &map_w, wb, 0, deconv_tap_of_tile(t) * p.w_rows_per_tap + p.w_row0);
+    }
+    __syncwarp();
+    uint32_t slot = 0, phase = 0, slot_addr = slots_base;
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+      int n, h0, w0, j0, nj;
+      decode(unit, n, h0, w0, j0, nj);
+      const int nload = nj + ((j0 + nj < p.Di) ? 1 : 0);
+      for (int i = 0; i < nload; ++i) {
+        mbar_wait(smem_u32(&empty_bar[slot]), phase ^ 1u);
+        if (elect_one()) {
+          const uint32_t fb = smem_u32(&full_bar[slot]);
+          mbar_expect_tx(fb, (uint32_t)p.plane_bytes);
+          tma_load_5d(slot_addr, &map_x, fb, 0, w0, h0, j0 + i, n);
+        }
+        __syncwarp();
+        slot_addr += (uint32_t)p.slot_bytes;
+        if (++slot == (uint32_t)p.nslots) { slot = 0; phase ^= 1u; slot_addr = slots_base; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t desc_hi = (uint32_t)(make_smem_desc(0, SUBROW) >> 32);
+    constexpr uint32_t lo_flags = 1u << 16;
+    const uint32_t b_lo0 = ((w_base >> 4) & 0x3FFFu) | lo_flags;
+    constexpr uint32_t b_tap = (uint32_t)(CP * KSTEPS * 32) >> 4;
+    const uint32_t a_lo0 = ((slots_base >> 4) & 0x3FFFu) | lo_flags;
+    const uint32_t a_step = (uint32_t)p.slot_bytes >> 4;
+    const uint32_t row16 = (uint32_t)SUBROW >> 4;                 // one voxel row in 16-byte units
+    const uint32_t sh_off = (uint32_t)p.WP * row16, sw_off = row16;
+    mbar_wait(smem_u32(&w_bar), 0);
+    uint32_t slot = 0, phase = 0, a_cur = a_lo0;
+    uint32_t it = 0;
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+      int n, h0, w0, j0, nj;
+      decode(unit, n, h0, w0, j0, nj);
+      const bool tail_plane = j0 + nj < p.Di;                    // an extra plane follows the last tile-step
+      mbar_wait(smem_u32(&full_bar[slot]), phase);               // plane j0
+      for (int i = 0; i < nj; ++i, ++it) {
+        const bool has_next = (i + 1 < nj) || tail_plane;
+        uint32_t nslot = slot + 1, nphase = phase, a_next = a_cur + a_step;
+        if (nslot == (uint32_t)p.nslots) { nslot = 0; nphase ^= 1u; a_next = a_lo0; }
+        if (has_next) mbar_wait(smem_u32(&full_bar[nslot]), nphase);
+        const uint32_t buf = it & 1u;
+        mbar_wait(smem_u32(&tmem_empty_bar[buf]), ((it >> 1) & 1u) ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * 256u;
+        if (elect_one()) {
+#pragma unroll
+          for (int r = 0; r < 14; ++r) {
+            const DeconvRun run = kDeconvRuns[r];
+            const bool sd = (run.s & 4) != 0;
+            if (sd && !has_next) continue;                       // plane j+1 is beyond the volume: zero contribution
+            const uint32_t a_base = (sd ? a_next : a_cur) + ((run.s & 2) ? sh_off : 0u) + ((run.s & 1) ? sw_off : 0u);
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((run.len * CP) >> 3) << 17) |
+                                   ((uint32_t)(kTileM >> 4) << 24);
+#pragma unroll
+            for (int k = 0; k < KSTEPS; ++k)
+              umma_bf16(d_tmem + (uint32_t)run.c0 * CP, desc64(desc_hi, a_base + 2u * k),
+                        desc64(desc_hi, b_lo0 + (uint32_t)run.tile0 * b_tap + 2u * k), idesc, (r | k) ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&tmem_full_bar[buf]));
+          umma_commit(smem_u32(&empty_bar[slot]));               // plane j is not needed by later tile-steps
+          if (i == nj - 1 && tail_plane) umma_commit(smem_u32(&empty_bar[nslot]));
+        }
+        __syncwarp();
+        slot = nslot; phase = nphase; a_cur = a_next;
+      }
+      if (tail_plane) {                                          // skip the extra plane's slot
+        a_cur += a_step;
+        if (++slot == (uint32_t)p.nslots) { slot = 0; phase ^= 1u; a_cur = a_lo0; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..9) =====================
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;              // output depth parity handled by this warp (classes 4*half .. 4*half+3)
+    const int row = quad * 32 + lane;
+    const int r_w = row % p.WP, r_h = row / p.WP;
+    const int Do = 2 * p.Di, Ho = 2 * p.Hi, Wo = 2 * p.Wi;
+    EpiFast f;
+    f.m1 = p.epi.residual_mode == 1 ? 1.f : 0.f;
+    f.m2 = p.epi.residual_mode == 2 ? 1.f : 0.f;
+    f.lo = p.epi.relu ? 0.f : -INFINITY;
+    __nv_bfloat16* const ybase = reinterpret_cast<__nv_bfloat16*>(p.epi.y) + p.epi.out_coffset;
+    const __nv_bfloat16* const rbase = p.epi.residual + p.epi.res_coffset;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 4 * CP);
+    uint32_t it = 0;
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+      int n, h0, w0, j0, nj;
+      decode(unit, n, h0, w0, j0, nj);
+      const int iw = w0 + r_w, ih = h0 + r_h;
+      const bool in_range = r_w < p.TWv && iw < p.Wi && ih < p.Hi;
+      for (int i = 0; i < nj; ++i, ++it) {
+        const int od = 2 * (j0 + i) + half;
+        const int64_t vox00 = (((int64_t)n * Do + od) * Ho + 2 * ih) * Wo + 2 * iw;   // class (ph, pw) = (0, 0)
+        ResidualRow32 rr[4];
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) rr[ci].q[q] = make_uint4(0u, 0u, 0u, 0u);
+          if (p.epi.residual_mode && in_range) {
+            const int64_t vox = vox00 + (int64_t)(ci >> 1) * Wo + (ci & 1);
+            const uint4* rp = reinterpret_cast<const uint4*>(rbase + vox * p.epi.res_cstride);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) rr[ci].q[q] = __ldg(rp + q);
+          }
+        }
+        const uint32_t buf = it & 1u;
+        mbar_wait(smem_u32(&tmem_full_bar[buf]), (it >> 1) & 1u);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+          uint32_t acc[32];
+          const uint32_t taddr = lane_base + buf * 256u + (uint32_t)(ci * CP);
+          tmem_ld16(taddr, *reinterpret_cast<uint32_t(*)[16]>(acc));
+          tmem_ld16(taddr + 16u, *reinterpret_cast<uint32_t(*)[16]>(acc + 16));
+          tmem_ld_wait();
+          if (in_range) {
+            const int64_t vox = vox00 + (int64_t)(ci >> 1) * Wo + (ci & 1);
+            __nv_bfloat16* yrow = ybase + vox * p.epi.out_cstride;
+            epilogue_chunk16_r32(acc, 0, s_scale, s_bias, rr[ci], f, yrow);
+            epilogue_chunk16_r32(acc + 16, 16, s_scale, s_bias, rr[ci], f, yrow);
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[buf]));
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------ weight packing
 // w fp32: conv [Cout,Cin,k,k,k] / deconv [Cin,Cout,k,k,k]  ->  packed bf16 [k^3][CoutPad][Cin]
 __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cin, int Cout,
@@ -1097,6 +1390,85 @@ int launch_halo(const void* x, const void* w_packed, const float* scale, const f
   return launch_status("conv3d_halo_kernel");
 }
 
+// ---- v4 host side: fused transposed conv; returns 1 when not eligible (caller uses the per-class launches)
+int launch_deconv(const void* x, const void* w_packed, const float* scale, const float* bias, const void* residual,
+                  void* y, const snvc_conv3d_desc& d, const ConvParams& cp, cudaStream_t stream, int cout0) {
+  if (!d.transposed || cp.sigmoid || cp.out_f32 || (cp.Cout % kDeconvCP) != 0) return 1;
+  if (((cp.out_cstride | cp.out_coffset) & 7) != 0) return 1;
+  if (!(d.Cin == 16 || d.Cin == 32 || d.Cin == 64)) return 1;
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return fail(SNVC_E_DRIVER, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  DeconvParams p{};
+  p.N = d.N; p.Cin = d.Cin; p.Di = d.Di; p.Hi = d.Hi; p.Wi = d.Wi;
+  p.scale = scale ? scale + cout0 : nullptr;
+  p.bias = bias ? bias + cout0 : nullptr;
+  p.epi.Cout = kDeconvCP; p.epi.CoutPad = kDeconvCP; p.epi.relu = cp.relu; p.epi.residual_mode = cp.residual_mode;
+  p.epi.sigmoid = 0; p.epi.out_f32 = 0; p.epi.out_cstride = cp.out_cstride; p.epi.out_coffset = cp.out_coffset + cout0;
+  p.epi.res_cstride = cp.res_cstride; p.epi.res_coffset = cp.res_coffset + cout0;
+  p.epi.residual = (const __nv_bfloat16*)residual; p.epi.y = y;
+  p.w_rows_per_tap = cp.CoutPad; p.w_row0 = cout0;
+  const int row_bytes = d.Cin * 2;
+  p.w_tap_bytes = kDeconvCP * row_bytes;
+  const int w_total = round_up(27 * p.w_tap_bytes, 1024);
+  const int budget = 225 * 1024 - 1024 - w_total;
+  double best = -1;
+  for (int wp = 16; wp <= 64; wp <<= 1) {
+    const int twv = wp - 1, th = 128 / wp;
+    const int slot = round_up(((th + 1) * wp + 16) * row_bytes, 1024);
+    if (budget < slot * 3) continue;
+    const double eff = ((double)d.Wi / (ceil_div(d.Wi, twv) * wp)) * ((double)d.Hi / (ceil_div(d.Hi, th) * th));
+    if (eff > best) { best = eff; p.WP = wp; p.TH = th; p.TWv = twv; p.slot_bytes = slot; }
+  }
+  if (best < 0) return 1;
+  p.nslots = std::min(kMaxSlots, budget / p.slot_bytes);
+  p.plane_bytes = (p.TH + 1) * p.WP * row_bytes;
+  p.tiles_h = (int)ceil_div(d.Hi, p.TH); p.tiles_w = (int)ceil_div(d.Wi, p.TWv);
+  // depth chunks: enough work units for ~6 waves when the volume allows it (each chunk re-loads one plane)
+  const int64_t cols = (int64_t)d.N * p.tiles_h * p.tiles_w;
+  int nchunk = 1;
+  while (cols * nchunk < 6ll * sm_count() && d.Di / (nchunk + 1) >= 4) ++nchunk;
+  p.DC = (int)ceil_div(d.Di, nchunk);
+  p.nchunk = (int)ceil_div(d.Di, p.DC);
+  const int64_t units = cols * p.nchunk;
+  SNVC_CHECK_ARG(units < (1ll << 31), "too many work units");
+  p.num_units = (int)units;
+  const size_t smem = (size_t)w_total + (size_t)p.nslots * p.slot_bytes + 1024;
+
+  CUtensorMap map_x, map_w;
+  {
+    const cuuint64_t cs = (cuuint64_t)(d.in_cstride ? d.in_cstride : d.Cin) * 2;
+    cuuint64_t dims[5] = {(cuuint64_t)d.Cin, (cuuint64_t)d.Wi, (cuuint64_t)d.Hi, (cuuint64_t)d.Di, (cuuint64_t)d.N};
+    cuuint64_t strides[4] = {cs, (cuuint64_t)d.Wi * cs, (cuuint64_t)d.Hi * d.Wi * cs, (cuuint64_t)d.Di * d.Hi * d.Wi * cs};
+    cuuint32_t box[5] = {(cuuint32_t)d.Cin, (cuuint32_t)p.WP, (cuuint32_t)(p.TH + 1), 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const void* xbase = static_cast<const char*>(x) + (size_t)d.in_coffset * 2;
+    CUresult r = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(xbase), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_mode(row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail((int)r, "cuTensorMapEncodeTiled(x, deconv) failed with CUresult %d", (int)r);
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)d.Cin, (cuuint64_t)27 * cp.CoutPad};
+    cuuint64_t strides[1] = {(cuuint64_t)d.Cin * 2};
+    cuuint32_t box[2] = {(cuuint32_t)d.Cin, (cuuint32_t)kDeconvCP};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_packed), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_mode(row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail((int)r, "cuTensorMapEncodeTiled(w, deconv) failed with CUresult %d", (int)r);
+  }
+  void (*kern)(const CUtensorMap, const CUtensorMap, const DeconvParams) = nullptr;
+  switch (d.Cin) {
+    case 16: kern = conv3d_deconv_kernel<1, 32>; break;
+    case 32: kern = conv3d_deconv_kernel<2, 64>; break;
+    case 64: kern = conv3d_deconv_kernel<4, 128>; break;
+  }
+  SNVC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = std::min(p.num_units, sm_count());
+  kern<<<grid, kDeconvThreads, smem, stream>>>(map_x, map_w, p);
+  return launch_status("conv3d_deconv_kernel");
+}
+
 }  // namespace
 }  // namespace snvc
 
@@ -1195,6 +1567,17 @@ extern "C" int snvc_conv3d_fwd(const void* x, const void* w_packed, const float*
   SNVC_CHECK_ARG(d.kernel == 3 && d.stride == 2 && d.pad == 1 && d.dilation == 1,
                  "transposed conv supports k=3, s=2, p=1, output_padding=1 only");
   SNVC_CHECK_ARG(d.Do == 2 * d.Di && d.Ho == 2 * d.Hi && d.Wo == 2 * d.Wi, "transposed conv output must be 2x input");
+  {
+    const char* mode = getenv("SNVC_CONV_MODE");
+    if (!(mode && mode[0] == 't')) {                     // SNVC_CONV_MODE=tap: per-class launches (A/B runs)
+      int r = 1;
+      for (int c0 = 0; c0 < d.Cout; c0 += kDeconvCP) {
+        r = launch_deconv(x, w_packed, scale, bias, residual, y, d, p, stream, c0);
+        if (r != 0) break;
+      }
+      if (r != 1) return r;
+    }
+  }
   p.Dj = d.Di; p.Hj = d.Hi; p.Wj = d.Wi;
   p.in_stride = 1;
   p.out_stride = 2;
