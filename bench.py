@@ -67,7 +67,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -145,11 +145,21 @@ def run_reference(args, rank, world):
 
 
 # ----------------------------------------------------------------------------------------------
+def roofline_traffic():
+    """DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return {}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     import synth
-    from snvc_b200.models.stereonet import GlobalHotPath
+    from snvc_b200 import _lib
+    from snvc_b200.models.stereonet import GlobalHotPath, HostPipeline
     from snvc_b200.extension.build_cost_volume import build_cost_volume_ndhwc_bf16
     from snvc_b200.utils.geometry import KITTI_P2, kitti_global_cfg, plane_sweep_shifts
 
@@ -159,6 +169,7 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
     cfg = kitti_global_cfg()
     model = GlobalHotPath(cfg).eval()
     model.load_state_dict(synth.det_state_dict(model, 41), strict=True)   # deterministic random init (tests/golden/synth.py)
@@ -174,24 +185,23 @@ def run_ours(args, rank, world, local_rank):
     os.environ["SNVC_B200_SKIP_SHIFT_CHECK"] = "1"
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    stage_ms = {"cost_volume": 0.0, "trunk": 0.0, "lift": 0.0}
+    stage_ms = {"cost_volume": 0.0, "conv1": 0.0, "trunk": 0.0, "lift": 0.0}
 
     def step(i, timed):
         l, r = lefts[i % NSETS], rights[i % NSETS]
+        e = [ev() for _ in range(5)] if timed else None
         if timed:
-            e = [ev() for _ in range(4)]
             e[0].record()
         cost = build_cost_volume_ndhwc_bf16(l, r, shift, 1)
         if timed:
             e[1].record()
-        feat = model.trunk(cost)
-        if timed:
-            e[2].record()
-        vox = model.lift(feat, proj, out_dtype, layout_out)
+        feat = model.trunk(cost, mark=(lambda name: e[2].record()) if timed else None)
         if timed:
             e[3].record()
-            return vox, e
-        return vox, None
+        vox = model.lift(feat, proj, out_dtype, layout_out)
+        if timed:
+            e[4].record()
+        return vox, e
 
     with torch.no_grad():
         for i in range(W):
@@ -205,64 +215,70 @@ def run_ours(args, rank, world, local_rank):
             sampler.start()
         t_start, t_stop = ev(), ev()
         evs = []
+        launches0 = L.snvc_launch_count()
         t_start.record()
         for i in range(K):
             _, e = step(W + i, True)
             evs.append(e)
         t_stop.record()
+        launches = L.snvc_launch_count() - launches0
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        clocks = sampler.stop() if rank == 0 else None
         elapsed_ms = t_start.elapsed_time(t_stop)
         for e in evs:
             stage_ms["cost_volume"] += e[0].elapsed_time(e[1])
-            stage_ms["trunk"] += e[1].elapsed_time(e[2])
-            stage_ms["lift"] += e[2].elapsed_time(e[3])
+            stage_ms["conv1"] += e[1].elapsed_time(e[2])
+            stage_ms["trunk"] += e[1].elapsed_time(e[3])
+            stage_ms["lift"] += e[3].elapsed_time(e[4])
 
-        # ---- end to end through the public module call with HOST buffers ----------------------
-        h_left = torch.randn((B, FEAT_C, FEAT_H, FEAT_W)).pin_memory()
-        h_right = torch.randn((B, FEAT_C, FEAT_H, FEAT_W)).pin_memory()
-        h_shift = torch.from_numpy(plane_sweep_shifts(cfg, B)).pin_memory()
-        h_proj = torch.from_numpy(KITTI_P2[None].repeat(B, 0).copy()).pin_memory()
+        # ---- end to end through the public host-buffer API: pinned host inputs -> H2D -> hot path -> D2H of
+        # the lifted voxels into pinned host memory, every step, copies overlapped with compute on separate
+        # streams (snvc_b200.models.stereonet.HostPipeline) -------------------------------------------------
+        NH = 2
+        h_in = [(torch.randn((B, FEAT_C, FEAT_H, FEAT_W)).pin_memory(), torch.randn((B, FEAT_C, FEAT_H, FEAT_W)).pin_memory(),
+                 torch.from_numpy(plane_sweep_shifts(cfg, B)).pin_memory(),
+                 torch.from_numpy(KITTI_P2[None].repeat(B, 0).copy()).pin_memory()) for _ in range(NH)]
         Z, Y, X = model.zs.numel(), model.ys.numel(), model.xs.numel()
-        h_out = torch.empty((B, Z, Y, X, 32), dtype=out_dtype).pin_memory()
-
-        def e2e_step():
-            dl, dr = h_left.to(dev, non_blocking=True), h_right.to(dev, non_blocking=True)
-            dsft, dp = h_shift.to(dev, non_blocking=True), h_proj.to(dev, non_blocking=True)
-            vox = model(dl, dr, dsft, dp, out_dtype, layout_out)
-            h_out.copy_(vox, non_blocking=True)
-
-        e2e_steps = max(2, min(K, 5))
-        for _ in range(2):
-            e2e_step()
+        h_out = [torch.empty((B, Z, Y, X, 32), dtype=out_dtype).pin_memory() for _ in range(NH)]
+        pipe = HostPipeline(model, depth=2, out_dtype=out_dtype, layout_out=layout_out)
+        e2e_steps = max(4, min(K, 20))
+        for i in range(3):
+            pipe.submit(*h_in[i % NH], h_out[i % NH])
+        pipe.drain()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
+        torch.cuda.synchronize()
         e0, e1 = ev(), ev()
+        cur = torch.cuda.current_stream()
         e0.record()
-        for _ in range(e2e_steps):
-            e2e_step()
+        for i in range(e2e_steps):
+            pipe.submit(*h_in[i % NH], h_out[i % NH])
+        cur.wait_stream(pipe.s_out)
+        cur.wait_stream(pipe.s_in)
         e1.record()
         torch.cuda.synchronize()
         e2e_ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if rank == 0 else None
 
-    t = torch.tensor([elapsed_ms, e2e_ms, stage_ms["cost_volume"], stage_ms["trunk"], stage_ms["lift"]],
+    t = torch.tensor([elapsed_ms, e2e_ms, stage_ms["cost_volume"], stage_ms["trunk"], stage_ms["lift"], stage_ms["conv1"]],
                      device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms, e2e_ms, cv_ms, trunk_ms, lift_ms = t.tolist()
+    elapsed_ms, e2e_ms, cv_ms, trunk_ms, lift_ms, conv1_ms = t.tolist()
 
     if rank == 0:
         peaks = measured_peaks()
         pairs = world * B * K
         value = pairs / (elapsed_ms * 1e-3)
         trunk_tflops = TRUNK_GFLOP_PER_PAIR * 1e-3 * B * K / (trunk_ms * 1e-3)
+        conv1_gflop = 2 * 27 * 64 * 32 * DEPTH_BINS * FEAT_H * FEAT_W * 1e-9      # dres0.conv1, per pair (159.0)
+        conv1_tflops = conv1_gflop * 1e-3 * B * K / (conv1_ms * 1e-3)
         cv_gbs = CV_BYTES_PER_PAIR_BF16 * B * K / (cv_ms * 1e-3) / 1e9
         lift_gbs = lift_bytes_per_pair(2) * B * K / (lift_ms * 1e-3) / 1e9
-        launches_per_step = 1 + 24 + 1     # cost volume + (8 convs + 2 deconvs x 8 parity classes) + lift
+        traffic = roofline_traffic()
         cpu_v, cpu_spp, cpu_threads = cpu_reference_pairs_per_s(2, 1) if world == 1 and not args.no_cpu_baseline \
             else (None, None, None)
         line = {
@@ -278,15 +294,21 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clocks,
             "e2e": {"value": world * B * e2e_steps / (e2e_ms * 1e-3), "unit": "pairs/s",
                     "h2d_bytes_per_step": int(2 * B * FEAT_C * FEAT_H * FEAT_W * 4 + B * DEPTH_BINS * 4 + B * 48),
-                    "d2h_bytes_per_step": int(B * LIFT_VOX * 32 * 2), "steps": e2e_steps},
-            "gpu_launches": launches_per_step * K,
-            "roofline": {"bound": "tensor", "kernel": "conv3d_tcgen05_kernel (24 launches / step)",
-                         "achieved": trunk_tflops, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                         "frac": trunk_tflops / peaks["tf_sustained"], "traffic": None,
+                    "d2h_bytes_per_step": int(B * LIFT_VOX * 32 * 2), "steps": e2e_steps,
+                    "api": "snvc_b200.models.stereonet.HostPipeline.submit (pinned host buffers; H2D / compute / D2H "
+                           "on three streams, 2 slots)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor",
+                         "kernel": "conv3d_kdfuse_kernel<4,128,32,512> (dres0.conv1 3x3x3 64->32, 1 launch / step)",
+                         "achieved": conv1_tflops, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                         "frac": conv1_tflops / peaks["tf_sustained"],
+                         "traffic": traffic.get("dres0.conv1_dram_bytes_per_launch"),
+                         "algorithmic_flop_per_launch": conv1_gflop * 1e9 * B,
                          "peak_source": peaks["source"] + " (sustained bf16, kernel timed inside a long step)",
-                         "share_of_step": trunk_ms / elapsed_ms},
+                         "share_of_step": conv1_ms / elapsed_ms},
             "stages": {"cost_volume": {"ms_per_step": cv_ms / K, "achieved_gbs": cv_gbs, "frac_hbm": cv_gbs / peaks["hbm"]},
-                       "trunk": {"ms_per_step": trunk_ms / K, "achieved_tflops": trunk_tflops},
+                       "trunk": {"ms_per_step": trunk_ms / K, "achieved_tflops": trunk_tflops,
+                                 "frac_tensor": trunk_tflops / peaks["tf_sustained"], "share_of_step": trunk_ms / elapsed_ms},
                        "lift": {"ms_per_step": lift_ms / K, "achieved_gbs": lift_gbs, "frac_hbm": lift_gbs / peaks["hbm"]}},
         }
         if cpu_v is not None:

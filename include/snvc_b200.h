@@ -47,6 +47,10 @@ extern "C" {
 
 int snvc_version(void);
 const char* snvc_last_error(void);
+/* Number of CUDA kernels this library has launched in this process so far (monotonic counter; the
+ * only process-wide state besides cached device attributes).  bench.py reports the difference over
+ * its timed region as `gpu_launches`. */
+int64_t snvc_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * A1  plane-sweep cost volume, forward.

@@ -24,6 +24,7 @@ class ConvDesc(ctypes.Structure):
 _SIGS = {
     "snvc_version": ([], _i32),
     "snvc_last_error": ([], ctypes.c_char_p),
+    "snvc_launch_count": ([], _i64),
     "snvc_cost_volume_fwd": ([_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _p], _i32),
     "snvc_cost_volume_bwd": ([_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _p], _i32),
     "snvc_cost_volume_xlow": ([_p, _p, _i64, _i64, _i64, _i32, _p], _i32),

@@ -1,5 +1,6 @@
 #include "common.cuh"
 
+#include <atomic>
 #include <mutex>
 
 namespace snvc {
@@ -17,6 +18,10 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+static std::atomic<int64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+int64_t launches() { return g_launches.load(std::memory_order_relaxed); }
+
 int sm_count() {
   static int cached[64] = {0};
   int dev = 0;
@@ -31,5 +36,7 @@ int sm_count() {
 
 }  // namespace snvc
 
+namespace snvc { int64_t launches(); }
+extern "C" int64_t snvc_launch_count(void) { return snvc::launches(); }
 extern "C" int snvc_version(void) { return SNVC_ABI_VERSION; }
 extern "C" const char* snvc_last_error(void) { return snvc::err_buf(); }

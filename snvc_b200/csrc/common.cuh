@@ -27,7 +27,11 @@ int fail(int code, const char* fmt, ...);
       return ::snvc::fail((int)e__, "%s failed: %s", #expr, cudaGetErrorString(e__));        \
   } while (0)
 
+// kernels launched by this library in this process (monotonic; read by snvc_launch_count())
+void count_launch();
+
 inline int launch_status(const char* what) {
+  count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail((int)e, "%s launch failed: %s", what, cudaGetErrorString(e));
   return 0;

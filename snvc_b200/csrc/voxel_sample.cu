@@ -8,6 +8,9 @@
 // cat) is the data movement: features are re-laid out channels-last once (tiny), every output
 // element is written exactly once, in the layout its consumer reads (NDHWC bf16 for the tcgen05
 // conv3d, or the reference's NCDHW fp32), with 128-bit accesses.
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace snvc {
@@ -284,6 +287,122 @@ lift_ndhwc_kernel(const __nv_bfloat16* __restrict__ vol, const float* __restrict
   }
 }
 
+// v2 of the NDHWC lift (the product path): the one-thread-per-voxel kernel above is bound by the L1
+// tag stage, not by HBM -- ncu (profiles/r01_step_v5.*): every LDG.128 of a warp touches 32 different
+// voxel rows (16.7 sectors per request, l1tex 94 % busy, DRAM 20 %).  Here a warp still owns 32
+// consecutive voxels and every lane still does the projection / floor / weight set-up of ONE voxel
+// (so the 5 IEEE divisions are never replicated), but the gather is done by LPV = C/8 adjacent lanes
+// per voxel, 16 bytes of the channel row each: one warp-wide LDG.128 now covers 32/LPV whole rows
+// (8 rows of 64 B for C = 32) and one STG.128 writes 32/LPV whole output rows -- 4x fewer L1 tag
+// look-ups per byte.  The per-voxel set-up (8 corner weights, base voxel index, in-bounds mask) moves
+// from the owning lane to the gathering lanes with warp shuffles; rounds whose voxels are all outside
+// the frustum are skipped on a ballot.  Arithmetic per channel is the same instruction sequence as the
+// kernel above, so results are bit-identical to it (and EXACT = bit-identical to the oracle).
+// Division of a 32-bit index by a run-time constant (Granlund-Montgomery): the flat voxel index is split into
+// (n, z, y, x) with three of these instead of four 64-bit software divisions (ncu: those were 250 of the
+// 393 set-up instructions per voxel, and the kernel was issue-bound).
+struct FastDiv { uint32_t m, s1, s2, d; };
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
+  const uint32_t t = __umulhi(f.m, n);
+  return (t + ((n - t) >> f.s1)) >> f.s2;
+}
+struct LiftDivs { FastDiv X, Y, Z; };
+
+template <typename OutT, bool EXACT>
+__global__ void __launch_bounds__(256)
+lift_ndhwc_coop_kernel(const __nv_bfloat16* __restrict__ vol, const float* __restrict__ proj,
+                       const float* __restrict__ zs, const float* __restrict__ ys, const float* __restrict__ xs,
+                       OutT* __restrict__ out, uint8_t* __restrict__ valid, int C, int log_lpv, LiftGeom g,
+                       LiftDivs dv, uint32_t total /* N*Z*Y*X < 2^31 */) {
+  const int lane = threadIdx.x & 31;
+  const int HW = g.H * g.W;
+  const int DHW = g.D * HW;
+  const int lpv = 1 << log_lpv;                 // lanes per voxel
+  const int vpr = 32 >> log_lpv;                // voxels per round
+  const int sub = lane & (lpv - 1);             // which 8-channel group of the row this lane gathers
+  const int vsel = lane >> log_lpv;             // which voxel of the round
+  const uint32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t row16 = (uint32_t)C >> 3;      // 16-byte pieces per voxel row
+  for (uint32_t chunk = warp0; chunk * 32u < total; chunk += nwarps) {
+    // ---- phase A: lane i sets up voxel chunk*32 + i
+    const uint32_t nv = chunk * 32u + lane;
+    float ww[8];
+    int base = 0;
+    unsigned m = 0;
+    if (nv < total) {
+      const uint32_t q1 = fdiv(nv, dv.X), xi = nv - q1 * dv.X.d;
+      const uint32_t q2 = fdiv(q1, dv.Y), yi = q1 - q2 * dv.Y.d;
+      const uint32_t n = fdiv(q2, dv.Z), zi = q2 - n * dv.Z.d;
+      const Trilinear t = trilinear_setup(proj + n * 12, __ldg(xs + xi), __ldg(ys + yi), __ldg(zs + zi), g);
+      if (valid) valid[nv] = t.valid ? 1 : 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {   // tnw,tne,tsw,tse,bnw,bne,bsw,bse
+        const int xx = t.x0 + (k & 1), yy = t.y0 + ((k >> 1) & 1), zz = t.z0 + (k >> 2) - g.d_base;
+        const bool in = t.valid && xx >= 0 && xx < g.W && yy >= 0 && yy < g.H && zz >= 0 && zz < g.D;
+        m |= in ? (1u << k) : 0u;
+        ww[k] = __fmul_rn(__fmul_rn(t.wx[k & 1], t.wy[(k >> 1) & 1]), t.wz[k >> 2]);
+      }
+      // voxel index of corner 0 in the whole batch (may be "negative" when corner 0 itself is outside; only
+      // in-bounds corners are dereferenced).  Host guarantees N*D*H*W < 2^31.
+      base = m ? (int)n * DHW + ((t.z0 - g.d_base) * g.H + t.y0) * g.W + t.x0 : 0;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) ww[k] = 0.f;
+    }
+    // ---- phase B: lpv rounds of vpr voxels; lane group `vsel` gathers voxel r*vpr + vsel
+    for (int r = 0; r < lpv; ++r) {
+      const int src = r * vpr + vsel;
+      const unsigned mm = __shfl_sync(0xffffffffu, m, src);
+      const uint32_t onv = chunk * 32u + src;
+      const bool live = onv < total;              // tail chunk only; dead voxels carry mm == 0
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      if (__ballot_sync(0xffffffffu, mm != 0u) != 0u) {
+        const int b = __shfl_sync(0xffffffffu, base, src);
+        float w[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) w[k] = __shfl_sync(0xffffffffu, ww[k], src);
+        uint4 q[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          q[k] = make_uint4(0u, 0u, 0u, 0u);
+          if (mm & (1u << k)) {
+            const uint32_t v = (uint32_t)(b + (k >> 2) * HW + ((k >> 1) & 1) * g.W + (k & 1));
+            q[k] = __ldg(reinterpret_cast<const uint4*>(vol) + (v * row16 + sub));      // host: volume < 2^32 x 16 B
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (mm & (1u << k)) {
+            const uint32_t u[4] = {q[k].x, q[k].y, q[k].z, q[k].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (EXACT) {
+                acc[2 * j] = __fadd_rn(acc[2 * j], __fmul_rn(bf16_lo(u[j]), w[k]));
+                acc[2 * j + 1] = __fadd_rn(acc[2 * j + 1], __fmul_rn(bf16_hi(u[j]), w[k]));
+              } else {
+                acc[2 * j] = fmaf(bf16_lo(u[j]), w[k], acc[2 * j]);
+                acc[2 * j + 1] = fmaf(bf16_hi(u[j]), w[k], acc[2 * j + 1]);
+              }
+            }
+          }
+        }
+      }
+      if (!live) continue;
+      OutT* o = out + (int64_t)onv * C + sub * 8;
+      if (sizeof(OutT) == 2) {
+        st_cs_v4(o, make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                               pack_bf16x2(acc[6], acc[7])));
+      } else {
+        st_cs_f4(reinterpret_cast<float*>(o), make_float4(acc[0], acc[1], acc[2], acc[3]));
+        st_cs_f4(reinterpret_cast<float*>(o) + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
+      }
+    }
+  }
+}
+
 // NCDHW fp32 volume (the reference's layout) -> NCDHW fp32; one thread per voxel, channel loop.
 __global__ void __launch_bounds__(256)
 lift_ncdhw_kernel(const float* __restrict__ vol, const float* __restrict__ proj, const float* __restrict__ zs,
@@ -434,6 +553,34 @@ static int lift_fwd_impl(const void* vol, const float* proj, const float* zs, co
     SNVC_CHECK_ARG((reinterpret_cast<uintptr_t>(vol) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                    "vol / out must be 16-byte aligned");
     const int blocks = grid_for(nvox, 16);
+    // cooperative gather (C/8 lanes per voxel) whenever the row splits into a power-of-two number of 16-byte
+    // pieces; SNVC_LIFT_MODE=thread keeps the one-thread-per-voxel kernel (A/B runs)
+    const int lpv = (int)(C / 8);
+    const char* lmode = getenv("SNVC_LIFT_MODE");
+    if (out_layout == SNVC_NDHWC && C % 8 == 0 && lpv <= 32 && (lpv & (lpv - 1)) == 0 && N * D * H * W < (1ll << 31) &&
+        nvox < (1ll << 31) && N * D * H * W * lpv < (1ll << 32) && !(lmode && lmode[0] == 't')) {
+      int log_lpv = 0;
+      while ((1 << log_lpv) < lpv) ++log_lpv;
+      auto mk = [](int64_t d) {
+        FastDiv f;
+        uint32_t l = 0;
+        while ((1ull << l) < (uint64_t)d) ++l;
+        f.m = (uint32_t)((((uint64_t)1 << 32) * (((uint64_t)1 << l) - (uint64_t)d)) / (uint64_t)d + 1);
+        f.s1 = l < 1 ? l : 1; f.s2 = l > 0 ? l - 1 : 0; f.d = (uint32_t)d;
+        return f;
+      };
+      LiftDivs dv{mk(X), mk(Y), mk(Z)};
+      const int cblocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(nvox, 256), (int64_t)sm_count() * 8));
+      if (out_dtype == SNVC_BF16)
+        lift_ndhwc_coop_kernel<__nv_bfloat16, false><<<cblocks, 256, 0, stream>>>(
+            (const __nv_bfloat16*)vol, proj, zs, ys, xs, (__nv_bfloat16*)out, valid, (int)C, log_lpv, g, dv, (uint32_t)nvox);
+      else if (out_dtype == SNVC_F32)
+        lift_ndhwc_coop_kernel<float, true><<<cblocks, 256, 0, stream>>>((const __nv_bfloat16*)vol, proj, zs, ys, xs,
+                                                                         (float*)out, valid, (int)C, log_lpv, g, dv, (uint32_t)nvox);
+      else
+        return fail(SNVC_E_UNSUPPORTED, "lift: unsupported output type for an NDHWC bf16 volume");
+      return launch_status("lift_ndhwc_coop_kernel");
+    }
     if (out_layout == SNVC_NDHWC && out_dtype == SNVC_BF16)
       lift_ndhwc_kernel<__nv_bfloat16, true, false><<<blocks, 256, 0, stream>>>(
           (const __nv_bfloat16*)vol, proj, zs, ys, xs, (__nv_bfloat16*)out, valid, (int)C, g, nvox);

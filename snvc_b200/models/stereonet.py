@@ -44,9 +44,14 @@ class GlobalHotPath(nn.Module):
         self.register_buffer("xs", voxel_centres(cfg.X_MIN, cfg.X_MAX, cfg.VOXEL_X_SIZE), persistent=False)
 
     # ---- stages on channels-last bf16 -----------------------------------------------------
-    def trunk(self, cost):
-        """cost [N,D,H,W,2F] bf16 -> [N,D,H,W,ch] bf16 (7 + 3*... fused conv launches)."""
-        x = self.dres0[1].fused(self.dres0[0].fused(cost))
+    def trunk(self, cost, mark=None):
+        """cost [N,D,H,W,2F] bf16 -> [N,D,H,W,ch] bf16 (one fused conv launch per layer; 64-channel layers
+        run as two output slices).  `mark(name)`, if given, is called right after the first layer has been
+        enqueued (bench.py records a CUDA event there to time the dominant kernel on its own)."""
+        x = self.dres0[0].fused(cost)
+        if mark is not None:
+            mark("dres0.conv1")
+        x = self.dres0[1].fused(x)
         x = self.dres1[1].fused(self.dres1[0].fused(x), residual=x, residual_mode=1)
         return self.hg.fused(x, out_residual=x)[0]
 
@@ -59,3 +64,57 @@ class GlobalHotPath(nn.Module):
         -> lifted voxels [N,ch,Z,Y,X] (layout_out 'NCDHW') or [N,Z,Y,X,ch] ('NDHWC')."""
         cost = build_cost_volume_ndhwc_bf16(left_feat, right_feat, shift, 1)
         return self.lift(self.trunk(cost), proj, out_dtype, layout_out)
+
+
+class HostPipeline:
+    """Host-buffer front end of `GlobalHotPath`: batches come from / go back to PINNED host memory.
+
+    The reference moves every batch with blocking `.cuda()` / `.cpu()` calls around the model
+    (tools/inference_agnostic.py:389-395, 605-640).  On B200 the lifted volume of 8 pairs is 0.6 GB, so
+    the device-to-host copy (PCIe) takes longer than the whole hot path; this front end therefore runs
+    three streams -- host-to-device, compute (the caller's current stream), device-to-host -- over
+    `depth` slots so that the copies of batch i-1 / i+1 overlap the kernels of batch i (PCIe is full
+    duplex).  `submit` enqueues one batch and returns immediately; `drain` waits for everything."""
+
+    def __init__(self, model, depth=2, out_dtype=torch.bfloat16, layout_out="NDHWC"):
+        self.model, self.depth, self.out_dtype, self.layout_out = model, depth, out_dtype, layout_out
+        dev = next(model.parameters()).device
+        self.dev = dev
+        self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.slots = [dict(inputs=None, computed=None, copied_out=None) for _ in range(depth)]
+        self.n = 0
+
+    def submit(self, h_left, h_right, h_shift, h_proj, h_out):
+        """All arguments are pinned host tensors; `h_out` receives the lifted voxels."""
+        for t in (h_left, h_right, h_shift, h_proj, h_out):
+            if t.is_cuda or not t.is_pinned():
+                raise RuntimeError("HostPipeline.submit expects pinned host tensors")
+        slot = self.slots[self.n % self.depth]
+        self.n += 1
+        cur = torch.cuda.current_stream(self.dev)
+        with torch.cuda.stream(self.s_in):
+            if slot["computed"] is not None:          # the slot's previous inputs must have been consumed
+                self.s_in.wait_event(slot["computed"])
+            if slot["inputs"] is None or slot["inputs"][0].shape != h_left.shape:
+                slot["inputs"] = tuple(torch.empty(t.shape, dtype=t.dtype, device=self.dev)
+                                       for t in (h_left, h_right, h_shift, h_proj))
+            for d, h in zip(slot["inputs"], (h_left, h_right, h_shift, h_proj)):
+                d.copy_(h, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(self.s_in)
+        cur.wait_event(ready)
+        vox = self.model(*slot["inputs"], self.out_dtype, self.layout_out)
+        slot["computed"] = torch.cuda.Event()
+        slot["computed"].record(cur)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(slot["computed"])
+            h_out.copy_(vox, non_blocking=True)
+            vox.record_stream(self.s_out)
+            slot["copied_out"] = torch.cuda.Event()
+            slot["copied_out"].record(self.s_out)
+        return slot["copied_out"]
+
+    def drain(self):
+        self.s_in.synchronize()
+        torch.cuda.current_stream(self.dev).synchronize()
+        self.s_out.synchronize()

@@ -83,6 +83,18 @@ def test_conv_3x3x3_s2(dhw):
     _case(64, 64, 3, 2, 1, 1, False, dhw, relu=True)
 
 
+def test_conv_s2_plane_march_variants(monkeypatch):
+    """Stride-2 pair-row kernel (Cin = 32, even extents): both Cout variants, batch, residual epilogues, a real
+    KITTI-width slab, and -- with the grid clamped to 2 CTAs -- many work units per CTA so that the TMEM accumulator
+    ring and the plane ring wrap around several times."""
+    _case(32, 32, 3, 2, 1, 1, False, (8, 16, 24), N=2, relu=True)
+    _case(32, 64, 3, 2, 1, 1, False, (6, 20, 64), N=2, relu=True, residual_mode=1)
+    _case(32, 64, 3, 2, 1, 1, False, (4, 96, 312), relu=True)
+    monkeypatch.setenv("SNVC_CONV_MAXGRID", "2")
+    _case(32, 64, 3, 2, 1, 1, False, (40, 16, 62), relu=True)
+    _case(32, 32, 3, 2, 1, 1, False, (72, 16, 30), relu=True, residual_mode=2)
+
+
 @pytest.mark.parametrize("Cin,Cout,mode", [(64, 64, 1), (64, 32, 1), (64, 64, 0)])
 def test_deconv_k3_s2(Cin, Cout, mode):
     _case(Cin, Cout, 3, 2, 1, 1, True, (3, 6, 10), N=2, relu=(mode == 1 and Cout == 64), residual_mode=mode)

@@ -153,3 +153,29 @@ def test_global_hot_path_vs_oracle_and_topk():
         while k < 99 and gaps[k] > noise:
             k += 1
         assert np.array_equal(top_ref[:k + 1], top_got[:k + 1])
+
+
+def test_host_pipeline_matches_direct_forward():
+    """HostPipeline (pinned host buffers, H2D / compute / D2H overlapped over 2 slots) returns, for every
+    submitted batch, exactly what the module's forward returns for that batch."""
+    from snvc_b200.models.stereonet import GlobalHotPath, HostPipeline
+    geom, cfg = _small_global()
+    N, Fc, H, W = 2, 32, geom.IH // 4, geom.IW // 4
+    m = GlobalHotPath(cfg).eval()
+    m.load_state_dict(synth.det_state_dict(m, 41), strict=True)
+    m = m.cuda()
+    shift = torch.from_numpy(np.ascontiguousarray(geom.shifts(N)))
+    Ps = torch.from_numpy(np.stack([geom.P, geom.P]).astype(np.float32))
+    batches = [(torch.from_numpy(synth.det_uniform((N, Fc, H, W), 400 + i)), torch.from_numpy(synth.det_uniform((N, Fc, H, W), 500 + i)))
+               for i in range(5)]
+    with torch.no_grad():
+        want = [m(l.cuda(), r.cuda(), shift.cuda(), Ps.cuda(), torch.bfloat16, "NDHWC").cpu() for l, r in batches]
+        pipe = HostPipeline(m, depth=2)
+        outs = [torch.empty(want[0].shape, dtype=torch.bfloat16).pin_memory() for _ in batches]
+        for (l, r), o in zip(batches, outs):
+            pipe.submit(l.pin_memory(), r.pin_memory(), shift.pin_memory(), Ps.pin_memory(), o)
+        pipe.drain()
+    for o, w in zip(outs, want):
+        assert torch.equal(o.view(torch.int16), w.view(torch.int16))
+    with pytest.raises(RuntimeError):
+        pipe.submit(batches[0][0], batches[0][1], shift, Ps, outs[0])       # pageable host memory is rejected

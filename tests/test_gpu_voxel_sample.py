@@ -132,3 +132,29 @@ def test_lift_indices_bit_exact_kitti_geometry(ac):
     assert 0.5 < wvalid.mean() < 0.65                     # ~58 % of centres in frustum
     for k, ref in enumerate((x0, y0, z0)):
         assert np.array_equal(idx[..., k][wvalid], ref.astype(np.int32)[wvalid])
+
+
+@pytest.mark.parametrize("C", [16, 32, 64])
+def test_lift_cooperative_kernel_matches_thread_per_voxel_kernel(C, monkeypatch):
+    """The product lift (C/8 lanes per voxel, set-up shared by warp shuffles) must be bit-identical to the
+    one-thread-per-voxel kernel (SNVC_LIFT_MODE=thread), incl. a voxel count that is not a multiple of 32."""
+    geom = ogb.GlobalGeometry(IH=48, IW=160, D=12, depth_min=2.0, depth_max=21.2, X_MIN=-6.2, X_MAX=6.2, Y_MIN=-1.0,
+                              Y_MAX=2.0, Z_MIN=2.0, Z_MAX=20.0, VOXEL_X_SIZE=0.4, VOXEL_Y_SIZE=0.6, VOXEL_Z_SIZE=0.6,
+                              P=np.array([[90.0, 0, 80.0, 5.6], [0, 90.0, 22.0, 0.03], [0, 0, 1.0, 0.0003]], np.float32))
+    N = 3
+    D, H, W = geom.D, geom.IH // 4, geom.IW // 4
+    F = _F()
+    vol = F.to_ndhwc_bf16(torch.from_numpy(synth.det_uniform((N, C, D, H, W), 11)).cuda())
+    zs, ys, xs = (torch.from_numpy(a).cuda() for a in ogb.voxel_centres(geom))
+    assert (N * zs.numel() * ys.numel() * xs.numel()) % 32 != 0
+    Ps = torch.from_numpy(np.stack([geom.P] * N)).cuda()
+    for od in (torch.bfloat16, torch.float32):
+        monkeypatch.setenv("SNVC_LIFT_MODE", "thread")
+        want, wv = F.frustum_lift(vol, Ps, zs, ys, xs, geom.cv_ranges(), True, layout_in="NDHWC", out_dtype=od,
+                                  return_valid=True)
+        monkeypatch.setenv("SNVC_LIFT_MODE", "coop")
+        got, gv = F.frustum_lift(vol, Ps, zs, ys, xs, geom.cv_ranges(), True, layout_in="NDHWC", out_dtype=od,
+                                 return_valid=True)
+        assert torch.equal(gv, wv) and 0.05 < wv.float().mean().item() < 0.95
+        assert torch.equal(got.view(torch.int16 if od == torch.bfloat16 else torch.int32),
+                           want.view(torch.int16 if od == torch.bfloat16 else torch.int32))
