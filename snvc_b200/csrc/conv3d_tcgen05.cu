@@ -185,8 +185,8 @@ __device__ __forceinline__ void residual_prefetch(const EpiParams& e, bool in_ra
 // the epilogue, not the tensor pipe, bounded every kernel variant.
 struct EpiFast { float m1, m2, lo; };
 
-__device__ __forceinline__ void epilogue_chunk16(const uint32_t* acc, int cc, const float* s_scale, const float* s_bias,
-                                                 const ResidualRow& rr, const EpiFast f, __nv_bfloat16* yrow) {
+__device__ __forceinline__ void epilogue_chunk16_vals(const uint32_t* acc, int cc, const float* s_scale, const float* s_bias,
+                                                      const ResidualRow& rr, const EpiFast f, uint4& o0, uint4& o1) {
   float v[16];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -205,10 +205,71 @@ __device__ __forceinline__ void epilogue_chunk16(const uint32_t* acc, int cc, co
     v[2 * j] = fmaf(r0, f.m2, fmaxf(fmaf(r0, f.m1, v[2 * j]), f.lo));
     v[2 * j + 1] = fmaf(r1, f.m2, fmaxf(fmaf(r1, f.m1, v[2 * j + 1]), f.lo));
   }
-  uint4* o = reinterpret_cast<uint4*>(yrow + cc);
-  o[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-  o[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+  o0 = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  o1 = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
 }
+
+__device__ __forceinline__ void epilogue_chunk16(const uint32_t* acc, int cc, const float* s_scale, const float* s_bias,
+                                                 const ResidualRow& rr, const EpiFast f, __nv_bfloat16* yrow) {
+  uint4 o0, o1;
+  epilogue_chunk16_vals(acc, cc, s_scale, s_bias, rr, f, o0, o1);
+  uint4* o = reinterpret_cast<uint4*>(yrow + cc);
+  o[0] = o0;
+  o[1] = o1;
+}
+
+// ---- staged epilogue: rows go to a shared-memory tile in the TMA swizzle pattern and ONE bulk tensor store
+// writes the tile.  Why: a direct store has every lane write 16 B of its own 64-byte voxel row, so each STG.128
+// touches 32 different sectors; ncu (profiles/r01_step_v5_summary.txt) showed the L1 data pipe -- which also
+// feeds the UMMA operand reads -- 87 % busy, 47 % of it LSU wavefronts of exactly these stores.  Staged, a row costs
+// conflict-free STS.128s and the TMA engine reads the tile at full width.
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// byte offset of 16-byte chunk `c` of row `rho` in a tile of RB-byte rows swizzled SWIZZLE_<RB>B (tile base 1024-aligned)
+template <int RB>
+__device__ __forceinline__ uint32_t swz(uint32_t rho, uint32_t c) {
+  const uint32_t a = rho * (uint32_t)RB + c * 16u;
+  return a ^ (((a >> 7) & (uint32_t)(RB / 16 - 1)) << 4);
+}
+template <int CP>
+__device__ __forceinline__ void epilogue_row_fast_smem(uint32_t taddr, bool store, uint32_t tile, uint32_t rho,
+                                                       const float* s_scale, const float* s_bias, const ResidualRow& rr,
+                                                       const EpiFast f) {
+#pragma unroll
+  for (int c0 = 0; c0 < CP; c0 += 32) {
+    uint32_t acc[32];
+    tmem_ld16(taddr + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[16]>(acc));
+    if (CP > 16) tmem_ld16(taddr + (uint32_t)c0 + 16u, *reinterpret_cast<uint32_t(*)[16]>(acc + 16));
+    tmem_ld_wait();
+    if (store) {
+      uint4 o0, o1;
+      epilogue_chunk16_vals(acc, c0, s_scale, s_bias, rr, f, o0, o1);
+      sts_v4(tile + swz<CP * 2>(rho, c0 / 8), o0);
+      sts_v4(tile + swz<CP * 2>(rho, c0 / 8 + 1), o1);
+      if (CP > 16) {
+        epilogue_chunk16_vals(acc + 16, c0 + 16, s_scale, s_bias, rr, f, o0, o1);
+        sts_v4(tile + swz<CP * 2>(rho, c0 / 8 + 2), o0);
+        sts_v4(tile + swz<CP * 2>(rho, c0 / 8 + 3), o1);
+      }
+    }
+  }
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ void epilogue_row_fast(int CoutPad, uint32_t taddr, bool in_range, __nv_bfloat16* yrow,
                                                   const float* s_scale, const float* s_bias, const ResidualRow& rr,
@@ -458,6 +519,7 @@ struct HaloParams {
   int sub_row_bytes, nsub, sub_tile_bytes, w_sub_bytes;
   int bo_mode;
   int w_rows_per_tap, w_row0;  // packed-weight rows per tap (full CoutPad) and first row of this launch's Cout slice
+  int tma_store, stage_bytes;  // staged epilogue (kd-fused kernel): two swizzled output tiles of stage_bytes each
   const float* scale;
   const float* bias;
   EpiParams epi;
@@ -664,10 +726,10 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 
 // TCOLS = TMEM columns this CTA allocates: 512 (one CTA per SM) or 256 (two co-resident CTAs per SM:
 // while one CTA's MMA warp does its per-plane bookkeeping the other CTA's MMAs keep the tensor pipe busy).
-template <int KSTEPS, int SUBROW, int CP, int TCOLS>
+template <int KSTEPS, int SUBROW, int CP, int TCOLS, bool STAGED>
 __global__ void __launch_bounds__(kThreads, TCOLS == 512 ? 1 : 2)
 conv3d_kdfuse_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
-                     const __grid_constant__ HaloParams p) {
+                     const __grid_constant__ CUtensorMap map_y, const __grid_constant__ HaloParams p) {
   constexpr int K = 3;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[kMaxSlots];
@@ -687,7 +749,8 @@ conv3d_kdfuse_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   static_assert(CP == 16 || CP == 32 || CP == 64, "CoutPad must be 16, 32 or 64");
   static_assert(R == 8u || R == 16u || R == 32u, "accumulator ring must hold 8, 16 or 32 blocks");
   const uint32_t w_base = (smem_u32(smem) + 1023u) & ~1023u;
-  const uint32_t slots_base = w_base + (((uint32_t)(K3 * p.w_tap_bytes) + 1023u) & ~1023u);
+  const uint32_t stage_base = w_base + (((uint32_t)(K3 * p.w_tap_bytes) + 1023u) & ~1023u);   // 2 output tiles (staged epilogue)
+  const uint32_t slots_base = stage_base + 2u * (uint32_t)p.stage_bytes;
   const uint32_t acc_per_col = (uint32_t)p.D + 2u;        // accumulator planes per column: out[-1] .. out[D]
 
   if (threadIdx.x < 64) {
@@ -697,6 +760,7 @@ conv3d_kdfuse_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    if (STAGED) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_y) : "memory");
     for (int s = 0; s < p.nslots; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
@@ -834,9 +898,16 @@ conv3d_kdfuse_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     const int row = quad * 32 + lane;
     const int r_w = row % p.WP, r_h = row / p.WP;
     const int variant = epilogue_variant(p.epi);
+    const bool staged = STAGED && variant == 1;           // uniform over the CTA (host launches STAGED only then)
+    const bool issuer = row == 0;                          // the thread that owns the bulk-store groups
+    const uint32_t rho = (uint32_t)(r_h * p.TWv + r_w);    // row of this thread in the compacted output tile
+    EpiFast f;
+    f.m1 = p.epi.residual_mode == 1 ? 1.f : 0.f;
+    f.m2 = p.epi.residual_mode == 2 ? 1.f : 0.f;
+    f.lo = p.epi.relu ? 0.f : -INFINITY;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
     const int64_t plane_vox = (int64_t)p.H * p.W;
-    uint32_t g = 0;
+    uint32_t g = 0, sbuf = 0;
     int tw = blockIdx.x % p.tiles_w, rest = blockIdx.x / p.tiles_w;
     for (int col = blockIdx.x; col < p.num_cols; col += gridDim.x) {
       const int th = rest % p.tiles_h, n = rest / p.tiles_h;
@@ -851,17 +922,32 @@ conv3d_kdfuse_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         mbar_wait(smem_u32(&acc_full_bar[blk]), (g >> LOGR) & 1u);
         tcgen05_fence_after();
         const uint32_t taddr = lane_base + blk * (uint32_t)CP;
-        if (real) epilogue_row(p.epi, variant, taddr, in_range, vox, s_scale, s_bias, rr);
+        if (real && staged) epilogue_row_fast_smem<CP>(taddr, r_w < p.TWv, stage_base + sbuf * (uint32_t)p.stage_bytes, rho,
+                                                       s_scale, s_bias, rr, f);
+        else if (real) epilogue_row(p.epi, variant, taddr, in_range, vox, s_scale, s_bias, rr);
 #pragma unroll
         for (int c = 0; c < CP; c += 16) tmem_st16_zero(taddr + (uint32_t)c);   // ready for its next output plane
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&acc_empty_bar[blk]));
+        if (real && staged) {
+          // tile complete -> one bulk tensor store.  The issuer first waits until the PREVIOUS store has finished
+          // reading the other buffer, so after this barrier every thread may overwrite that buffer (next plane).
+          fence_proxy_async_smem();
+          if (issuer) tma_store_wait_read0();
+          epi_bar_sync();
+          if (issuer) {
+            tma_store_5d(&map_y, stage_base + sbuf * (uint32_t)p.stage_bytes, 0, tw * p.TWv, th * p.TH, (int)a - 1, n);
+            tma_store_commit();
+          }
+          sbuf ^= 1u;
+        }
       }
       const int nc = col + (int)gridDim.x;
       tw = nc % p.tiles_w; rest = nc / p.tiles_w;
     }
+    if (staged && issuer) tma_store_wait_all();
   }
 
   tcgen05_fence_before();
@@ -891,7 +977,7 @@ conv3d_kdfuse_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 // before waiting for the accumulator and write each output voxel row (64 B) exactly once.
 // Cout = 64 runs as two 32-channel output slices (weights 2 x 110 KB).
 // ==========================================================================================
-constexpr int kDeconvThreads = 320;      // producer, MMA issuer, 8 epilogue warps
+constexpr int kDeconvThreads = 384;      // producer, MMA issuer, 8 epilogue warps, 2 staged-tile managers
 constexpr int kDeconvCP = 32;
 
 struct DeconvParams {
@@ -904,6 +990,7 @@ struct DeconvParams {
   int plane_bytes, slot_bytes, nslots;
   int w_tap_bytes;             // 32 * Cin * 2
   int w_rows_per_tap, w_row0;
+  int stage_bytes;             // one staged output tile: TH x 2*TWv voxel rows of 64 B (4 tiles follow the weights)
   const float* scale;
   const float* bias;
   EpiParams epi;
@@ -938,8 +1025,9 @@ __device__ __forceinline__ int deconv_tap_of_tile(int t) {
 
 struct ResidualRow32 { uint4 q[4]; };
 
-__device__ __forceinline__ void epilogue_chunk16_r32(const uint32_t* acc, int cc, const float* s_scale, const float* s_bias,
-                                                     const ResidualRow32& rr, const EpiFast f, __nv_bfloat16* yrow) {
+__device__ __forceinline__ void epilogue_chunk16_r32_vals(const uint32_t* acc, int cc, const float* s_scale,
+                                                          const float* s_bias, const ResidualRow32& rr, const EpiFast f,
+                                                          uint4& o0, uint4& o1) {
   float v[16];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -958,14 +1046,14 @@ __device__ __forceinline__ void epilogue_chunk16_r32(const uint32_t* acc, int cc
     v[2 * j] = fmaf(r0, f.m2, fmaxf(fmaf(r0, f.m1, v[2 * j]), f.lo));
     v[2 * j + 1] = fmaf(r1, f.m2, fmaxf(fmaf(r1, f.m1, v[2 * j + 1]), f.lo));
   }
-  uint4* o = reinterpret_cast<uint4*>(yrow + cc);
-  o[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-  o[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+  o0 = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  o1 = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
 }
 
 template <int KSTEPS, int SUBROW>
 __global__ void __launch_bounds__(kDeconvThreads, 1)
 conv3d_deconv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                     const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_r,
                      const __grid_constant__ DeconvParams p) {
   constexpr int CP = kDeconvCP;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -974,13 +1062,16 @@ conv3d_deconv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   __shared__ __align__(8) uint64_t w_bar;
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ __align__(8) uint64_t tile_bar[4];            // staged tile b holds its residual (or is simply free again)
+  __shared__ __align__(8) uint64_t ready_bar[4];           // staged tile b has been computed by its four warps
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float s_scale[32], s_bias[32];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t w_base = (smem_u32(smem) + 1023u) & ~1023u;
-  const uint32_t slots_base = w_base + (((uint32_t)(27 * p.w_tap_bytes) + 1023u) & ~1023u);
+  const uint32_t stage_base = w_base + (((uint32_t)(27 * p.w_tap_bytes) + 1023u) & ~1023u);
+  const uint32_t slots_base = stage_base + 4u * (uint32_t)p.stage_bytes;
 
   if (threadIdx.x < 32) {
     s_scale[threadIdx.x] = p.scale ? p.scale[threadIdx.x] : 1.f;
@@ -989,6 +1080,12 @@ conv3d_deconv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_y) : "memory");
+    if (p.epi.residual_mode) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_r) : "memory");
+    for (int b = 0; b < 4; ++b) {
+      mbar_init(smem_u32(&tile_bar[b]), 1);
+      mbar_init(smem_u32(&ready_bar[b]), 4);               // one arrive per epilogue warp of the group
+    }
     for (int s = 0; s < p.nslots; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
@@ -1099,60 +1196,123 @@ conv3d_deconv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
       }
     }
   } else {
-    // ===================== epilogue (warps 2..9) =====================
+    // ===================== epilogue (warps 2..9) + staged-tile managers (warps 10, 11) =====================
+    // Two groups of four epilogue warps; group g owns the output depth parity pd = g (classes 4g .. 4g+3).  A
+    // direct store would have every lane write 16 B of its own voxel row with 128 B between lanes (stride-2
+    // output): 32 L1 wavefronts per instruction, and ncu showed exactly that -- LSU wavefronts 72 % of the cycles,
+    // tensor pipe 9 % (profiles/r01_step_v5_summary.txt).  Instead, per (tile-step, ph) the group works IN PLACE on
+    // a staged tile of TH x 2*TWv output voxel rows (both pw classes interleaved = contiguous in W), swizzled
+    // SWIZZLE_64B: the residual rows arrive by one TMA tensor load, each thread updates its two rows with
+    // conflict-free LDS/STS.128, one TMA tensor store writes the tile (image edges are clipped by the TMA unit).
+    // Each group double-buffers its tile.  The loads / stores are issued by one manager thread per group (its own
+    // warp, so that waiting for "the store has read the tile" never stalls an epilogue warp); epilogue warps and
+    // manager talk through two mbarriers per tile (armed: residual landed or tile free; ready: tile computed).
+    const bool manager = warp >= 10;
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;              // output depth parity handled by this warp (classes 4*half .. 4*half+3)
+    const int grp = manager ? warp - 10 : (warp - 2) >> 2;        // output depth parity handled by this group
     const int row = quad * 32 + lane;
     const int r_w = row % p.WP, r_h = row / p.WP;
-    const int Do = 2 * p.Di, Ho = 2 * p.Hi, Wo = 2 * p.Wi;
-    EpiFast f;
-    f.m1 = p.epi.residual_mode == 1 ? 1.f : 0.f;
-    f.m2 = p.epi.residual_mode == 2 ? 1.f : 0.f;
-    f.lo = p.epi.relu ? 0.f : -INFINITY;
-    __nv_bfloat16* const ybase = reinterpret_cast<__nv_bfloat16*>(p.epi.y) + p.epi.out_coffset;
-    const __nv_bfloat16* const rbase = p.epi.residual + p.epi.res_coffset;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 4 * CP);
-    uint32_t it = 0;
-    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
-      int n, h0, w0, j0, nj;
-      decode(unit, n, h0, w0, j0, nj);
-      const int iw = w0 + r_w, ih = h0 + r_h;
-      const bool in_range = r_w < p.TWv && iw < p.Wi && ih < p.Hi;
-      for (int i = 0; i < nj; ++i, ++it) {
-        const int od = 2 * (j0 + i) + half;
-        const int64_t vox00 = (((int64_t)n * Do + od) * Ho + 2 * ih) * Wo + 2 * iw;   // class (ph, pw) = (0, 0)
-        ResidualRow32 rr[4];
-#pragma unroll
-        for (int ci = 0; ci < 4; ++ci) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) rr[ci].q[q] = make_uint4(0u, 0u, 0u, 0u);
-          if (p.epi.residual_mode && in_range) {
-            const int64_t vox = vox00 + (int64_t)(ci >> 1) * Wo + (ci & 1);
-            const uint4* rp = reinterpret_cast<const uint4*>(rbase + vox * p.epi.res_cstride);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) rr[ci].q[q] = __ldg(rp + q);
+    const bool has_res = p.epi.residual_mode != 0;
+    const int Do = 2 * p.Di;
+    const uint32_t tile0 = stage_base + (uint32_t)(2 * grp) * (uint32_t)p.stage_bytes;
+    if (manager) {
+      if (lane == 0) {
+        // hand tile `b` to item (n, h0, w0, j, ph): residual load, or a plain "tile is free" arrive
+        auto arm_tile = [&](uint32_t b, bool valid_item, int n, int h0, int w0, int j, int ph) {
+          const uint32_t bar = smem_u32(&tile_bar[2 * grp + b]);
+          if (valid_item && has_res) {
+            mbar_expect_tx(bar, (uint32_t)p.stage_bytes);
+            tma_load_5d(tile0 + b * (uint32_t)p.stage_bytes, &map_r, bar, 0, 2 * w0, ph, h0, n * Do + 2 * j + grp);
+          } else {
+            mbar_arrive(bar);
+          }
+        };
+        uint32_t item = 0;
+        int unit = blockIdx.x;
+        if (unit < p.num_units) {                            // prologue: the first tile-step's two items
+          int n, h0, w0, j0, nj;
+          decode(unit, n, h0, w0, j0, nj);
+          arm_tile(0u, true, n, h0, w0, j0, 0);
+          arm_tile(1u, true, n, h0, w0, j0, 1);
+        }
+        for (; unit < p.num_units; unit += gridDim.x) {
+          int n, h0, w0, j0, nj;
+          decode(unit, n, h0, w0, j0, nj);
+          for (int i = 0; i < nj; ++i) {
+            // the tile-step after this one (what the freed tiles are armed for)
+            int nn = n, nh0 = h0, nw0 = w0, j_next = j0 + i + 1;
+            bool next_valid = true;
+            if (i + 1 >= nj) {
+              const int nu = unit + (int)gridDim.x;
+              next_valid = nu < p.num_units;
+              if (next_valid) { int t1; decode(nu, nn, nh0, nw0, j_next, t1); }
+            }
+            for (int ph = 0; ph < 2; ++ph, ++item) {
+              const uint32_t b = item & 1u;
+              mbar_wait(smem_u32(&ready_bar[2 * grp + b]), (item >> 1) & 1u);
+              tma_store_5d(&map_y, tile0 + b * (uint32_t)p.stage_bytes, 0, 2 * w0, ph, h0, n * Do + 2 * (j0 + i) + grp);
+              tma_store_commit();
+              tma_store_wait_read0();                        // the tile has been read: re-arm it for item + 2
+              arm_tile(b, next_valid, nn, nh0, nw0, j_next, ph);
+            }
           }
         }
-        const uint32_t buf = it & 1u;
-        mbar_wait(smem_u32(&tmem_full_bar[buf]), (it >> 1) & 1u);
-        tcgen05_fence_after();
+        tma_store_wait_all();
+      }
+    } else {
+      EpiFast f;
+      f.m1 = p.epi.residual_mode == 1 ? 1.f : 0.f;
+      f.m2 = p.epi.residual_mode == 2 ? 1.f : 0.f;
+      f.lo = p.epi.relu ? 0.f : -INFINITY;
+      const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(grp * 4 * CP);
+      const uint32_t rho0 = (uint32_t)(r_h * 2 * p.TWv + 2 * r_w);   // this thread's pw = 0 row in the staged tile
+      uint32_t it = 0, item = 0;                     // tile-steps / staged items processed by this group
+      for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+        int n, h0, w0, j0, nj;
+        decode(unit, n, h0, w0, j0, nj);
+        for (int i = 0; i < nj; ++i, ++it) {
+          const uint32_t abuf = it & 1u;
 #pragma unroll
-        for (int ci = 0; ci < 4; ++ci) {
-          uint32_t acc[32];
-          const uint32_t taddr = lane_base + buf * 256u + (uint32_t)(ci * CP);
-          tmem_ld16(taddr, *reinterpret_cast<uint32_t(*)[16]>(acc));
-          tmem_ld16(taddr + 16u, *reinterpret_cast<uint32_t(*)[16]>(acc + 16));
-          tmem_ld_wait();
-          if (in_range) {
-            const int64_t vox = vox00 + (int64_t)(ci >> 1) * Wo + (ci & 1);
-            __nv_bfloat16* yrow = ybase + vox * p.epi.out_cstride;
-            epilogue_chunk16_r32(acc, 0, s_scale, s_bias, rr[ci], f, yrow);
-            epilogue_chunk16_r32(acc + 16, 16, s_scale, s_bias, rr[ci], f, yrow);
+          for (int ph = 0; ph < 2; ++ph, ++item) {
+            const uint32_t b = item & 1u;
+            const uint32_t tile = tile0 + b * (uint32_t)p.stage_bytes;
+            mbar_wait(smem_u32(&tile_bar[2 * grp + b]), (item >> 1) & 1u);          // residual landed / tile free
+            if (ph == 0) {
+              mbar_wait(smem_u32(&tmem_full_bar[abuf]), (it >> 1) & 1u);
+              tcgen05_fence_after();
+            }
+#pragma unroll
+            for (int pw = 0; pw < 2; ++pw) {
+              uint32_t acc[32];
+              const uint32_t taddr = lane_base + abuf * 256u + (uint32_t)((ph * 2 + pw) * CP);
+              tmem_ld16(taddr, *reinterpret_cast<uint32_t(*)[16]>(acc));
+              tmem_ld16(taddr + 16u, *reinterpret_cast<uint32_t(*)[16]>(acc + 16));
+              tmem_ld_wait();
+              if (r_w < p.TWv) {
+                const uint32_t rho = rho0 + (uint32_t)pw;
+                ResidualRow32 rr;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  rr.q[q] = has_res ? lds_v4(tile + swz<64>(rho, (uint32_t)q)) : make_uint4(0u, 0u, 0u, 0u);
+                uint4 o0, o1, o2, o3;
+                epilogue_chunk16_r32_vals(acc, 0, s_scale, s_bias, rr, f, o0, o1);
+                epilogue_chunk16_r32_vals(acc + 16, 16, s_scale, s_bias, rr, f, o2, o3);
+                sts_v4(tile + swz<64>(rho, 0u), o0);
+                sts_v4(tile + swz<64>(rho, 1u), o1);
+                sts_v4(tile + swz<64>(rho, 2u), o2);
+                sts_v4(tile + swz<64>(rho, 3u), o3);
+              }
+            }
+            if (ph == 1) {                                   // all eight classes of this tile-step have left TMEM
+              tcgen05_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[abuf]));
+            }
+            fence_proxy_async_smem();                        // generic-proxy writes -> visible to the TMA store
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&ready_bar[2 * grp + b]));
           }
         }
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[buf]));
       }
     }
   }
@@ -1555,19 +1715,46 @@ int launch_halo(const void* x, const void* w_packed, const float* scale, const f
   const int K3 = d.kernel * d.kernel * d.kernel;
   p.w_tap_bytes = cp.CoutPad * d.Cin * 2;
   const int w_total = round_up(K3 * p.w_tap_bytes, 1024);
-  const int budget = 225 * 1024 - 1024 - w_total;       // dynamic smem left for the plane ring
-  // pick the row pitch: maximise useful MMA rows, subject to the ring fitting (>= hw + 2 slots)
-  double best = -1;
-  for (int wp = 16; wp <= 64; wp <<= 1) {
-    const int twv = wp - hw, th = 128 / wp;
-    if (twv <= 0) continue;
-    const int slot = p.nsub * round_up(((th + hw) * wp + 16) * p.sub_row_bytes, 1024);
-    if (budget < slot * (hw + 2)) continue;
-    double eff = ((double)d.Wi / (ceil_div(d.Wi, twv) * wp)) * ((double)d.Hi / (ceil_div(d.Hi, th) * th));
-    if (eff > best) { best = eff; p.WP = wp; p.TH = th; p.TWv = twv; p.slot_bytes = slot; }
+  const char* mode = getenv("SNVC_CONV_MODE");
+  const bool kdfuse = d.dilation == 1 && !(mode && mode[0] == 'h');     // SNVC_CONV_MODE=halo: v2 (A/B runs)
+  if (!kdfuse && ncout > 0) return 1;                                   // Cout slicing is implemented by the kd-fused kernel only
+  // staged epilogue (bulk tensor store of a swizzled smem tile), opt-in with SNVC_CONV_STORE=staged.  Measured
+  // (profiles/r01_umma_rate.txt, r01_layer_times_staged_vs_direct.txt): an SS-mode M=128,K=16 MMA costs
+  // max(71.6, N/2) cycles, so at N = 96 this kernel is bound by MMA issue (18 x 71.6 = 1289 of the 1319 cycles
+  // per plane tile), not by the L1 data pipe: removing the store wavefronts changed nothing (615 vs 614 us) and
+  // the smaller plane ring made the residual layer slower (773 vs 684 us).  Direct stores stay the default.
+  const char* smode = getenv("SNVC_CONV_STORE");
+  const bool staged = kdfuse && cp.Cout == cp.CoutPad && !cp.sigmoid && !cp.out_f32 &&
+                      ((cp.out_cstride | cp.out_coffset) & 7) == 0 &&
+                      (cp.CoutPad == 16 || cp.CoutPad == 32 || cp.CoutPad == 64) && (smode && smode[0] == 's');
+  // pick the row pitch: maximise useful MMA rows, subject to the ring fitting (>= hw + 2 slots) in `budget` bytes
+  auto pick = [&](int budget, int min_slots) {
+    double best = -1;
+    for (int wp = 16; wp <= 64; wp <<= 1) {
+      const int twv = wp - hw, th = 128 / wp;
+      if (twv <= 0) continue;
+      const int slot = p.nsub * round_up(((th + hw) * wp + 16) * p.sub_row_bytes, 1024);
+      const int stage = staged ? round_up(th * twv * cp.CoutPad * 2, 1024) : 0;
+      if (budget - 2 * stage < slot * min_slots) continue;
+      double eff = ((double)d.Wi / (ceil_div(d.Wi, twv) * wp)) * ((double)d.Hi / (ceil_div(d.Hi, th) * th));
+      if (eff > best) { best = eff; p.WP = wp; p.TH = th; p.TWv = twv; p.slot_bytes = slot; p.stage_bytes = stage; }
+    }
+    if (best < 0) return false;
+    p.nslots = std::min(kMaxSlots, (budget - 2 * p.stage_bytes) / p.slot_bytes);
+    return true;
+  };
+  if (!pick(225 * 1024 - 1024 - w_total, hw + 2)) return 1;            // weights + ring do not fit: per-tap kernel
+  int ctas_per_sm = 1;
+  if (kdfuse && cp.CoutPad <= 32) {
+    // two CTAs per SM when weights + staging + a 3-slot plane ring fit in half the shared memory (Cin = Cout = 32
+    // does): while one CTA's MMA warp does its per-plane bookkeeping the other CTA's MMAs keep the tensor pipe busy
+    const int half_budget = (233472 - 2 * 1024) / 2 - 2048 /* static */ - 1024 /* alignment */;
+    const char* occ = getenv("SNVC_CONV_OCC");
+    HaloParams keep = p;
+    if (!(occ && occ[0] == '1') && pick(half_budget - w_total, staged ? 3 : 4)) ctas_per_sm = 2;
+    else p = keep;
   }
-  if (best < 0) return 1;                                // weights + ring do not fit: per-tap kernel
-  p.nslots = std::min(kMaxSlots, budget / p.slot_bytes);
+  p.tma_store = staged ? 1 : 0;
   p.sub_tile_bytes = p.slot_bytes / p.nsub;
   p.w_sub_bytes = cp.CoutPad * p.sub_row_bytes;
   p.plane_bytes = (p.TH + hw) * p.WP * row_bytes;
@@ -1575,7 +1762,7 @@ int launch_halo(const void* x, const void* w_packed, const float* scale, const f
   const int64_t ncols = (int64_t)d.N * p.tiles_h * p.tiles_w;
   SNVC_CHECK_ARG(ncols < (1ll << 31), "too many tile columns");
   p.num_cols = (int)ncols;
-  size_t smem = (size_t)w_total + (size_t)p.nslots * p.slot_bytes + 1024;
+  const size_t smem = (size_t)w_total + 2 * (size_t)p.stage_bytes + (size_t)p.nslots * p.slot_bytes + 1024;
 
   CUtensorMap map_x, map_w;
   {
@@ -1600,45 +1787,53 @@ int launch_halo(const void* x, const void* w_packed, const float* scale, const f
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail((int)r, "cuTensorMapEncodeTiled(w, halo) failed with CUresult %d", (int)r);
   }
-  void (*kern)(const CUtensorMap, const CUtensorMap, const HaloParams) = nullptr;
-  const char* mode = getenv("SNVC_CONV_MODE");
-  const bool kdfuse = d.dilation == 1 && !(mode && mode[0] == 'h');     // SNVC_CONV_MODE=halo: v2 (A/B runs)
-  if (!kdfuse && ncout > 0) return 1;                                   // Cout slicing is implemented by the kd-fused kernel only
-  switch (d.Cin) {
-    case 16: kern = conv3d_halo_kernel<3, 1, 32>; break;
-    case 32: kern = conv3d_halo_kernel<3, 2, 64>; break;
-    case 64: kern = conv3d_halo_kernel<3, 4, 128>; break;
-  }
-  int ctas_per_sm = 1;
-  if (kdfuse) {
-    // two CTAs per SM when weights + a 4-slot plane ring fit in half the shared memory (Cin = Cout = 32 does)
-    const size_t half_budget = (233472 - 2 * 1024) / 2 - 2048 /* static */ - 1024 /* alignment */;
-    const char* occ = getenv("SNVC_CONV_OCC");
-    if (cp.CoutPad <= 32 && (size_t)w_total + 4 * (size_t)p.slot_bytes <= half_budget && !(occ && occ[0] == '1')) {
-      ctas_per_sm = 2;
-      p.nslots = (int)std::min<size_t>(kMaxSlots, (half_budget - w_total) / p.slot_bytes);
-      smem = (size_t)w_total + (size_t)p.nslots * p.slot_bytes + 1024;
-    }
-#define SNVC_KDFUSE_T(KS, SR, T)                                                                         \
-    kern = cp.CoutPad == 16 ? conv3d_kdfuse_kernel<KS, SR, 16, T>                                        \
-                            : (cp.CoutPad == 32 ? conv3d_kdfuse_kernel<KS, SR, 32, T> : nullptr)
-#define SNVC_KDFUSE(KS, SR)                                                                              \
-    if (ctas_per_sm == 2) { SNVC_KDFUSE_T(KS, SR, 256); }                                                \
-    else if (cp.CoutPad == 64) kern = conv3d_kdfuse_kernel<KS, SR, 64, 512>;                             \
-    else { SNVC_KDFUSE_T(KS, SR, 512); }
+  if (!kdfuse) {
+    void (*kern)(const CUtensorMap, const CUtensorMap, const HaloParams) = nullptr;
     switch (d.Cin) {
-      case 16: SNVC_KDFUSE(1, 32); break;
-      case 32: SNVC_KDFUSE(2, 64); break;
-      case 64: SNVC_KDFUSE(4, 128); break;
+      case 16: kern = conv3d_halo_kernel<3, 1, 32>; break;
+      case 32: kern = conv3d_halo_kernel<3, 2, 64>; break;
+      case 64: kern = conv3d_halo_kernel<3, 4, 128>; break;
     }
+    SNVC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = std::min(p.num_cols, sm_count());
+    kern<<<grid, kThreads, smem, stream>>>(map_x, map_w, p);
+    return launch_status("conv3d_halo_kernel");
+  }
+  CUtensorMap map_y = map_w;                             // (unused unless staged)
+  if (staged) {
+    // output slice viewed as (Cout, W, H, D, N); box = the compacted tile (Cout, TWv, TH); edges are clipped by TMA
+    const cuuint64_t cs = (cuuint64_t)cp.out_cstride * 2;
+    cuuint64_t dims[5] = {(cuuint64_t)cp.Cout, (cuuint64_t)d.Wi, (cuuint64_t)d.Hi, (cuuint64_t)d.Di, (cuuint64_t)d.N};
+    cuuint64_t strides[4] = {cs, (cuuint64_t)d.Wi * cs, (cuuint64_t)d.Hi * d.Wi * cs, (cuuint64_t)d.Di * d.Hi * d.Wi * cs};
+    cuuint32_t box[5] = {(cuuint32_t)cp.Cout, (cuuint32_t)p.TWv, (cuuint32_t)p.TH, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    void* ybase = static_cast<char*>(y) + (size_t)cp.out_coffset * 2;
+    CUresult r = enc(&map_y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, ybase, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_mode(cp.Cout * 2), CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail((int)r, "cuTensorMapEncodeTiled(y, staged store) failed with CUresult %d", (int)r);
+  }
+  void (*kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const HaloParams) = nullptr;
+#define SNVC_KDFUSE_S(KS, SR, C, T) (staged ? conv3d_kdfuse_kernel<KS, SR, C, T, true> : conv3d_kdfuse_kernel<KS, SR, C, T, false>)
+#define SNVC_KDFUSE_T(KS, SR, T)                                                                         \
+  kern = cp.CoutPad == 16 ? SNVC_KDFUSE_S(KS, SR, 16, T) : (cp.CoutPad == 32 ? SNVC_KDFUSE_S(KS, SR, 32, T) : nullptr)
+#define SNVC_KDFUSE(KS, SR)                                                                              \
+  if (ctas_per_sm == 2) { SNVC_KDFUSE_T(KS, SR, 256); }                                                  \
+  else if (cp.CoutPad == 64) kern = SNVC_KDFUSE_S(KS, SR, 64, 512);                                      \
+  else { SNVC_KDFUSE_T(KS, SR, 512); }
+  switch (d.Cin) {
+    case 16: SNVC_KDFUSE(1, 32); break;
+    case 32: SNVC_KDFUSE(2, 64); break;
+    case 64: SNVC_KDFUSE(4, 128); break;
+  }
 #undef SNVC_KDFUSE
 #undef SNVC_KDFUSE_T
-    if (!kern) return 1;                                  // CoutPad 48: per-tap kernel
-  }
+#undef SNVC_KDFUSE_S
+  if (!kern) return 1;                                  // CoutPad 48: per-tap kernel
   SNVC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = std::min(p.num_cols, ctas_per_sm * sm_count());
-  kern<<<grid, kThreads, smem, stream>>>(map_x, map_w, p);
-  return launch_status("conv3d_halo_kernel");
+  kern<<<grid, kThreads, smem, stream>>>(map_x, map_w, map_y, p);
+  return launch_status("conv3d_kdfuse_kernel");
 }
 
 // ---- v4 host side: fused transposed conv; returns 1 when not eligible (caller uses the per-class launches)
@@ -1661,17 +1856,20 @@ int launch_deconv(const void* x, const void* w_packed, const float* scale, const
   const int row_bytes = d.Cin * 2;
   p.w_tap_bytes = kDeconvCP * row_bytes;
   const int w_total = round_up(27 * p.w_tap_bytes, 1024);
-  const int budget = 225 * 1024 - 1024 - w_total;
+  const int budget = 226 * 1024 - 1024 - w_total;          // 227 KB per CTA minus static smem and alignment
   double best = -1;
   for (int wp = 16; wp <= 64; wp <<= 1) {
     const int twv = wp - 1, th = 128 / wp;
-    const int slot = round_up(((th + 1) * wp + 16) * row_bytes, 1024);
-    if (budget < slot * 3) continue;
+    // a plane slot holds the (TH+1) x WP box (= 128 + WP rows) plus the one row the most shifted MMA window
+    // (WP + 1 rows down) reads past it
+    const int slot = round_up((128 + wp + 1) * row_bytes, 1024);
+    const int stage = round_up(th * 2 * twv * kDeconvCP * 2, 1024);           // one staged output tile (64-byte rows)
+    if (budget - 4 * stage < slot * 3) continue;
     const double eff = ((double)d.Wi / (ceil_div(d.Wi, twv) * wp)) * ((double)d.Hi / (ceil_div(d.Hi, th) * th));
-    if (eff > best) { best = eff; p.WP = wp; p.TH = th; p.TWv = twv; p.slot_bytes = slot; }
+    if (eff > best) { best = eff; p.WP = wp; p.TH = th; p.TWv = twv; p.slot_bytes = slot; p.stage_bytes = stage; }
   }
   if (best < 0) return 1;
-  p.nslots = std::min(kMaxSlots, budget / p.slot_bytes);
+  p.nslots = std::min(kMaxSlots, (budget - 4 * p.stage_bytes) / p.slot_bytes);
   p.plane_bytes = (p.TH + 1) * p.WP * row_bytes;
   p.tiles_h = (int)ceil_div(d.Hi, p.TH); p.tiles_w = (int)ceil_div(d.Wi, p.TWv);
   // depth chunks: enough work units for ~6 waves when the volume allows it (each chunk re-loads one plane)
@@ -1681,9 +1879,9 @@ int launch_deconv(const void* x, const void* w_packed, const float* scale, const
   p.DC = (int)ceil_div(d.Di, nchunk);
   p.nchunk = (int)ceil_div(d.Di, p.DC);
   const int64_t units = cols * p.nchunk;
-  SNVC_CHECK_ARG(units < (1ll << 31), "too many work units");
+  SNVC_CHECK_ARG(units < (1ll << 31) && (int64_t)d.N * d.Di * 2 < (1ll << 31), "too many work units");
   p.num_units = (int)units;
-  const size_t smem = (size_t)w_total + (size_t)p.nslots * p.slot_bytes + 1024;
+  const size_t smem = (size_t)w_total + 4 * (size_t)p.stage_bytes + (size_t)p.nslots * p.slot_bytes + 1024;
 
   CUtensorMap map_x, map_w;
   {
@@ -1708,15 +1906,35 @@ int launch_deconv(const void* x, const void* w_packed, const float* scale, const
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail((int)r, "cuTensorMapEncodeTiled(w, deconv) failed with CUresult %d", (int)r);
   }
-  void (*kern)(const CUtensorMap, const CUtensorMap, const DeconvParams) = nullptr;
+  // staged tiles: output (and residual) viewed as (32 ch, Wo, ph, Hi, N*Do planes); one box = TH rows x 2*TWv voxels
+  CUtensorMap map_y, map_r;
+  for (int which = 0; which < 2; ++which) {
+    const bool res = which == 1;
+    if (res && !cp.residual_mode) { map_r = map_y; break; }
+    const cuuint64_t cs = (cuuint64_t)(res ? cp.res_cstride : cp.out_cstride) * 2;
+    const int coff = (res ? cp.res_coffset : cp.out_coffset) + cout0;
+    const int Wo = 2 * d.Wi;
+    cuuint64_t dims[5] = {(cuuint64_t)kDeconvCP, (cuuint64_t)Wo, 2, (cuuint64_t)d.Hi, (cuuint64_t)d.N * 2 * d.Di};
+    cuuint64_t strides[4] = {cs, (cuuint64_t)Wo * cs, (cuuint64_t)2 * Wo * cs, (cuuint64_t)2 * d.Hi * Wo * cs};
+    cuuint32_t box[5] = {(cuuint32_t)kDeconvCP, (cuuint32_t)(2 * p.TWv), 1, (cuuint32_t)p.TH, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    char* base = (res ? static_cast<char*>(const_cast<void*>(residual)) : static_cast<char*>(y)) + (size_t)coff * 2;
+    CUresult r = enc(res ? &map_r : &map_y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                     res ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail((int)r, "cuTensorMapEncodeTiled(%s, deconv) failed with CUresult %d", res ? "residual" : "y", (int)r);
+  }
+  void (*kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const DeconvParams) = nullptr;
   switch (d.Cin) {
     case 16: kern = conv3d_deconv_kernel<1, 32>; break;
     case 32: kern = conv3d_deconv_kernel<2, 64>; break;
     case 64: kern = conv3d_deconv_kernel<4, 128>; break;
   }
   SNVC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = std::min(p.num_units, sm_count());
-  kern<<<grid, kDeconvThreads, smem, stream>>>(map_x, map_w, p);
+  int grid = std::min(p.num_units, sm_count());
+  if (const char* mg = getenv("SNVC_CONV_MAXGRID")) grid = std::max(1, std::min(grid, atoi(mg)));   // tests: force ring wrap-around
+  kern<<<grid, kDeconvThreads, smem, stream>>>(map_x, map_w, map_y, map_r, p);
   return launch_status("conv3d_deconv_kernel");
 }
 

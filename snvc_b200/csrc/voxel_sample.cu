@@ -168,6 +168,7 @@ __global__ void roi_indices_kernel(const float* __restrict__ pts, int32_t* __res
 
 // ---- A4: frustum-to-voxel lift --------------------------------------------------------------
 struct LiftGeom {
+  int range_ordered;   // all three CV ranges are given low-to-high (enables the conservative early-out)
   float cv[6];   // CV_X_MIN, CV_X_MAX, CV_Y_MIN, CV_Y_MAX, CV_Z_MIN, CV_Z_MAX
   int D, H, W;   // extent of the volume tensor passed in (z-bins, rows, cols)
   int Dt, d_base;// depth-slab mode: the tensor holds planes [d_base, d_base + D) of a Dt-plane volume (else Dt = D, 0)
@@ -182,15 +183,17 @@ struct Trilinear {
 };
 
 // oracle/global_branch.py `lift_grid`: 4-term dots left to right, then divide, normalise
-__device__ __forceinline__ Trilinear trilinear_setup(const float* __restrict__ Pm, float x, float y, float z,
-                                                     const LiftGeom& g) {
+__device__ __forceinline__ void projection_dots(const float* __restrict__ Pm, float x, float y, float z, float& uh,
+                                                float& vh, float& wh) {
   auto row = [&](int r) {
     float a = __fmul_rn(Pm[4 * r + 0], x);
     a = __fadd_rn(a, __fmul_rn(Pm[4 * r + 1], y));
     a = __fadd_rn(a, __fmul_rn(Pm[4 * r + 2], z));
     return __fadd_rn(a, Pm[4 * r + 3]);
   };
-  float uh = row(0), vh = row(1), wh = row(2);
+  uh = row(0); vh = row(1); wh = row(2);
+}
+__device__ __forceinline__ Trilinear trilinear_finish(float uh, float vh, float wh, float z, const LiftGeom& g) {
   float u = __fdiv_rn(uh, wh), v = __fdiv_rn(vh, wh);
   auto norm = [](float c, float lo, float hi) {
     return __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(c, lo), __fsub_rn(hi, lo)), 2.f), 1.f);
@@ -208,6 +211,24 @@ __device__ __forceinline__ Trilinear trilinear_setup(const float* __restrict__ P
   t.wy[0] = __fsub_rn(__fadd_rn(fy0, 1.f), iy); t.wy[1] = __fsub_rn(iy, fy0);
   t.wz[0] = __fsub_rn(__fadd_rn(fz0, 1.f), iz); t.wz[1] = __fsub_rn(iz, fz0);
   return t;
+}
+__device__ __forceinline__ Trilinear trilinear_setup(const float* __restrict__ Pm, float x, float y, float z,
+                                                     const LiftGeom& g) {
+  float uh, vh, wh;
+  projection_dots(Pm, x, y, z, uh, vh, wh);
+  return trilinear_finish(uh, vh, wh, z, g);
+}
+// Conservative early-out of the cooperative lift: true only if the exact computation above is certain to give
+// valid == false (image coordinate outside the cost-volume range by a margin ~1e-3 of the range, four orders of
+// magnitude above the fp32 rounding of the quotient).  ~42 % of the KITTI voxel grid is outside the frustum, in
+// runs much longer than a warp, so most warps skip the five IEEE divisions and the corner set-up entirely.
+__device__ __forceinline__ bool clearly_outside(float uh, float vh, float wh, float z, const LiftGeom& g) {
+  if (!(wh > 1e-6f) || !(wh < 1e30f)) return false;
+  const float mx = 1e-3f * (g.cv[1] - g.cv[0]) + 1e-3f, my = 1e-3f * (g.cv[3] - g.cv[2]) + 1e-3f,
+              mz = 1e-3f * (g.cv[5] - g.cv[4]) + 1e-3f;
+  // fabs() of the products: the ranges are given low-to-high (checked on the host); written for wh > 0
+  return uh < (g.cv[0] - mx) * wh || uh > (g.cv[1] + mx) * wh || vh < (g.cv[2] - my) * wh || vh > (g.cv[3] + my) * wh ||
+         z < g.cv[4] - mz || z > g.cv[5] + mz;
 }
 
 // NDHWC bf16 volume -> NDHWC (bf16|f32) or NCDHW f32.  One thread per voxel: the projection / index /
@@ -309,7 +330,7 @@ __device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
 struct LiftDivs { FastDiv X, Y, Z; };
 
 template <typename OutT, bool EXACT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 lift_ndhwc_coop_kernel(const __nv_bfloat16* __restrict__ vol, const float* __restrict__ proj,
                        const float* __restrict__ zs, const float* __restrict__ ys, const float* __restrict__ xs,
                        OutT* __restrict__ out, uint8_t* __restrict__ valid, int C, int log_lpv, LiftGeom g,
@@ -334,21 +355,47 @@ lift_ndhwc_coop_kernel(const __nv_bfloat16* __restrict__ vol, const float* __res
       const uint32_t q1 = fdiv(nv, dv.X), xi = nv - q1 * dv.X.d;
       const uint32_t q2 = fdiv(q1, dv.Y), yi = q1 - q2 * dv.Y.d;
       const uint32_t n = fdiv(q2, dv.Z), zi = q2 - n * dv.Z.d;
-      const Trilinear t = trilinear_setup(proj + n * 12, __ldg(xs + xi), __ldg(ys + yi), __ldg(zs + zi), g);
-      if (valid) valid[nv] = t.valid ? 1 : 0;
+      const float zc = __ldg(zs + zi);
+      float uh, vh, wh;
+      projection_dots(proj + n * 12, __ldg(xs + xi), __ldg(ys + yi), zc, uh, vh, wh);
+      bool tvalid = false;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {   // tnw,tne,tsw,tse,bnw,bne,bsw,bse
-        const int xx = t.x0 + (k & 1), yy = t.y0 + ((k >> 1) & 1), zz = t.z0 + (k >> 2) - g.d_base;
-        const bool in = t.valid && xx >= 0 && xx < g.W && yy >= 0 && yy < g.H && zz >= 0 && zz < g.D;
-        m |= in ? (1u << k) : 0u;
-        ww[k] = __fmul_rn(__fmul_rn(t.wx[k & 1], t.wy[(k >> 1) & 1]), t.wz[k >> 2]);
+      for (int k = 0; k < 8; ++k) ww[k] = 0.f;
+      if (!(g.range_ordered && clearly_outside(uh, vh, wh, zc, g))) {
+        const Trilinear t = trilinear_finish(uh, vh, wh, zc, g);
+        tvalid = t.valid;
+        // per-axis in-bounds bits of the low / high corner (unsigned compare = both bounds)
+        const int z0 = t.z0 - g.d_base;
+        const bool x0i = (unsigned)t.x0 < (unsigned)g.W, x1i = (unsigned)(t.x0 + 1) < (unsigned)g.W;
+        const bool y0i = (unsigned)t.y0 < (unsigned)g.H, y1i = (unsigned)(t.y0 + 1) < (unsigned)g.H;
+        const bool z0i = (unsigned)z0 < (unsigned)g.D, z1i = (unsigned)(z0 + 1) < (unsigned)g.D;
+        const unsigned mxy = (x0i && y0i ? 1u : 0u) | (x1i && y0i ? 2u : 0u) | (x0i && y1i ? 4u : 0u) | (x1i && y1i ? 8u : 0u);
+        m = t.valid ? ((z0i ? mxy : 0u) | (z1i ? mxy << 4 : 0u)) : 0u;   // tnw,tne,tsw,tse,bnw,bne,bsw,bse
+        const float wxy[4] = {__fmul_rn(t.wx[0], t.wy[0]), __fmul_rn(t.wx[1], t.wy[0]), __fmul_rn(t.wx[0], t.wy[1]),
+                              __fmul_rn(t.wx[1], t.wy[1])};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) ww[k] = __fmul_rn(wxy[k & 3], t.wz[k >> 2]);
+        // voxel index of corner 0 in the whole batch (may be "negative" when corner 0 itself is outside; only
+        // in-bounds corners are dereferenced).  Host guarantees N*D*H*W < 2^31.
+        base = m ? (int)n * DHW + (z0 * g.H + t.y0) * g.W + t.x0 : 0;
       }
-      // voxel index of corner 0 in the whole batch (may be "negative" when corner 0 itself is outside; only
-      // in-bounds corners are dereferenced).  Host guarantees N*D*H*W < 2^31.
-      base = m ? (int)n * DHW + ((t.z0 - g.d_base) * g.H + t.y0) * g.W + t.x0 : 0;
+      if (valid) valid[nv] = tvalid ? 1 : 0;
     } else {
 #pragma unroll
       for (int k = 0; k < 8; ++k) ww[k] = 0.f;
+    }
+    // ---- whole chunk outside the frustum (42 % of the KITTI grid, in long runs): write its zero rows and move on
+    if (__ballot_sync(0xffffffffu, m != 0u) == 0u && chunk * 32u + 32u <= total) {
+      const int64_t pieces = (int64_t)chunk * 32 * row16;          // 16-byte pieces (bf16) of the chunk's output rows
+      for (uint32_t i = lane; i < 32u * row16; i += 32u) {
+        if (sizeof(OutT) == 2) {
+          st_cs_v4(reinterpret_cast<uint4*>(out) + pieces + i, make_uint4(0u, 0u, 0u, 0u));
+        } else {
+          st_cs_f4(reinterpret_cast<float*>(out) + (pieces + i) * 8, make_float4(0.f, 0.f, 0.f, 0.f));
+          st_cs_f4(reinterpret_cast<float*>(out) + (pieces + i) * 8 + 4, make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+      }
+      continue;
     }
     // ---- phase B: lpv rounds of vpr voxels; lane group `vsel` gathers voxel r*vpr + vsel
     for (int r = 0; r < lpv; ++r) {
@@ -356,9 +403,11 @@ lift_ndhwc_coop_kernel(const __nv_bfloat16* __restrict__ vol, const float* __res
       const unsigned mm = __shfl_sync(0xffffffffu, m, src);
       const uint32_t onv = chunk * 32u + src;
       const bool live = onv < total;              // tail chunk only; dead voxels carry mm == 0
-      float acc[8];
+      // accumulators as fp32 pairs: sm_100 has packed FFMA2 / FMUL2 / FADD2 (two IEEE fp32 operations per issue
+      // slot, results identical to the scalar instructions) -- ncu showed this kernel bound by instruction issue
+      float2 acc2[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      for (int j = 0; j < 4; ++j) acc2[j] = make_float2(0.f, 0.f);
       if (__ballot_sync(0xffffffffu, mm != 0u) != 0u) {
         const int b = __shfl_sync(0xffffffffu, base, src);
         float w[8];
@@ -373,23 +422,24 @@ lift_ndhwc_coop_kernel(const __nv_bfloat16* __restrict__ vol, const float* __res
             q[k] = __ldg(reinterpret_cast<const uint4*>(vol) + (v * row16 + sub));      // host: volume < 2^32 x 16 B
           }
         }
+        // masked corners were loaded as zeros and the weights are finite: x + 0 * w == x, so no per-corner branch
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          if (mm & (1u << k)) {
-            const uint32_t u[4] = {q[k].x, q[k].y, q[k].z, q[k].w};
+          const uint32_t u[4] = {q[k].x, q[k].y, q[k].z, q[k].w};
+          const float2 wk = make_float2(w[k], w[k]);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (EXACT) {
-                acc[2 * j] = __fadd_rn(acc[2 * j], __fmul_rn(bf16_lo(u[j]), w[k]));
-                acc[2 * j + 1] = __fadd_rn(acc[2 * j + 1], __fmul_rn(bf16_hi(u[j]), w[k]));
-              } else {
-                acc[2 * j] = fmaf(bf16_lo(u[j]), w[k], acc[2 * j]);
-                acc[2 * j + 1] = fmaf(bf16_hi(u[j]), w[k], acc[2 * j + 1]);
-              }
+          for (int j = 0; j < 4; ++j) {
+            const float2 v = make_float2(bf16_lo(u[j]), bf16_hi(u[j]));
+            if (EXACT) {   // scalar intrinsics: nvcc contracts __fadd2_rn(__fmul2_rn()) into FFMA2 (seen in the SASS)
+              acc2[j].x = __fadd_rn(acc2[j].x, __fmul_rn(v.x, wk.x));
+              acc2[j].y = __fadd_rn(acc2[j].y, __fmul_rn(v.y, wk.y));
+            } else {
+              acc2[j] = __ffma2_rn(v, wk, acc2[j]);
             }
           }
         }
       }
+      const float acc[8] = {acc2[0].x, acc2[0].y, acc2[1].x, acc2[1].y, acc2[2].x, acc2[2].y, acc2[3].x, acc2[3].y};
       if (!live) continue;
       OutT* o = out + (int64_t)onv * C + sub * 8;
       if (sizeof(OutT) == 2) {
@@ -528,6 +578,7 @@ static int make_geom(LiftGeom& g, const float* cv, int64_t D, int64_t H, int64_t
   SNVC_CHECK_ARG(D < (1 << 20) && H < (1 << 20) && W < (1 << 20) && Z < (1 << 20) && Y < (1 << 20) && X < (1 << 20),
                  "dimension too large");
   for (int i = 0; i < 6; ++i) g.cv[i] = cv[i];
+  g.range_ordered = (cv[0] < cv[1] && cv[2] < cv[3] && cv[4] < cv[5]) ? 1 : 0;
   g.D = (int)D; g.H = (int)H; g.W = (int)W; g.Z = (int)Z; g.Y = (int)Y; g.X = (int)X;
   g.Dt = (int)D; g.d_base = 0;
   g.align_corners = ac ? 1 : 0;
@@ -570,7 +621,7 @@ static int lift_fwd_impl(const void* vol, const float* proj, const float* zs, co
         return f;
       };
       LiftDivs dv{mk(X), mk(Y), mk(Z)};
-      const int cblocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(nvox, 256), (int64_t)sm_count() * 8));
+      const int cblocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(nvox, 256), (int64_t)sm_count() * 4));   // 4 resident blocks / SM, one wave
       if (out_dtype == SNVC_BF16)
         lift_ndhwc_coop_kernel<__nv_bfloat16, false><<<cblocks, 256, 0, stream>>>(
             (const __nv_bfloat16*)vol, proj, zs, ys, xs, (__nv_bfloat16*)out, valid, (int)C, log_lpv, g, dv, (uint32_t)nvox);

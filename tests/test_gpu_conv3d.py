@@ -100,6 +100,26 @@ def test_deconv_k3_s2(Cin, Cout, mode):
     _case(Cin, Cout, 3, 2, 1, 1, True, (3, 6, 10), N=2, relu=(mode == 1 and Cout == 64), residual_mode=mode)
 
 
+def test_deconv_staged_tiles_many_units_per_cta(monkeypatch):
+    """Fused transposed conv with its staged (TMA load residual -> in-place update -> TMA store) epilogue: tiles
+    clipped at the H / W edges, several work units per CTA (grid clamped) so that both tile buffers, the plane ring
+    and the TMEM double buffer wrap, every residual mode."""
+    monkeypatch.setenv("SNVC_CONV_MAXGRID", "3")
+    _case(64, 32, 3, 2, 1, 1, True, (10, 20, 40), N=2, residual_mode=1)                 # hourglass conv6 (+ out residual)
+    _case(64, 64, 3, 2, 1, 1, True, (6, 12, 39), relu=True, residual_mode=1)            # hourglass conv5: relu(bn + pre)
+    _case(64, 32, 3, 2, 1, 1, True, (5, 9, 17), N=3)                                    # no residual
+    _case(32, 32, 3, 2, 1, 1, True, (4, 8, 16), relu=True, residual_mode=2)
+
+
+def test_conv_staged_tma_store_epilogue(monkeypatch):
+    """Opt-in epilogue of the kd-fused kernel: rows staged in a swizzled shared-memory tile, one bulk tensor store."""
+    monkeypatch.setenv("SNVC_CONV_STORE", "staged")
+    _case(32, 32, 3, 1, 1, 1, False, (6, 10, 40), N=2, relu=True, residual_mode=1)
+    _case(64, 32, 3, 1, 1, 1, False, (4, 96, 312), relu=True)
+    _case(64, 64, 3, 1, 1, 1, False, (5, 12, 70), relu=True)
+    _case(16, 16, 3, 1, 1, 1, False, (6, 10, 20), N=2, relu=True)
+
+
 def test_conv_residual_modes_and_sigmoid():
     _case(32, 32, 3, 1, 1, 1, False, (4, 8, 16), residual_mode=1)                      # dres1.1: bn + x
     _case(32, 32, 3, 1, 1, 1, False, (4, 8, 16), relu=True, residual_mode=1)           # hourglass conv2 (+postsqu)
