@@ -133,6 +133,19 @@ def test_conv_instance_kernels():
     _case(32, 32, 5, 1, 4, 2, False, (10, 12, 16), relu=True, residual_mode=2)         # conv3 5^3 dilation 2
 
 
+def test_conv_large_kernel_plane_march(monkeypatch):
+    """5^3 / 7^3 plane march with streamed weights (instance conv1-conv3): more than 16 planes (the TMEM accumulator
+    ring wraps), depths that are not multiples of the 4-plane group, several tile columns per CTA (grid clamped), both
+    dilations (dilation 2 uses the parity-split ring; an odd depth falls back to the per-tap kernel)."""
+    monkeypatch.setenv("SNVC_CONV_MAXGRID", "2")
+    _case(64, 32, 7, 1, 3, 1, False, (18, 9, 40), relu=True)                               # conv1
+    _case(32, 32, 5, 1, 2, 1, False, (21, 12, 60), N=2, relu=True, residual_mode=2)        # conv2
+    _case(32, 32, 5, 1, 4, 2, False, (22, 10, 50), relu=True, residual_mode=2)             # conv3 (dilation 2)
+    _case(32, 32, 5, 1, 4, 2, False, (7, 10, 20), relu=True)                               # odd depth -> per-tap path
+    _case(32, 32, 7, 1, 3, 1, False, (5, 8, 30), relu=True)
+    _case(64, 32, 5, 1, 2, 1, False, (9, 8, 24), relu=True)
+
+
 def test_conv_kitti_level_shapes():
     """One slab of the global trunk's real W/H (W=312 is not a multiple of the tile)."""
     _case(64, 32, 3, 1, 1, 1, False, (4, 96, 312), relu=True)
