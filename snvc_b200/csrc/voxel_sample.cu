@@ -125,6 +125,118 @@ roi_sample_ndhwc_kernel(const float* __restrict__ fl, const float* __restrict__ 
   }
 }
 
+// Division of a 32-bit index by a run-time constant (Granlund-Montgomery): the flat voxel index is split into
+// (n, z, y, x) with three of these instead of four 64-bit software divisions (ncu: those were 250 of the
+// 393 set-up instructions per voxel, and the kernel was issue-bound).
+struct FastDiv { uint32_t m, s1, s2, d; };
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
+  const uint32_t t = __umulhi(f.m, n);
+  return (t + ((n - t) >> f.s1)) >> f.s2;
+}
+
+// ---- A3, NDHWC output, v2: cooperative gather.  The kernel above recomputes the bilinear set-up (two IEEE
+// divisions per axis pair) in every one of the C/8 threads of a (point, view); ncu / bench_instance: 1.5 TB/s,
+// issue-bound.  Here a warp owns 32 consecutive points: lane i does the set-up of point i for BOTH views once,
+// then C/8 adjacent lanes gather each (point, view) -- 8 channels (two 16-byte loads per corner) per lane -- with
+// the set-up handed over by warp shuffles, and write 16 bytes of the bf16 row each.  Arithmetic per channel is
+// the separately rounded mul / add chain of acc4(), two channels per instruction (see mul2_exact / add2_exact),
+// so the output stays bit-identical to the oracle.
+// Exact packed product / sum built from the packed FMA only: RN(a*b + 0) == RN(a*b) and RN(b*1 + a) == RN(a + b).
+// (mul.rn.f32x2 followed by add.rn.f32x2 is NOT usable: ptxas 12.9 contracts the pair into one FFMA2 even with
+// explicit .rn and -fmad=false -- seen in the SASS -- which changes the rounding.)
+__device__ __forceinline__ float2 mul2_exact(float2 a, float2 b) { return __ffma2_rn(a, b, make_float2(0.f, 0.f)); }
+__device__ __forceinline__ float2 add2_exact(float2 a, float2 b) { return __ffma2_rn(b, make_float2(1.f, 1.f), a); }
+
+template <typename OutT>
+__global__ void __launch_bounds__(256, 4)
+roi_sample_coop_kernel(const float* __restrict__ fl, const float* __restrict__ fr, const float* __restrict__ pl,
+                       const float* __restrict__ pr, OutT* __restrict__ out, int C, int log_lpv, int Hf, int Wf,
+                       FastDiv divP, float res_x, float res_y, uint32_t total /* N*P < 2^31 */) {
+  const int lane = threadIdx.x & 31;
+  const int lpv = 1 << log_lpv;                 // lanes per (point, view) = C / 8
+  const int ppr = 32 >> log_lpv;                // points per round
+  const int cg = lane & (lpv - 1);
+  const int psel = lane >> log_lpv;
+  const uint32_t P = divP.d;
+  const uint32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t chunk = warp0; chunk * 32u < total; chunk += nwarps) {
+    // ---- phase A: lane i sets up point chunk*32 + i for both views
+    const uint32_t np = chunk * 32u + lane;
+    int base[2] = {0, 0};
+    unsigned msk[2] = {0u, 0u};
+    float w[2][4];
+#pragma unroll
+    for (int v = 0; v < 2; ++v)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) w[v][k] = 0.f;
+    if (np < total) {
+      const uint32_t n = fdiv(np, divP), pi = np - n * P;
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        const float* pts = (v ? pr : pl) + (size_t)n * 2 * P;
+        const Bilinear b = bilinear_setup(__ldg(pts + pi), __ldg(pts + P + pi), res_x, res_y, Wf, Hf);
+        msk[v] = b.mask;
+        base[v] = b.mask ? (int)n * Hf * Wf + b.y0 * Wf + b.x0 : 0;
+        if (b.mask) {                              // (all corners outside: weights may be non-finite, keep zeros)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) w[v][k] = b.w[k];
+        }
+      }
+    }
+    // ---- phase B: per view, lpv rounds of ppr points; lane cg owns channels [8cg, 8cg+8) of the view.
+    // (Measured alternatives, bench_instance.py on B200: float4 #cg and #(cg+lpv) per lane 0.055 ms / proposal,
+    // 4 channels per lane with C/4 lanes per point 0.059 ms; this form 0.050 ms.)
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      const float* feat = v ? fr : fl;
+      for (int r = 0; r < lpv; ++r) {
+        const int src = r * ppr + psel;
+        const unsigned mm = __shfl_sync(0xffffffffu, msk[v], src);
+        const int b = __shfl_sync(0xffffffffu, base[v], src);
+        float wk[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) wk[k] = __shfl_sync(0xffffffffu, w[v][k], src);
+        const uint32_t onp = chunk * 32u + src;
+        float2 acc2[4];
+        float4 q[4][2];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          q[k][0] = q[k][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (mm & (1u << k)) {
+            const float4* sp = reinterpret_cast<const float4*>(feat + (size_t)(b + (k >> 1) * Wf + (k & 1)) * C) + cg * 2;
+            q[k][0] = __ldg(sp);
+            q[k][1] = __ldg(sp + 1);
+          }
+        }
+        // o = (((0 + v_nw*w_nw) + v_ne*w_ne) + v_sw*w_sw) + v_se*w_se; a masked corner contributes +0 (x + 0 == x)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 wv = make_float2(wk[k], wk[k]);
+          const float2 p0 = mul2_exact(make_float2(q[k][0].x, q[k][0].y), wv), p1 = mul2_exact(make_float2(q[k][0].z, q[k][0].w), wv);
+          const float2 p2 = mul2_exact(make_float2(q[k][1].x, q[k][1].y), wv), p3 = mul2_exact(make_float2(q[k][1].z, q[k][1].w), wv);
+          if (k == 0) {          // 0 + p == p (the product already carries the "+ 0")
+            acc2[0] = p0; acc2[1] = p1; acc2[2] = p2; acc2[3] = p3;
+          } else {
+            acc2[0] = add2_exact(acc2[0], p0); acc2[1] = add2_exact(acc2[1], p1);
+            acc2[2] = add2_exact(acc2[2], p2); acc2[3] = add2_exact(acc2[3], p3);
+          }
+        }
+        if (onp < total) {
+          OutT* o = out + (size_t)onp * (2 * C) + v * C + cg * 8;
+          if (sizeof(OutT) == 2) {
+            *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16x2(acc2[0].x, acc2[0].y), pack_bf16x2(acc2[1].x, acc2[1].y),
+                                                      pack_bf16x2(acc2[2].x, acc2[2].y), pack_bf16x2(acc2[3].x, acc2[3].y));
+          } else {
+            *reinterpret_cast<float4*>(o) = make_float4(acc2[0].x, acc2[0].y, acc2[1].x, acc2[1].y);
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(o) + 4) = make_float4(acc2[2].x, acc2[2].y, acc2[3].x, acc2[3].y);
+          }
+        }
+      }
+    }
+  }
+}
+
 // ---- A3, NCDHW fp32 output (the reference's layout): one thread per (point, view); channel loop;
 //      stores are coalesced across the warp's consecutive points. -------------------------------
 __global__ void __launch_bounds__(256)
@@ -319,14 +431,6 @@ lift_ndhwc_kernel(const __nv_bfloat16* __restrict__ vol, const float* __restrict
 // from the owning lane to the gathering lanes with warp shuffles; rounds whose voxels are all outside
 // the frustum are skipped on a ballot.  Arithmetic per channel is the same instruction sequence as the
 // kernel above, so results are bit-identical to it (and EXACT = bit-identical to the oracle).
-// Division of a 32-bit index by a run-time constant (Granlund-Montgomery): the flat voxel index is split into
-// (n, z, y, x) with three of these instead of four 64-bit software divisions (ncu: those were 250 of the
-// 393 set-up instructions per voxel, and the kernel was issue-bound).
-struct FastDiv { uint32_t m, s1, s2, d; };
-__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
-  const uint32_t t = __umulhi(f.m, n);
-  return (t + ((n - t) >> f.s1)) >> f.s2;
-}
 struct LiftDivs { FastDiv X, Y, Z; };
 
 template <typename OutT, bool EXACT>
@@ -509,6 +613,15 @@ __global__ void lift_indices_kernel(const float* __restrict__ proj, const float*
   }
 }
 
+FastDiv make_fastdiv(int64_t d) {
+  FastDiv f;
+  uint32_t l = 0;
+  while ((1ull << l) < (uint64_t)d) ++l;
+  f.m = (uint32_t)((((uint64_t)1 << 32) * (((uint64_t)1 << l) - (uint64_t)d)) / (uint64_t)d + 1);
+  f.s1 = l < 1 ? l : 1; f.s2 = l > 0 ? l - 1 : 0; f.d = (uint32_t)d;
+  return f;
+}
+
 int grid_for(int64_t total, int per_sm = 8) {
   return (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total, 256), (int64_t)sm_count() * per_sm));
 }
@@ -541,6 +654,23 @@ extern "C" int snvc_roi_voxel_sample_fwd(const float* feat_l, const float* feat_
   if (out_layout == SNVC_NDHWC) {
     SNVC_CHECK_ARG(C % 8 == 0, "NDHWC output needs C %% 8 == 0");
     const int64_t total = N * P * (2 * C / 8);
+    // cooperative kernel (set-up once per point, C/8 lanes per (point, view)); SNVC_ROI_MODE=thread keeps v1 (A/B runs)
+    const int lpv = (int)(C / 8);
+    const char* rmode = getenv("SNVC_ROI_MODE");
+    if (lpv <= 32 && (lpv & (lpv - 1)) == 0 && N * P < (1ll << 31) && N * Hf * Wf < (1ll << 31) &&
+        (out_dtype == SNVC_BF16 || out_dtype == SNVC_F32) && !(rmode && rmode[0] == 't')) {
+      int log_lpv = 0;
+      while ((1 << log_lpv) < lpv) ++log_lpv;
+      const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(N * P, 256), (int64_t)sm_count() * 4));
+      if (out_dtype == SNVC_BF16)
+        roi_sample_coop_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(wl, wr, pts_l, pts_r, (__nv_bfloat16*)out, (int)C, log_lpv,
+                                                                          (int)Hf, (int)Wf, make_fastdiv(P), res_x, res_y,
+                                                                          (uint32_t)(N * P));
+      else
+        roi_sample_coop_kernel<float><<<blocks, 256, 0, stream>>>(wl, wr, pts_l, pts_r, (float*)out, (int)C, log_lpv, (int)Hf,
+                                                                  (int)Wf, make_fastdiv(P), res_x, res_y, (uint32_t)(N * P));
+      return launch_status("roi_sample_coop_kernel");
+    }
     if (out_dtype == SNVC_BF16)
       roi_sample_ndhwc_kernel<__nv_bfloat16><<<grid_for(total, 16), 256, 0, stream>>>(
           wl, wr, pts_l, pts_r, (__nv_bfloat16*)out, (int)C, (int)Hf, (int)Wf, P, res_x, res_y, total);
@@ -612,15 +742,7 @@ static int lift_fwd_impl(const void* vol, const float* proj, const float* zs, co
         nvox < (1ll << 31) && N * D * H * W * lpv < (1ll << 32) && !(lmode && lmode[0] == 't')) {
       int log_lpv = 0;
       while ((1 << log_lpv) < lpv) ++log_lpv;
-      auto mk = [](int64_t d) {
-        FastDiv f;
-        uint32_t l = 0;
-        while ((1ull << l) < (uint64_t)d) ++l;
-        f.m = (uint32_t)((((uint64_t)1 << 32) * (((uint64_t)1 << l) - (uint64_t)d)) / (uint64_t)d + 1);
-        f.s1 = l < 1 ? l : 1; f.s2 = l > 0 ? l - 1 : 0; f.d = (uint32_t)d;
-        return f;
-      };
-      LiftDivs dv{mk(X), mk(Y), mk(Z)};
+      LiftDivs dv{make_fastdiv(X), make_fastdiv(Y), make_fastdiv(Z)};
       const int cblocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(nvox, 256), (int64_t)sm_count() * 4));   // 4 resident blocks / SM, one wave
       if (out_dtype == SNVC_BF16)
         lift_ndhwc_coop_kernel<__nv_bfloat16, false><<<cblocks, 256, 0, stream>>>(
