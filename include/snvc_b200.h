@@ -181,6 +181,23 @@ int snvc_conv3d_fwd(const void* x, const void* w_packed, const float* scale, con
                     const void* residual, void* y, const snvc_conv3d_desc* desc, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * N1  projection of the instance sampling grid into the left / right ROI frames.
+ * Replaces refinementDataset._generate_grid_proj, the per-proposal numpy float64 loop upstream of A3
+ *   snvc/dataset/KITTIRefinement_dataset.py:847-868 (_to_cam :828-845, _init_3d_grid :267-282)
+ *   snvc/dataset/kitti_util.py:282-293 (project_rect_to_image), snvc/utils/img_proc.py:71-74 (affine_transform)
+ * pose     [N,5] float64: cos(ry+pi/2), sin(ry+pi/2), x, y - h/2, z   (computed on the host as the reference does)
+ * P_left/P_right [N,3,4] float64 camera projections; trans_l/trans_r [N,2,3] float64 ROI affines
+ * x_pts [nw], y_pts [nh], z_pts [nl] float64: np.linspace of the grid ranges
+ * coord_l/coord_r [N,2,P] float32 (P = nh*nw*nl, point index (ih*nw+iw)*nl+il) -- the l_pts / r_pts of A3;
+ * grid_cam [N,P,3] float32 camera-frame grid points, or NULL.
+ * float64 arithmetic, one cast to float32; dot products are FMA chains in k order (<= 1 float32 ulp vs the
+ * reference's dgemm, bit-identical for > 99.99 % of the values). */
+int snvc_roi_grid_project(const double* pose, const double* P_left, const double* P_right, const double* trans_l,
+                          const double* trans_r, const double* x_pts, const double* y_pts, const double* z_pts,
+                          float* coord_l, float* coord_r, float* grid_cam, int64_t N, int64_t nh, int64_t nw,
+                          int64_t nl, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Layout / elementwise helpers on the path.
  */
 /* NCDHW fp32 [N,C,S] <-> NDHWC bf16 [N,S,C]  (S = D*H*W) */

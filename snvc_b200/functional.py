@@ -116,6 +116,46 @@ def frustum_lift_indices(proj, zs, ys, xs, cv_range, vol_dhw, align_corners=True
     return idx, valid
 
 
+def roi_grid_project(boxes, P_left, P_right, trans_l, trans_r, x_range, y_range, z_range, grid_resolution, device=None,
+                     return_grid=False):
+    """GPU replacement of refinementDataset._generate_grid_proj (KITTIRefinement_dataset.py:847-868).
+
+    boxes [N,7] = [h,w,l,x,y,z,ry] (host array-like), P_left / P_right [3,4] or [N,3,4], trans_l / trans_r [N,2,3]
+    (host), ranges + grid_resolution = cfg.x_range / y_range / z_range / grid_resolution.  Returns device tensors
+    coord_l, coord_r [N,2,P] float32 (what VernierScale.forward takes as grid_proj_left / grid_proj_right) and, if
+    asked, the camera-frame grid [N,P,3] float32.  Only O(N) numbers are prepared on the host (pose, linspace)."""
+    import numpy as np
+    L = _lib.lib()
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    boxes = np.asarray(boxes, dtype=np.float64).reshape(-1, 7)
+    N = boxes.shape[0]
+    nh, nw, nl = (int(v) for v in grid_resolution)
+    ry = boxes[:, 6] + 0.5 * np.pi                                           # _to_cam: heading + pi/2
+    pose = np.stack([np.cos(ry), np.sin(ry), boxes[:, 3], boxes[:, 4] - boxes[:, 0] * 0.5, boxes[:, 5]], axis=1)
+
+    def per_proposal(a, shape):
+        a = np.asarray(a, dtype=np.float64)
+        if a.shape == shape:
+            a = np.broadcast_to(a, (N,) + shape)
+        if a.shape != (N,) + shape:
+            raise RuntimeError(f"roi_grid_project: expected {shape} or {(N,) + shape}, got {a.shape}")
+        return np.ascontiguousarray(a)
+
+    host = [pose, per_proposal(P_left, (3, 4)), per_proposal(P_right, (3, 4)), per_proposal(trans_l, (2, 3)),
+            per_proposal(trans_r, (2, 3)), np.linspace(x_range[0], x_range[1], nw), np.linspace(y_range[0], y_range[1], nh),
+            np.linspace(z_range[0], z_range[1], nl)]
+    d = [torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev) for a in host]
+    P = nh * nw * nl
+    cl = torch.empty((N, 2, P), dtype=torch.float32, device=dev)
+    cr = torch.empty((N, 2, P), dtype=torch.float32, device=dev)
+    cam = torch.empty((N, P, 3), dtype=torch.float32, device=dev) if return_grid else None
+    with torch.cuda.device(dev):
+        st = L.snvc_roi_grid_project(*[t.data_ptr() for t in d], cl.data_ptr(), cr.data_ptr(),
+                                     cam.data_ptr() if cam is not None else None, N, nh, nw, nl, _lib.stream_ptr())
+    _lib.check(st, "snvc_roi_grid_project")
+    return (cl, cr, cam) if return_grid else (cl, cr)
+
+
 # ------------------------------------------------------------------------------------ layouts
 def to_ndhwc_bf16(x):
     """[N,C,D,H,W] fp32 -> [N,D,H,W,C] bf16."""

@@ -107,9 +107,38 @@ def case_vernier():
                 voxel_bev=bev.numpy(), occupancy=occ.numpy(), ncf=ncf.numpy(), coordinates=coords.numpy())
 
 
+def case_grid_proj():
+    """The reference's own `refinementDataset._generate_grid_proj` (KITTIRefinement_dataset.py:847-868, with
+    `_init_3d_grid` :267-282, `_to_cam` :828-845, kitti_util.Calibration.project_rect_to_image, img_proc.affine_transform)
+    on synthetic proposals (oracle.grid_proj.synthetic_case: inputs are regenerated from the seed, outputs stored)."""
+    for name in ("imageio", "tensorboardX", "matplotlib.patches", "matplotlib.lines"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    from snvc.dataset import KITTIRefinement_dataset as ref_ds
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import grid_proj as ogp
+    c = ogp.synthetic_case()
+    ds = object.__new__(ref_ds.refinementDataset)
+    ds.cfg = types.SimpleNamespace(x_range=c["x_range"], y_range=c["y_range"], z_range=c["z_range"],
+                                   grid_resolution=list(c["grid_resolution"]))
+    ds._init_3d_grid()
+    calib = lambda P: types.SimpleNamespace(project_rect_to_image=lambda pts, P=P: _project(pts, P))
+
+    def _project(pts, P):
+        from snvc.dataset import kitti_util
+        cal = object.__new__(kitti_util.Calibration)
+        cal.P = P
+        return cal.project_rect_to_image(pts)
+
+    meta = {"trans_l": c["trans_l"], "trans_r": c["trans_r"]}
+    coord_l, coord_r, grid_3d = ds._generate_grid_proj(c["samples"], calib(c["P_left"]), calib(c["P_right"]), meta)
+    return dict(coord_l=coord_l, coord_r=coord_r, grid_3d=grid_3d.astype(np.float32))
+
+
 if __name__ == "__main__":
     cases = {"hourglass_bn": lambda: case_hourglass(False), "hourglass_gn": lambda: case_hourglass(True),
-             "hg16_bn": case_hg16, "vernier_bev3": case_vernier}
+             "hg16_bn": case_hg16, "vernier_bev3": case_vernier, "grid_proj": case_grid_proj}
+    if len(sys.argv) > 1:
+        cases = {k: v for k, v in cases.items() if k in sys.argv[1:]}
     for name, fn in cases.items():
         d = fn()
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **{k: np.asarray(v) for k, v in d.items()})
