@@ -198,6 +198,20 @@ int snvc_roi_grid_project(const double* pose, const double* P_left, const double
                           int64_t nl, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * A5 / N2  depth head behind the trunk.
+ * snvc_disparity_regression replaces `disparityregression.forward` (snvc/models/submodule.py:76-83):
+ *   prob [N,K,H*W] fp32 (softmaxed volume), depth_values [K] fp32 -> out [N,H*W] fp32 = sum_k prob * depth[k].
+ * snvc_depth_regression_fwd fuses what the (restated, DSGN-lineage) global branch runs in front of it:
+ *   F.interpolate(logits [N,1,D,H,W] -> (Dout,Hout,Wout), mode='trilinear', align_corners) -> softmax(dim=depth)
+ *   -> disparityregression; logits [N,D,H,W] fp32, depth_values [Dout] fp32 -> out [N,Hout,Wout] fp32.  The
+ *   up-sampled probability volume is never written.  fp32; within 1e-5 relative of the torch ops (tests). */
+int snvc_disparity_regression(const float* prob, const float* depth_values, float* out, int64_t N, int64_t K,
+                              int64_t HW, void* stream);
+int snvc_depth_regression_fwd(const float* logits, const float* depth_values, float* out, int64_t N, int64_t D,
+                              int64_t H, int64_t W, int64_t Dout, int64_t Hout, int64_t Wout, int32_t align_corners,
+                              void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Layout / elementwise helpers on the path.
  */
 /* NCDHW fp32 [N,C,S] <-> NDHWC bf16 [N,S,C]  (S = D*H*W) */

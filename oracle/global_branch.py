@@ -135,3 +135,16 @@ def frustum_lift(volume, Ps, geom: GlobalGeometry):
         outs.append(o * valid[None].astype(F32))
         valids.append(valid)
     return np.stack(outs), np.stack(valids)
+
+
+def depth_head(vol, classif, depth_values, out_size, align_corners=True):
+    """Restated depth head (SURVEY.md 3.4 'adjacent'; blocks pinned by submodule.py:32-50,76-83): plain torch fp32.
+    vol [N,C,D,H,W] torch tensor, classif = Sequential(convbn_3d, ReLU, Conv3d(C,1)), depth_values [Dout] tensor,
+    out_size (Dout,Hout,Wout) -> depth [N,Hout,Wout] (numpy)."""
+    import torch
+    import torch.nn.functional as F
+    with torch.no_grad():
+        cost = classif(vol)                                                        # [N,1,D,H,W]
+        cost = F.interpolate(cost, list(out_size), mode="trilinear", align_corners=align_corners)
+        prob = F.softmax(torch.squeeze(cost, 1), dim=1)
+        return torch.sum(prob * depth_values[None, :, None, None], 1).numpy()      # disparityregression.forward

@@ -156,6 +156,41 @@ def roi_grid_project(boxes, P_left, P_right, trans_l, trans_r, x_range, y_range,
     return (cl, cr, cam) if return_grid else (cl, cr)
 
 
+# ------------------------------------------------------------------------------------ depth head
+def disparity_regression(prob, depth):
+    """`disparityregression.forward` (submodule.py:76-83): prob [N,K,H,W] fp32, depth [K] fp32 -> [N,H,W]."""
+    _lib.require_cuda(prob, depth)
+    if prob.dtype != torch.float32 or depth.dtype != torch.float32:
+        raise RuntimeError("disparity_regression: fp32 tensors expected")
+    prob, depth = prob.contiguous(), depth.contiguous()
+    N, K, H, W = prob.shape
+    out = torch.empty((N, H, W), dtype=torch.float32, device=prob.device)
+    with torch.cuda.device(prob.device):
+        st = _lib.lib().snvc_disparity_regression(prob.data_ptr(), depth.data_ptr(), out.data_ptr(), N, K, H * W,
+                                                  _lib.stream_ptr())
+    _lib.check(st, "snvc_disparity_regression")
+    return out
+
+
+def depth_regression_from_logits(logits, depth_values, out_size, align_corners=True):
+    """Fused F.interpolate(trilinear) -> softmax(depth) -> disparityregression.
+    logits [N,D,H,W] (or [N,1,D,H,W]) fp32, depth_values [Dout] fp32, out_size (Dout,Hout,Wout) -> [N,Hout,Wout]."""
+    _lib.require_cuda(logits, depth_values)
+    if logits.dim() == 5:
+        logits = logits[:, 0]
+    logits, depth_values = logits.float().contiguous(), depth_values.float().contiguous()
+    N, D, H, W = logits.shape
+    Dout, Hout, Wout = (int(v) for v in out_size)
+    if depth_values.numel() != Dout:
+        raise RuntimeError(f"depth_regression_from_logits: {Dout} depth values expected, got {depth_values.numel()}")
+    out = torch.empty((N, Hout, Wout), dtype=torch.float32, device=logits.device)
+    with torch.cuda.device(logits.device):
+        st = _lib.lib().snvc_depth_regression_fwd(logits.data_ptr(), depth_values.data_ptr(), out.data_ptr(), N, D, H, W,
+                                                  Dout, Hout, Wout, int(bool(align_corners)), _lib.stream_ptr())
+    _lib.check(st, "snvc_depth_regression_fwd")
+    return out
+
+
 # ------------------------------------------------------------------------------------ layouts
 def to_ndhwc_bf16(x):
     """[N,C,D,H,W] fp32 -> [N,D,H,W,C] bf16."""

@@ -66,6 +66,37 @@ class GlobalHotPath(nn.Module):
         return self.lift(self.trunk(cost), proj, out_dtype, layout_out)
 
 
+class DepthHead(nn.Module):
+    """Depth head behind the trunk (restated wiring; blocks: convbn_3d submodule.py:32-50,
+    disparityregression :76-83): classif = convbn_3d(ch, ch, 3, 1, 1) + ReLU + Conv3d(ch, 1, 3, 1, 1, bias=False);
+    depth = disparityregression(softmax(F.interpolate(classif(x), [maxdisp, H, W], 'trilinear')), depth_values).
+    The two convs run on the tcgen05 kernels, the rest as ONE fused kernel (snvc_depth_regression_fwd)."""
+
+    def __init__(self, cfg, channels=32, maxdisp=192):
+        super().__init__()
+        self.classif = nn.Sequential(convbn_3d(channels, channels, 3, 1, 1, gn=bool(getattr(cfg, "GN", False))),
+                                     nn.ReLU(inplace=True), nn.Conv3d(channels, 1, 3, 1, 1, bias=False))
+        self.align_corners = bool(getattr(cfg, "align_corners", True))
+        self.maxdisp = maxdisp
+
+    def _logit_conv(self):
+        from snvc_b200.conv import PackedConv3d
+        conv = self.classif[2]
+        vers = (conv.weight.data_ptr(), conv.weight._version)
+        plan = getattr(self, "_plan", None)
+        if plan is None or plan[0] != vers:
+            plan = (vers, PackedConv3d(conv.weight, None, stride=1, pad=1))
+            object.__setattr__(self, "_plan", plan)
+        return plan[1]
+
+    def forward(self, vol, depth_values, out_hw):
+        """vol [N,D,H,W,ch] bf16 channels-last (the trunk output), depth_values [maxdisp] fp32 -> depth [N,Hout,Wout]."""
+        h = self.classif[0].fused(vol, relu=True)
+        logits = self._logit_conv()(h, out_dtype=torch.float32)              # [N,D,H,W,1] fp32
+        return SF.depth_regression_from_logits(logits[..., 0], depth_values, (self.maxdisp, out_hw[0], out_hw[1]),
+                                               self.align_corners)
+
+
 class HostPipeline:
     """Host-buffer front end of `GlobalHotPath`: batches come from / go back to PINNED host memory.
 

@@ -150,6 +150,18 @@ def get_hg_up_sample(channel_in, channel_out, gn):
     return _deconvbn_3d(channel_in, channel_out, gn)
 
 
+class disparityregression(nn.Module):
+    """submodule.py:76-83: forward(x, depth) = sum(x * depth[None, :, None, None], 1) on the GPU kernel.
+    (The reference's constructor calls `.cuda()` on an unused `arange(maxdisp)` buffer, :79; kept as a buffer.)"""
+
+    def __init__(self, maxdisp, cfg=None):
+        super().__init__()
+        self.register_buffer("disp", torch.arange(maxdisp, dtype=torch.float32), persistent=False)
+
+    def forward(self, x, depth):
+        return SF.disparity_regression(x.float(), depth.float())
+
+
 class hourglass(nn.Module):
     """submodule.py:85-168.  forward(x, presqu, postsqu) -> (out, pre, post); the caller adds the
     residual to `out` (as in the reference)."""
