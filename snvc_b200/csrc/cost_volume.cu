@@ -217,19 +217,37 @@ cv_ndhwc_bf16_kernel(const float* __restrict__ left, const float* __restrict__ r
       const float4 b = *chunk_ptr(sL, col, 2 * cg + 1, C, mask);
       vl = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
     }
+    // The two right-image samples of a bin are kept in registers: the shift shrinks with depth, so from one bin to
+    // the next x_low stays or advances by one column for most bins (all lanes of a warp alike: iw is an integer),
+    // and 0 or 2 instead of 4 LDS.128 are needed -- the shared-memory pipe, not HBM, was the busiest unit (ncu: 88 %).
+    int cur_xl = -0x40000000, cur_xh = -0x40000000;
+    float r0[8], r1[8];
     for (int dd = 0; dd < dn; ++dd, o += dstride) {
       *reinterpret_cast<uint4*>(o) = vl;                       // left half: broadcast over depth
       int xl, xh;
       float lx;
       uint4 v = make_uint4(0u, 0u, 0u, 0u);
       if (sample_pos<float>(iw, sS[dd], img_w, xl, xh, lx)) {  // right half: 1-D interpolation along the row
-        float r0[8], r1[8];
         if (xl >= rlo) {
-          const int c0 = xl - rlo, c1 = xh - rlo;
-          *reinterpret_cast<float4*>(r0) = *chunk_ptr(sR, c0, 2 * cg, C, mask);
-          *reinterpret_cast<float4*>(r0 + 4) = *chunk_ptr(sR, c0, 2 * cg + 1, C, mask);
-          *reinterpret_cast<float4*>(r1) = *chunk_ptr(sR, c1, 2 * cg, C, mask);
-          *reinterpret_cast<float4*>(r1 + 4) = *chunk_ptr(sR, c1, 2 * cg + 1, C, mask);
+          if (xl != cur_xl || xh != cur_xh) {
+            if (xl == cur_xh) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) r0[j] = r1[j];
+            } else {
+              const int c0 = xl - rlo;
+              *reinterpret_cast<float4*>(r0) = *chunk_ptr(sR, c0, 2 * cg, C, mask);
+              *reinterpret_cast<float4*>(r0 + 4) = *chunk_ptr(sR, c0, 2 * cg + 1, C, mask);
+            }
+            if (xh == xl) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) r1[j] = r0[j];
+            } else {
+              const int c1 = xh - rlo;
+              *reinterpret_cast<float4*>(r1) = *chunk_ptr(sR, c1, 2 * cg, C, mask);
+              *reinterpret_cast<float4*>(r1 + 4) = *chunk_ptr(sR, c1, 2 * cg + 1, C, mask);
+            }
+            cur_xl = xl; cur_xh = xh;
+          }
         } else {
           // sample left of the staged window (very large shift on a w-tiled row): read HBM directly
 #pragma unroll
@@ -237,6 +255,7 @@ cv_ndhwc_bf16_kernel(const float* __restrict__ left, const float* __restrict__ r
             r0[j] = rrow[(int64_t)(cg * 8 + j) * cstride + xl];
             r1[j] = rrow[(int64_t)(cg * 8 + j) * cstride + xh];
           }
+          cur_xl = xl; cur_xh = xh;
         }
         const float hx = __fsub_rn(1.f, lx);
         float r[8];
