@@ -212,6 +212,20 @@ int snvc_depth_regression_fwd(const float* logits, const float* depth_values, fl
                               void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * N4  rotated BEV IoU and NMS.  Replaces snvc/extension/iou3d_nms:
+ *   boxes_iou_bev_gpu   iou3d_nms.cpp:74-95,   iou3d_nms_kernel.cu:228-282
+ *   nms_gpu             iou3d_nms.cpp:131-177, iou3d_nms_kernel.cu:296-336 (+ the host keep loop)
+ * Boxes are [x, y, z, dx, dy, dz, heading] fp32 rows.
+ * snvc_nms_bev: boxes_sorted [N,7] in descending score order (iou3d_nms_utils.py:93-98 sorts before the call);
+ *   workspace: snvc_nms_bev_workspace_bytes(N) bytes; keep [N] int64 receives the kept positions (ascending), the
+ *   count goes to *num_keep (device int32).  Unlike the reference, nothing is copied to the host and nothing
+ *   synchronises: the greedy keep loop runs in a second kernel. */
+int snvc_boxes_iou_bev(const float* boxes_a, const float* boxes_b, float* iou, int64_t N, int64_t M, void* stream);
+int64_t snvc_nms_bev_workspace_bytes(int64_t N);
+int snvc_nms_bev(const float* boxes_sorted, void* workspace, int64_t* keep, int32_t* num_keep, int64_t N,
+                 float thresh, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Layout / elementwise helpers on the path.
  */
 /* NCDHW fp32 [N,C,S] <-> NDHWC bf16 [N,S,C]  (S = D*H*W) */

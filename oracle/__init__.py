@@ -16,4 +16,6 @@ blocks        plain-torch restatement of convbn_3d / hourglass / hourglass_downs
 global_branch restated global trunk + frustum lift (blocks pinned
               by submodule.py, wiring restated from the DSGN lineage, README.md:68)
 instance_branch ROI voxel sampling + refinement 3-D CNN (vernier.py:323-360,414-438)
+grid_proj     numpy float64 restatement of refinementDataset._generate_grid_proj (N1)
+iou3d_nms     scalar fp32 restatement of the rotated BEV IoU / NMS (N4) + exact float64 clipper
 """

@@ -38,6 +38,9 @@ _SIGS = {
     "snvc_roi_grid_project": ([_p] * 11 + [_i64] * 4 + [_p], _i32),
     "snvc_disparity_regression": ([_p, _p, _p, _i64, _i64, _i64, _p], _i32),
     "snvc_depth_regression_fwd": ([_p, _p, _p] + [_i64] * 7 + [_i32, _p], _i32),
+    "snvc_boxes_iou_bev": ([_p, _p, _p, _i64, _i64, _p], _i32),
+    "snvc_nms_bev_workspace_bytes": ([_i64], _i64),
+    "snvc_nms_bev": ([_p, _p, _p, _p, _i64, _f, _p], _i32),
     "snvc_conv3d_packed_weight_bytes": ([_i32, _i32, _i32], _i64),
     "snvc_conv3d_pack_weights": ([_p, _p, _i32, _i32, _i32, _i32, _p], _i32),
     "snvc_conv3d_fwd": ([_p, _p, _p, _p, _p, _p, ctypes.POINTER(ConvDesc), _p], _i32),

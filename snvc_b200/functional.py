@@ -156,6 +156,49 @@ def roi_grid_project(boxes, P_left, P_right, trans_l, trans_r, x_range, y_range,
     return (cl, cr, cam) if return_grid else (cl, cr)
 
 
+# ------------------------------------------------------------------------------------ rotated NMS (N4)
+def boxes_iou_bev(boxes_a, boxes_b):
+    """iou3d_nms_utils.boxes_iou_bev: [N,7], [M,7] fp32 ([x,y,z,dx,dy,dz,heading]) -> IoU [N,M]."""
+    _lib.require_cuda(boxes_a, boxes_b)
+    a, b = boxes_a.float().contiguous(), boxes_b.float().contiguous()
+    if a.shape[-1] != 7 or b.shape[-1] != 7:
+        raise RuntimeError("boxes_iou_bev: boxes must be [*, 7]")
+    out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        st = _lib.lib().snvc_boxes_iou_bev(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.shape[0], b.shape[0],
+                                           _lib.stream_ptr())
+    _lib.check(st, "snvc_boxes_iou_bev")
+    return out
+
+
+def nms_gpu_device(boxes, scores, thresh, pre_maxsize=None):
+    """Sync-free rotated NMS: returns (selected [n] int64 indices into `boxes`, padded with -1 after the kept ones;
+    num_kept int32 device scalar).  The greedy keep loop runs on the GPU (the reference runs it on the host)."""
+    _lib.require_cuda(boxes, scores)
+    if boxes.shape[-1] != 7:
+        raise RuntimeError("nms: boxes must be [N, 7]")
+    order = scores.sort(0, descending=True)[1]
+    if pre_maxsize is not None:
+        order = order[:pre_maxsize]
+    b = boxes.float()[order].contiguous()
+    n = b.shape[0]
+    L = _lib.lib()
+    ws = torch.empty(max(8, L.snvc_nms_bev_workspace_bytes(n)), dtype=torch.uint8, device=b.device)
+    keep = torch.full((n,), -1, dtype=torch.int64, device=b.device)
+    num = torch.zeros((), dtype=torch.int32, device=b.device)
+    with torch.cuda.device(b.device):
+        st = L.snvc_nms_bev(b.data_ptr(), ws.data_ptr(), keep.data_ptr(), num.data_ptr(), n, float(thresh), _lib.stream_ptr())
+    _lib.check(st, "snvc_nms_bev")
+    sel = torch.where(keep >= 0, order[keep.clamp(min=0)], keep)
+    return sel, num
+
+
+def nms_gpu(boxes, scores, thresh, pre_maxsize=None, **kwargs):
+    """Drop-in for iou3d_nms_utils.nms_gpu (iou3d_nms_utils.py:86-102): -> (indices of the kept boxes, None)."""
+    sel, num = nms_gpu_device(boxes, scores, thresh, pre_maxsize)
+    return sel[:int(num.item())].contiguous(), None
+
+
 # ------------------------------------------------------------------------------------ depth head
 def disparity_regression(prob, depth):
     """`disparityregression.forward` (submodule.py:76-83): prob [N,K,H,W] fp32, depth [K] fp32 -> [N,H,W]."""
