@@ -45,6 +45,16 @@ def geometry():
     return GlobalGeometry()
 
 
+def workload_config(world):
+    """`config` of the JSON line; both arms print the same one (the reference arm adds its sample)."""
+    return {"workload": "global branch hot path, batch 8 synthetic KITTI pairs per GPU (feat 8x32x96x312 "
+                        "fp32 -> cost volume 64x48x96x312 bf16 -> dres0/dres1/hourglass bf16 -> lift to "
+                        "192x20x304 voxels), random init, BN eval folded",
+            "pairs_per_gpu_per_step": PAIRS_PER_GPU, "parallelism": f"pair-sharded x{world}, no collective",
+            "l2": "inputs rotate over 4 sets (245 MB) and each step streams >3 GB of intermediates; "
+                  "both exceed the 126 MB L2"}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -136,8 +146,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": "stereo pairs/s (cost volume + 3D trunk + voxel lift)", "value": v,
             "unit": "pairs/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": spp * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "global branch hot path, 1 KITTI-shaped pair per step (3x384x1248 -> feat 32x96x312, "
-                                   "D=48, voxels 192x20x304), random init", "pairs_per_step": 1},
+            "config": dict(workload_config(world), sample="each step = 1 pair of that workload on the host cores"),
             "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -285,12 +294,7 @@ def run_ours(args, rank, world, local_rank):
             "metric": "stereo pairs/s (cost volume + 3D trunk + voxel lift)", "value": value, "unit": "pairs/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": elapsed_ms / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "global branch hot path, batch 8 synthetic KITTI pairs per GPU (feat 8x32x96x312 "
-                                   "fp32 -> cost volume 64x48x96x312 bf16 -> dres0/dres1/hourglass bf16 -> lift to "
-                                   "192x20x304 voxels), random init, BN eval folded",
-                       "pairs_per_gpu_per_step": B, "parallelism": f"pair-sharded x{world}, no collective",
-                       "l2": "inputs rotate over 4 sets (245 MB) and each step streams >3 GB of intermediates; "
-                             "both exceed the 126 MB L2"},
+            "config": workload_config(world),
             "clocks": clocks,
             "e2e": {"value": world * B * e2e_steps / (e2e_ms * 1e-3), "unit": "pairs/s",
                     "h2d_bytes_per_step": int(2 * B * FEAT_C * FEAT_H * FEAT_W * 4 + B * DEPTH_BINS * 4 + B * 48),
