@@ -59,7 +59,7 @@ int main() {
   printf("cycles per tcgen05.mma M=128 K=16 (SS), %d back-to-back, 1 CTA / SM x grid\n", iters);
   for (int grid : {1, 148})
     for (int sw : {64, 128})
-      for (int N : {16, 32, 48, 64, 96, 128, 160, 192, 256}) {
+      for (int N : {16, 32, 48, 64, 96, 128, 144, 160, 192, 256}) {
         k<<<grid, 128, 100 * 1024>>>(N, sw, iters, 0, d, 3, 0);
         k<<<grid, 128, 100 * 1024>>>(N, sw, iters, 0, d, 3, 0);
         cudaError_t e = cudaDeviceSynchronize();

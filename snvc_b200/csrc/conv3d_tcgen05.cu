@@ -185,9 +185,9 @@ __device__ __forceinline__ void residual_prefetch(const EpiParams& e, bool in_ra
 // the epilogue, not the tensor pipe, bounded every kernel variant.
 struct EpiFast { float m1, m2, lo; };
 
-__device__ __forceinline__ void epilogue_chunk16_vals(const uint32_t* acc, int cc, const float* s_scale, const float* s_bias,
-                                                      const ResidualRow& rr, const EpiFast f, uint4& o0, uint4& o1) {
-  float v[16];
+__device__ __forceinline__ void epilogue_chunk16_floats(const uint32_t* acc, int cc, const float* s_scale,
+                                                        const float* s_bias, const ResidualRow& rr, const EpiFast f,
+                                                        float (&v)[16]) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const float4 sc = *reinterpret_cast<const float4*>(s_scale + cc + 4 * q);
@@ -205,6 +205,12 @@ __device__ __forceinline__ void epilogue_chunk16_vals(const uint32_t* acc, int c
     v[2 * j] = fmaf(r0, f.m2, fmaxf(fmaf(r0, f.m1, v[2 * j]), f.lo));
     v[2 * j + 1] = fmaf(r1, f.m2, fmaxf(fmaf(r1, f.m1, v[2 * j + 1]), f.lo));
   }
+}
+
+__device__ __forceinline__ void epilogue_chunk16_vals(const uint32_t* acc, int cc, const float* s_scale, const float* s_bias,
+                                                      const ResidualRow& rr, const EpiFast f, uint4& o0, uint4& o1) {
+  float v[16];
+  epilogue_chunk16_floats(acc, cc, s_scale, s_bias, rr, f, v);
   o0 = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
   o1 = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
 }
@@ -989,8 +995,15 @@ __device__ __forceinline__ KwRing kw_next(KwRing r) {
   return n;
 }
 
-template <int KSTEPS, int SUBROW>
-__global__ void __launch_bounds__(kThreads, 1)
+// Warps: 0 = TMA producer, 1 = MMA issuer, 2..9 = epilogue, two groups of four.  ncu on the first version (one group):
+// the epilogue, not the tensor pipe, set the pace -- 421 instructions per plane per warp with ONE warp per scheduler
+// (SHFL / LDS round trips and dependent FP32 chains fully exposed: 3.9 cycles per instruction, tensor pipe 37 % busy).
+// Two groups drain alternate accumulator planes, so every scheduler has two epilogue warps to interleave, and the
+// per-channel scale / bias live in registers.
+constexpr int kKwThreads = 320;
+
+template <int KSTEPS, int SUBROW, bool RES>
+__global__ void __launch_bounds__(kKwThreads, 1)
 conv3d_kwfuse_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                      const __grid_constant__ HaloParams p) {
   constexpr int K = 3, CP = 32, K3 = 27;
@@ -1038,7 +1051,7 @@ conv3d_kwfuse_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
-  if (warp >= 2) {                                        // zero the whole accumulator ring once
+  if (warp >= 2 && warp < 6) {                            // zero the whole accumulator ring once
     const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     for (uint32_t c = 0; c < TCOLS; c += 16u) tmem_st16_zero(lane_base + c);
     tmem_st_wait();
@@ -1137,32 +1150,45 @@ conv3d_kwfuse_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
       r0 = kw_next(kw_next(r0));                          // acc_per_col = D + 2
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int quad = warp & 3;
+    // ===================== epilogue (warps 2..9) =====================
+    const int quad = warp & 3;                            // TMEM lane quadrant this warp may access
+    const uint32_t grp = (uint32_t)(warp - 2) >> 2;       // drains accumulator planes with (global index & 1) == grp
     const int row = quad * 32 + lane;
     const int r_w = row % p.WP, r_h = row / p.WP;
-    EpiFast f;
-    f.m1 = p.epi.residual_mode == 1 ? 1.f : 0.f;
-    f.m2 = p.epi.residual_mode == 2 ? 1.f : 0.f;
-    f.lo = p.epi.relu ? 0.f : -INFINITY;
+    const float m1 = p.epi.residual_mode == 1 ? 1.f : 0.f, m2 = p.epi.residual_mode == 2 ? 1.f : 0.f;
+    const float lo = p.epi.relu ? 0.f : -INFINITY;
+    float2 sc[CP / 2], bi[CP / 2];
+#pragma unroll
+    for (int j = 0; j < CP / 2; ++j) {
+      sc[j] = make_float2(s_scale[2 * j], s_scale[2 * j + 1]);
+      bi[j] = make_float2(s_bias[2 * j], s_bias[2 * j + 1]);
+    }
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
     const int64_t plane_vox = (int64_t)p.H * p.W;
     KwRing rg{0u, 0u};
+    uint32_t par = 0;                                     // parity of the global accumulator-plane index
+    const bool out_f32 = p.epi.out_f32 != 0;
     int tw = blockIdx.x % p.tiles_w, rest = blockIdx.x / p.tiles_w;
     for (int col = blockIdx.x; col < p.num_cols; col += gridDim.x) {
       const int th = rest % p.tiles_h, n = rest / p.tiles_h;
       const int ow = tw * p.TWv + r_w, oh = th * p.TH + r_h;
       const bool in_range = r_w < p.TWv && ow < p.W && oh < p.H;
       int64_t vox = (((int64_t)n * p.D) * p.H + oh) * p.W + ow - plane_vox;       // accumulator plane a <-> output plane a - 1
-      for (uint32_t a = 0; a < acc_per_col; ++a, vox += plane_vox) {
+      for (uint32_t a = 0; a < acc_per_col; ++a, vox += plane_vox, rg = kw_next(rg), par ^= 1u) {
+        if (par != grp) continue;
         const bool real = a >= 1u && a <= (uint32_t)p.D;
-        ResidualRow rr;
-        residual_prefetch(p.epi, in_range && real, vox, rr);
+        uint4 rq[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rq[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (RES && in_range && real) {                    // issued before the wait: overlaps the MMAs of this plane
+          const uint4* rp = reinterpret_cast<const uint4*>(p.epi.residual + vox * p.epi.res_cstride + p.epi.res_coffset);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) rq[i] = __ldg(rp + i);
+        }
         mbar_wait(smem_u32(&acc_full_bar[rg.b]), rg.ph);
         tcgen05_fence_after();
         const uint32_t taddr = lane_base + rg.b * kKwBlkCols;
         if (real) {
-          __nv_bfloat16* yrow = reinterpret_cast<__nv_bfloat16*>(p.epi.y) + vox * p.epi.out_cstride + p.epi.out_coffset;
 #pragma unroll
           for (int c0 = 0; c0 < CP; c0 += 16) {
             uint32_t q0[16], q1[16], q2[16];
@@ -1171,13 +1197,42 @@ conv3d_kwfuse_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             tmem_ld16(taddr + (uint32_t)(2 * CP + c0), q2);
             tmem_ld_wait();
             // out[m] = P_0[m] + P_1[m+1] + P_2[m+2]  (rows = lanes; the upper lanes of a tile row are not output columns)
+            float v[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float s1 = __shfl_down_sync(0xffffffffu, __uint_as_float(q1[j]), 1);
-              const float s2 = __shfl_down_sync(0xffffffffu, __uint_as_float(q2[j]), 2);
-              q0[j] = __float_as_uint((__uint_as_float(q0[j]) + s1) + s2);
+            for (int j = 0; j < 8; ++j) {
+              const float2 s1 = make_float2(__shfl_down_sync(0xffffffffu, __uint_as_float(q1[2 * j]), 1),
+                                            __shfl_down_sync(0xffffffffu, __uint_as_float(q1[2 * j + 1]), 1));
+              const float2 s2 = make_float2(__shfl_down_sync(0xffffffffu, __uint_as_float(q2[2 * j]), 2),
+                                            __shfl_down_sync(0xffffffffu, __uint_as_float(q2[2 * j + 1]), 2));
+              float2 t = __fadd2_rn(make_float2(__uint_as_float(q0[2 * j]), __uint_as_float(q0[2 * j + 1])), s1);
+              t = __fadd2_rn(t, s2);
+              t = __ffma2_rn(t, sc[c0 / 2 + j], bi[c0 / 2 + j]);
+              if (RES) {                                  // x += r*m1; x = max(x, lo); x += r*m2   (EpiFast semantics)
+                const uint4 rv = rq[c0 / 8 + (j >> 2)];   // channels c0 + 2j, c0 + 2j + 1
+                const uint32_t w = (j & 3) == 0 ? rv.x : ((j & 3) == 1 ? rv.y : ((j & 3) == 2 ? rv.z : rv.w));
+                const float2 r = make_float2(bf16_lo(w), bf16_hi(w));
+                t = __ffma2_rn(r, make_float2(m1, m1), t);
+                t = make_float2(fmaxf(t.x, lo), fmaxf(t.y, lo));
+                t = __ffma2_rn(r, make_float2(m2, m2), t);
+              } else {
+                t = make_float2(fmaxf(t.x, lo), fmaxf(t.y, lo));
+              }
+              v[2 * j] = t.x;
+              v[2 * j + 1] = t.y;
             }
-            if (in_range) epilogue_chunk16(q0, c0, s_scale, s_bias, rr, f, yrow);
+            if (in_range && !out_f32) {
+              uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.epi.y) + vox * p.epi.out_cstride +
+                                                  p.epi.out_coffset + c0);
+              o[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+              o[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
+                                pack_bf16x2(v[14], v[15]));
+            }
+            if (in_range && out_f32) {                    // fp32 rows (tests, module boundaries): same arithmetic, no rounding
+              float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.epi.y) + vox * p.epi.out_cstride +
+                                                    p.epi.out_coffset + c0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
           }
         }
 #pragma unroll
@@ -1186,7 +1241,6 @@ conv3d_kwfuse_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&acc_empty_bar[rg.b]));
-        rg = kw_next(rg);
       }
       const int nc = col + (int)gridDim.x;
       tw = nc % p.tiles_w; rest = nc / p.tiles_w;
@@ -2351,9 +2405,96 @@ int launch_halo(const void* x, const void* w_packed, const float* scale, const f
 #undef SNVC_KDFUSE_S
   if (!kern) return 1;                                  // CoutPad 48: per-tap kernel
   SNVC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = std::min(p.num_cols, ctas_per_sm * sm_count());
+  int grid = std::min(p.num_cols, ctas_per_sm * sm_count());
+  if (const char* mg = getenv("SNVC_CONV_MAXGRID")) grid = std::max(1, std::min(grid, atoi(mg)));   // tests: force ring wrap-around
   kern<<<grid, kThreads, smem, stream>>>(map_x, map_w, map_y, p);
   return launch_status("conv3d_kdfuse_kernel");
+}
+
+// ---- v7 host side: kw+kd-fused plane march; returns 1 when not eligible (caller uses the kd-fused kernel).
+// Eligible: 3x3x3, stride 1, dilation 1, "same" padding, a 32-channel output (slice) on the lean epilogue path.
+int launch_kwfuse(const void* x, const void* w_packed, const float* scale, const float* bias, const void* residual,
+                  void* y, const snvc_conv3d_desc& d, const ConvParams& cp_full, cudaStream_t stream, int cout0 = 0,
+                  int ncout = 0) {
+  const char* mode = getenv("SNVC_CONV_MODE");
+  if (mode && (mode[0] == 'h' || mode[0] == 'k')) return 1;            // SNVC_CONV_MODE=kd / halo: v3 / v2 (A/B runs)
+  ConvParams cp = cp_full;
+  if (ncout > 0) {
+    cp.Cout = ncout; cp.CoutPad = round_up(ncout, 16);
+    cp.out_coffset += cout0; cp.res_coffset += cout0;
+    if (scale) scale += cout0;
+    if (bias) bias += cout0;
+  }
+  if (d.transposed || d.stride != 1 || d.kernel != 3 || d.dilation != 1 || d.pad != 1) return 1;
+  if (d.Do != d.Di || d.Ho != d.Hi || d.Wo != d.Wi) return 1;
+  if (cp.Cout != 32 || cp.CoutPad != 32 || cp.sigmoid || ((cp.out_cstride | cp.out_coffset) & 7) != 0) return 1;
+  if (d.Cin != 32 && d.Cin != 64) return 1;
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return fail(SNVC_E_DRIVER, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  HaloParams p{};
+  p.N = d.N; p.Cin = d.Cin; p.D = d.Di; p.H = d.Hi; p.W = d.Wi;
+  p.K = 3; p.dil = 1; p.pad = 1;
+  p.scale = scale; p.bias = bias;
+  p.epi.Cout = cp.Cout; p.epi.CoutPad = cp.CoutPad; p.epi.relu = cp.relu; p.epi.residual_mode = cp.residual_mode;
+  p.epi.sigmoid = 0; p.epi.out_f32 = cp.out_f32; p.epi.out_cstride = cp.out_cstride;
+  p.epi.out_coffset = cp.out_coffset; p.epi.res_cstride = cp.res_cstride; p.epi.res_coffset = cp.res_coffset;
+  p.epi.residual = (const __nv_bfloat16*)residual; p.epi.y = y;
+  p.w_rows_per_tap = cp_full.CoutPad; p.w_row0 = cout0;
+  p.sub_row_bytes = d.Cin * 2; p.nsub = 1;
+  const int row_bytes = d.Cin * 2, hw = 2;
+  p.w_tap_bytes = cp.CoutPad * row_bytes;
+  const int w_total = round_up(27 * p.w_tap_bytes, 1024);
+  // row pitch 16 or 32 only: output column w and its partial sums at w+1, w+2 must sit in the same warp
+  double best = -1;
+  for (int wp = 32; wp >= 16; wp >>= 1) {
+    const int twv = wp - hw, th = 128 / wp;
+    const double eff = ((double)d.Wi / (ceil_div(d.Wi, twv) * wp)) * ((double)d.Hi / (ceil_div(d.Hi, th) * th));
+    if (eff > best) { best = eff; p.WP = wp; p.TH = th; p.TWv = twv; }
+  }
+  p.slot_bytes = round_up((p.TH + hw) * p.WP * row_bytes, 1024);
+  const int budget = 225 * 1024 - 1024 - w_total;
+  p.nslots = std::min(kMaxSlots, budget / p.slot_bytes);
+  if (p.nslots < 3) return 1;
+  p.sub_tile_bytes = p.slot_bytes;
+  p.w_sub_bytes = p.w_tap_bytes;
+  p.plane_bytes = (p.TH + hw) * p.WP * row_bytes;
+  p.tiles_h = (int)ceil_div(d.Hi, p.TH); p.tiles_w = (int)ceil_div(d.Wi, p.TWv);
+  const int64_t ncols = (int64_t)d.N * p.tiles_h * p.tiles_w;
+  SNVC_CHECK_ARG(ncols < (1ll << 31), "too many tile columns");
+  p.num_cols = (int)ncols;
+  const size_t smem = (size_t)w_total + (size_t)p.nslots * p.slot_bytes + 1024;
+
+  CUtensorMap map_x, map_w;
+  {
+    const cuuint64_t cs = (cuuint64_t)(d.in_cstride ? d.in_cstride : d.Cin) * 2;
+    cuuint64_t dims[5] = {(cuuint64_t)d.Cin, (cuuint64_t)d.Wi, (cuuint64_t)d.Hi, (cuuint64_t)d.Di, (cuuint64_t)d.N};
+    cuuint64_t strides[4] = {cs, (cuuint64_t)d.Wi * cs, (cuuint64_t)d.Hi * d.Wi * cs, (cuuint64_t)d.Di * d.Hi * d.Wi * cs};
+    cuuint32_t box[5] = {(cuuint32_t)d.Cin, (cuuint32_t)p.WP, (cuuint32_t)(p.TH + hw), 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const void* xbase = static_cast<const char*>(x) + (size_t)d.in_coffset * 2;
+    CUresult r = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(xbase), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_mode(row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail((int)r, "cuTensorMapEncodeTiled(x, kwfuse) failed with CUresult %d", (int)r);
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)d.Cin, (cuuint64_t)27 * cp_full.CoutPad};
+    cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)d.Cin, (cuuint32_t)cp.CoutPad};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_packed), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_mode(row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail((int)r, "cuTensorMapEncodeTiled(w, kwfuse) failed with CUresult %d", (int)r);
+  }
+  void (*kern)(const CUtensorMap, const CUtensorMap, const HaloParams) =
+      d.Cin == 32 ? (cp.residual_mode ? conv3d_kwfuse_kernel<2, 64, true> : conv3d_kwfuse_kernel<2, 64, false>)
+                  : (cp.residual_mode ? conv3d_kwfuse_kernel<4, 128, true> : conv3d_kwfuse_kernel<4, 128, false>);
+  SNVC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = std::min(p.num_cols, sm_count());
+  if (const char* mg = getenv("SNVC_CONV_MAXGRID")) grid = std::max(1, std::min(grid, atoi(mg)));   // tests: force ring wrap-around
+  kern<<<grid, kKwThreads, smem, stream>>>(map_x, map_w, p);
+  return launch_status("conv3d_kwfuse_kernel");
 }
 
 // ---- v4 host side: fused transposed conv; returns 1 when not eligible (caller uses the per-class launches)
@@ -2698,12 +2839,17 @@ extern "C" int snvc_conv3d_fwd(const void* x, const void* w_packed, const float*
       if (r != 1) return r;
       r = launch_bigk(x, w_packed, scale, bias, residual, y, d, p, stream);
       if (r != 1) return r;
+      r = launch_kwfuse(x, w_packed, scale, bias, residual, y, d, p, stream);
+      if (r != 1) return r;
       r = launch_halo(x, w_packed, scale, bias, residual, y, d, p, stream, 0);
       if (r != 1) return r;
       // 64 -> 64: all 27 weight tiles (221 KB) do not fit next to the plane ring; run the plane march twice on
       // 32-channel output slices (the input, at most half resolution on this path, is read twice from L2/HBM)
       if (p.CoutPad == 64 && d.Cout == 64 && d.dilation == 1 && d.kernel == 3 && d.stride == 1 &&
           ((p.out_cstride | p.out_coffset) & 7) == 0) {
+        r = launch_kwfuse(x, w_packed, scale, bias, residual, y, d, p, stream, 0, 32);
+        if (r == 0) r = launch_kwfuse(x, w_packed, scale, bias, residual, y, d, p, stream, 32, 32);
+        if (r != 1) return r;
         r = launch_halo(x, w_packed, scale, bias, residual, y, d, p, stream, 0, 0, 32);
         if (r == 0) r = launch_halo(x, w_packed, scale, bias, residual, y, d, p, stream, 0, 32, 32);
         if (r != 1) return r;

@@ -48,9 +48,16 @@ class GlobalHotPath(nn.Module):
         """cost [N,D,H,W,2F] bf16 -> [N,D,H,W,ch] bf16 (one fused conv launch per layer; 64-channel layers
         run as two output slices).  `mark(name)`, if given, is called right after the first layer has been
         enqueued (bench.py records a CUDA event there to time the dominant kernel on its own)."""
-        x = self.dres0[0].fused(cost)
+        x = self.trunk_head(cost)
         if mark is not None:
             mark("dres0.conv1")
+        return self.trunk_tail(x)
+
+    def trunk_head(self, cost):
+        """dres0.conv1 (3x3x3, 2F -> ch): the single largest kernel of the path."""
+        return self.dres0[0].fused(cost)
+
+    def trunk_tail(self, x):
         x = self.dres0[1].fused(x)
         x = self.dres1[1].fused(self.dres1[0].fused(x), residual=x, residual_mode=1)
         return self.hg.fused(x, out_residual=x)[0]
@@ -64,6 +71,74 @@ class GlobalHotPath(nn.Module):
         -> lifted voxels [N,ch,Z,Y,X] (layout_out 'NCDHW') or [N,Z,Y,X,ch] ('NDHWC')."""
         cost = build_cost_volume_ndhwc_bf16(left_feat, right_feat, shift, 1)
         return self.lift(self.trunk(cost), proj, out_dtype, layout_out)
+
+
+class GraphedHotPath:
+    """CUDA-graph replay of `GlobalHotPath` for one fixed batch shape.
+
+    The eager path costs the host ~15 Python -> ctypes launches per batch (each with two tensor-map encodes and an
+    output allocation); at 4-5 ms of GPU work per 8 pairs that host work is on the critical path whenever the CPU is
+    busy or slow (bench.py measured 3.9 - 14 ms per step for the same 3.9 ms of kernels).  Here the launches of one
+    batch are captured once -- the C ABI launches on the caller's stream, keeps no host state and never synchronises,
+    so it is capturable as is -- and replayed with one `cudaGraphLaunch` per stage.
+
+    `stages=True` captures four graphs (cost volume | dres0.conv1 | rest of the trunk | lift) sharing one memory
+    pool, so a caller can record events between them (bench.py); `stages=False` captures one graph.
+    Inputs are copied into the graph's static buffers (`self.inputs`); the result is the static tensor `self.vox`
+    (valid until the next replay).  `launches_per_replay` = kernels captured, from the library's launch counter."""
+
+    def __init__(self, model, batch, feat_channels, feat_hw, depth_bins, out_dtype=torch.bfloat16, layout_out="NDHWC",
+                 stages=False):
+        from snvc_b200 import _lib
+        self.model = model
+        dev = next(model.parameters()).device
+        self.dev = dev
+        H, W = feat_hw
+        self.inputs = (torch.zeros((batch, feat_channels, H, W), device=dev), torch.zeros((batch, feat_channels, H, W), device=dev),
+                       torch.zeros((batch, depth_bins), device=dev), torch.zeros((batch, 3, 4), device=dev))
+        self.inputs[3][:, 2, 2] = 1.0                       # a harmless projection for the warm-up pass
+        l, r, sh, pr = self.inputs
+        fns = [lambda: setattr(self, "_cost", build_cost_volume_ndhwc_bf16(l, r, sh, 1)),
+               lambda: setattr(self, "_x1", model.trunk_head(self._cost)),
+               lambda: setattr(self, "_feat", model.trunk_tail(self._x1)),
+               lambda: setattr(self, "vox", model.lift(self._feat, pr, out_dtype, layout_out))]
+        if not stages:
+            parts = list(fns)
+            fns = [lambda: [f() for f in parts]]
+        L = _lib.lib()
+        with torch.no_grad():
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):                  # eager warm-up: weight packing, lazy module state
+                for f in fns:
+                    f()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graphs, pool = [], None
+            n0 = L.snvc_launch_count()
+            for f in fns:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    f()
+                pool = g.pool()
+                self.graphs.append(g)
+            self.launches_per_replay = int(L.snvc_launch_count() - n0)
+
+    def load(self, left_feat, right_feat, shift, proj):
+        for d, s in zip(self.inputs, (left_feat, right_feat, shift, proj)):
+            d.copy_(s, non_blocking=True)
+
+    def replay(self, between=None):
+        """Replays the captured stages in order on the current stream; `between(i)` is called after stage i."""
+        for i, g in enumerate(self.graphs):
+            g.replay()
+            if between is not None:
+                between(i)
+        return self.vox
+
+    def __call__(self, left_feat, right_feat, shift, proj):
+        self.load(left_feat, right_feat, shift, proj)
+        return self.replay()
 
 
 class DepthHead(nn.Module):

@@ -146,6 +146,29 @@ def test_conv_large_kernel_plane_march(monkeypatch):
     _case(64, 32, 5, 1, 2, 1, False, (9, 8, 24), relu=True)
 
 
+def test_conv_kw_kd_fused_plane_march(monkeypatch):
+    """v7 kernel (kw and kd taps fused into N, 5-block TMEM ring, shuffle epilogue): both row pitches (W = 60 -> 32,
+    W = 40 / 14 -> 16), Cin 32 / 64, the 64 -> 64 output slices, every residual mode, ragged H / W edges, depths 1 and 2,
+    and -- grid clamped -- several tile columns per CTA with depths that are not multiples of 5, so the accumulator
+    ring wraps at every phase."""
+    monkeypatch.setenv("SNVC_CONV_MAXGRID", "2")
+    _case(32, 32, 3, 1, 1, 1, False, (13, 10, 60), N=2, relu=True, residual_mode=1)
+    _case(64, 32, 3, 1, 1, 1, False, (7, 16, 40), relu=True)
+    _case(64, 64, 3, 1, 1, 1, False, (6, 12, 44), relu=True, residual_mode=1)
+    _case(32, 32, 3, 1, 1, 1, False, (9, 9, 14), N=3, residual_mode=2, relu=True)
+    _case(32, 32, 3, 1, 1, 1, False, (1, 8, 30))
+    _case(64, 32, 3, 1, 1, 1, False, (2, 5, 33), residual_mode=1)
+    _case(32, 32, 3, 1, 1, 1, False, (24, 4, 31), relu=True)
+
+
+def test_conv_kd_fused_kernel_still_green(monkeypatch):
+    """SNVC_CONV_MODE=kd keeps the v3 kernel (kd taps only) reachable for A/B runs; it also serves Cout = 16 / 64."""
+    monkeypatch.setenv("SNVC_CONV_MODE", "kd")
+    monkeypatch.setenv("SNVC_CONV_MAXGRID", "2")
+    _case(32, 32, 3, 1, 1, 1, False, (13, 10, 60), N=2, relu=True, residual_mode=1)
+    _case(64, 32, 3, 1, 1, 1, False, (7, 16, 40), relu=True)
+
+
 def test_conv_kitti_level_shapes():
     """One slab of the global trunk's real W/H (W=312 is not a multiple of the tile)."""
     _case(64, 32, 3, 1, 1, 1, False, (4, 96, 312), relu=True)
