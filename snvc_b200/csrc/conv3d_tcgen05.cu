@@ -164,6 +164,22 @@ struct EpiParams {
   void* y;
 };
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256).  A warp's epilogue access touches 32 different voxel rows,
+// so its L1 data-pipe cost is one wavefront per row per instruction whatever the width: 32 bytes per instruction
+// halve the LSU wavefronts of the 128-bit form.  ncu on the kw-fused kernel: the L1 data pipe, which also feeds the
+// UMMA operand reads, is the binding unit (tensor-core reads 53 % + LSU 33 % of its cycles).
+__device__ __forceinline__ void stg256(void* p, uint4 a, uint4 b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+               "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+__device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
+__device__ __forceinline__ bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; }
+
 // Residual row prefetch: issued BEFORE waiting for the accumulator so the global-load latency
 // overlaps the MMAs of this tile (up to 64 channels = 8 x 16 B per row).
 struct ResidualRow { uint4 q[8]; };
@@ -173,6 +189,12 @@ __device__ __forceinline__ void residual_prefetch(const EpiParams& e, bool in_ra
   if (!e.residual_mode || !in_range) return;
   const __nv_bfloat16* rp = e.residual + vox * e.res_cstride + e.res_coffset;
   // host guarantees: Cout % 16 == 0 and 16-byte aligned rows whenever a residual is given
+  if (aligned32(rp)) {                                   // (Cout % 16 == 0: whole 32-byte pieces)
+#pragma unroll
+    for (int i = 0; i < 8; i += 2)
+      if (i * 8 < e.Cout) ldg256(reinterpret_cast<const uint4*>(rp) + i, rr.q[i], rr.q[i + 1]);
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i)
     if (i * 8 < e.Cout) rr.q[i] = __ldg(reinterpret_cast<const uint4*>(rp) + i);
@@ -220,6 +242,7 @@ __device__ __forceinline__ void epilogue_chunk16(const uint32_t* acc, int cc, co
   uint4 o0, o1;
   epilogue_chunk16_vals(acc, cc, s_scale, s_bias, rr, f, o0, o1);
   uint4* o = reinterpret_cast<uint4*>(yrow + cc);
+  if (aligned32(o)) { stg256(o, o0, o1); return; }
   o[0] = o0;
   o[1] = o1;
 }
@@ -1182,8 +1205,11 @@ conv3d_kwfuse_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         for (int i = 0; i < 4; ++i) rq[i] = make_uint4(0u, 0u, 0u, 0u);
         if (RES && in_range && real) {                    // issued before the wait: overlaps the MMAs of this plane
           const uint4* rp = reinterpret_cast<const uint4*>(p.epi.residual + vox * p.epi.res_cstride + p.epi.res_coffset);
+          if (aligned32(rp)) { ldg256(rp, rq[0], rq[1]); ldg256(rp + 2, rq[2], rq[3]); }
+          else {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) rq[i] = __ldg(rp + i);
+            for (int i = 0; i < 4; ++i) rq[i] = __ldg(rp + i);
+          }
         }
         mbar_wait(smem_u32(&acc_full_bar[rg.b]), rg.ph);
         tcgen05_fence_after();
@@ -1223,9 +1249,12 @@ conv3d_kwfuse_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             if (in_range && !out_f32) {
               uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.epi.y) + vox * p.epi.out_cstride +
                                                   p.epi.out_coffset + c0);
-              o[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-              o[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
-                                pack_bf16x2(v[14], v[15]));
+              const uint4 o0 = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                          pack_bf16x2(v[6], v[7]));
+              const uint4 o1 = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
+                                          pack_bf16x2(v[14], v[15]));
+              if (aligned32(o)) stg256(o, o0, o1);
+              else { o[0] = o0; o[1] = o1; }
             }
             if (in_range && out_f32) {                    // fp32 rows (tests, module boundaries): same arithmetic, no rounding
               float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.epi.y) + vox * p.epi.out_cstride +
