@@ -134,6 +134,25 @@ def test_lift_indices_bit_exact_kitti_geometry(ac):
         assert np.array_equal(idx[..., k][wvalid], ref.astype(np.int32)[wvalid])
 
 
+@pytest.mark.parametrize("C", [8, 16, 32, 64, 128])
+def test_roi_sample_kernel_generations_agree(C, monkeypatch):
+    """The product ROI sampler (v3: both views per round, 256-bit corner loads) must be bit-identical to v2
+    (SNVC_ROI_MODE=coop1) and to the one-thread-per-(point, view, 8 channels) kernel (SNVC_ROI_MODE=thread), with a
+    point count that is not a multiple of 16."""
+    lf, rf, gl, gr, (nh, nw, nl), res = _roi_case(N=2, C=C, Hf=12, Wf=20, grid=(3, 7, 11), res=(48, 80), seed=C)
+    assert (2 * nh * nw * nl) % 16 != 0
+    t = [torch.from_numpy(a).cuda() for a in (lf, rf, gl, gr)]
+    for od in (torch.bfloat16, torch.float32):
+        outs = []
+        for mode in ("thread", "coop1", "v3"):
+            monkeypatch.setenv("SNVC_ROI_MODE", mode)
+            outs.append(_F().roi_voxel_sample(*t, res, out_dtype=od, layout="NDHWC"))
+        view = torch.int16 if od == torch.bfloat16 else torch.int32
+        assert torch.equal(outs[0].view(view), outs[1].view(view))
+        assert torch.equal(outs[0].view(view), outs[2].view(view))
+        assert outs[2].float().abs().max().item() > 0
+
+
 @pytest.mark.parametrize("C", [16, 32, 64])
 def test_lift_cooperative_kernel_matches_thread_per_voxel_kernel(C, monkeypatch):
     """The product lift (C/8 lanes per voxel, set-up shared by warp shuffles) must be bit-identical to the
