@@ -1285,6 +1285,358 @@ conv3d_kwfuse_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 }
 
 // ==========================================================================================
+// v8: CTA-pair kd-fused plane march (3x3x3, stride 1, 32-channel output slice) -- tcgen05.mma.cta_group::2.
+//
+// Measured (scripts/micro/umma_2cta.cu, profiles/r01_umma_2cta.txt): issued over a CTA pair (M = 256, each CTA
+// supplies its own 128 A rows and HALF of the B rows), an SS-mode MMA costs max(51.3, N/2) cycles instead of
+// max(71.6, N/2) -- N = 96 runs at 94 % of the tensor peak instead of 67 % -- and each SM reads only N/2 weight rows
+// per instruction.  That removes both limits of the Cout = 32 layers at once: the issue floor that v7 attacked by
+// fusing kw into N (paying 64 shuffles and 3x the TMEM traffic per output row in the epilogue), and the L1 data pipe
+// that then bound v7 (operand reads 5.6 KB per 51-cycle MMA instead of 8.7 KB per 72).
+//
+// Structure: a cluster of two CTAs; each CTA marches its OWN tile column (its own plane ring, TMA loads, TMEM
+// accumulators and epilogue, exactly as v3) and holds half of every weight tile: rank r keeps rows [48r, 48r+48) of
+// the 96-row [kd=2 | kd=1 | kd=0] slab of each in-plane tap at the same shared-memory offset.  The leader's MMA warp
+// issues for both; every TMA load (either CTA) completes on the LEADER's full barrier (cta_group::2 form), commits
+// are multicast to both CTAs' barriers, and the follower's epilogue warps release accumulator blocks with remote
+// arrives on the leader's barriers.
+// Accumulator ring without instruction variants (a split MMA would need differently shifted weight halves): 14 ring
+// blocks + 2 MIRROR blocks (positions 14, 15 alias ring indices 0, 1), so the three blocks an input plane updates are
+// always the contiguous positions i, i+1, i+2; a plane whose ring index is 0 or 1 may hold partial sums in both its
+// primary and its mirror block, and the epilogue adds the two.
+// ==========================================================================================
+constexpr int kPairThreads = 320;
+constexpr uint32_t kPairRing = 14;
+
+struct PairRing { uint32_t i, ph; };
+__device__ __forceinline__ PairRing pr_next(PairRing r) {
+  PairRing n{r.i + 1u, r.ph};
+  if (n.i == kPairRing) { n.i = 0u; n.ph ^= 1u; }
+  return n;
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA's window) in the cluster's rank-0 CTA
+__device__ __forceinline__ uint32_t leader_addr(uint32_t addr) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(addr));
+  return r;
+}
+// (relaxed: the producer has nothing to publish, and a cluster-scope release is MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR --
+// ~1000 cycles per plane in the producer warp, which capped the Cin = 32 layers at 1565 cycles per plane: ncu showed the
+// MMA warp waiting for the plane's full barrier and the tensor pipe 55 % busy)
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.relaxed.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Relaxed on purpose: a release at cluster scope also waits for the thread's outstanding GLOBAL stores (the output
+// rows just written), which put ~700 cycles per plane on the epilogue's critical path (32->32 layers: 631 us with
+// .release against 578 us for v7).  What the arrive must order -- the tcgen05.st zero fill of the drained block -- is
+// already complete (tcgen05.wait::st) and fenced (tcgen05.fence::before_thread_sync) when the arrive is issued.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                                 int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, 1, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+
+// WPT = row pitch as a template parameter: every operand-descriptor offset of the 9*KSTEPS MMAs of a plane is then an
+// immediate added to two uniform registers.  With the pitch a run-time value the 36 descriptors of a Cin = 64 plane
+// did not fit the uniform register file; ptxas built them in vector registers and moved them over with R2UR, ~20
+// instructions and 70-90 cycles per UTCHMMA.2CTA -- more than the 51-cycle MMA itself (first version: 32->32 layers
+// 620 us, slower than v7).
+template <int KSTEPS, int SUBROW, bool RES, int WPT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
+conv3d_kdpair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                     const __grid_constant__ HaloParams p) {
+  constexpr int K = 3, CP = 32;
+  constexpr uint32_t TCOLS = 512;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxSlots];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxSlots];
+  __shared__ __align__(8) uint64_t w_bar;
+  __shared__ __align__(8) uint64_t acc_full_bar[kPairRing];
+  __shared__ __align__(8) uint64_t acc_empty_bar[kPairRing];
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(16) float s_scale[64], s_bias[64];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t w_base = (smem_u32(smem) + 1023u) & ~1023u;
+  const uint32_t slots_base = w_base + (((uint32_t)(K * K * p.w_tap_bytes) + 1023u) & ~1023u);
+  const uint32_t acc_per_col = (uint32_t)p.D + 2u;        // accumulator planes per column: out[-1] .. out[D]
+  const int npairs = (p.num_cols + 1) >> 1;
+  const int pair0 = (int)(blockIdx.x >> 1), pstep = (int)(gridDim.x >> 1);
+
+  if (threadIdx.x < 64) {
+    s_scale[threadIdx.x] = (p.scale && threadIdx.x < p.epi.Cout) ? p.scale[threadIdx.x] : 1.f;
+    s_bias[threadIdx.x] = (p.bias && threadIdx.x < p.epi.Cout) ? p.bias[threadIdx.x] : 0.f;
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    for (int s = 0; s < p.nslots; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 2);               // leader's copy: one arrive + tx per CTA
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(&w_bar), 2);
+    for (uint32_t b = 0; b < kPairRing; ++b) {
+      mbar_init(smem_u32(&acc_full_bar[b]), 1);
+      mbar_init(smem_u32(&acc_empty_bar[b]), 8);          // leader's copy: one arrive per epilogue warp of the draining group, both CTAs
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                 "r"(TCOLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  if (warp >= 2 && warp < 6) {                            // zero this CTA's whole accumulator ring once
+    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    for (uint32_t c = 0; c < TCOLS; c += 16u) tmem_st16_zero(lane_base + c);
+    tmem_st_wait();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                     // both CTAs: barriers initialised, TMEM allocated and zeroed
+  tcgen05_fence_after();
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs; every load completes on the LEADER's barrier) =====================
+    const uint32_t wb = leader_addr(smem_u32(&w_bar));
+    if (elect_one()) {
+      mbar_expect_tx_cluster(wb, (uint32_t)(K * K * p.w_tap_bytes));
+      // this CTA's half of every tap's 96-row slab [kd=2 | kd=1 | kd=0]: slab rows [48*rank, 48*rank + 48), 16 at a time
+      for (int t2 = 0; t2 < K * K; ++t2)
+        for (int j = 0; j < 3; ++j) {
+          const int srow = 48 * (int)rank + 16 * j;
+          const int kd = 2 - (srow >> 5), c0 = srow & 31;
+          tma_load_2d_pair(w_base + t2 * p.w_tap_bytes + j * 16 * SUBROW, &map_w, wb, 0,
+                           (kd * K * K + t2) * p.w_rows_per_tap + p.w_row0 + c0);
+        }
+    }
+    __syncwarp();
+    uint32_t slot = 0, phase = 0;
+    uint32_t slot_addr = slots_base;
+    for (int q = pair0; q < npairs; q += pstep) {
+      const int col = min(2 * q + (int)rank, p.num_cols - 1);           // (odd column count: the last follower re-reads a column)
+      const int tw = col % p.tiles_w, rest = col / p.tiles_w;
+      const int th = rest % p.tiles_h, n = rest / p.tiles_h;
+      const int w0 = tw * p.TWv - p.pad, h0 = th * p.TH - p.pad;
+      for (int ip = 0; ip < p.D; ++ip) {
+        mbar_wait(smem_u32(&empty_bar[slot]), phase ^ 1u);
+        if (elect_one()) {
+          const uint32_t fb = leader_addr(smem_u32(&full_bar[slot]));
+          mbar_expect_tx_cluster(fb, (uint32_t)p.plane_bytes);
+          tma_load_5d_pair(slot_addr, &map_x, fb, 0, w0, h0, ip, n);
+        }
+        __syncwarp();
+        slot_addr += (uint32_t)p.slot_bytes;
+        if (++slot == (uint32_t)p.nslots) { slot = 0; phase ^= 1u; slot_addr = slots_base; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((3 * CP) >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      const uint32_t desc_hi = (uint32_t)(make_smem_desc(0, SUBROW) >> 32);
+      constexpr uint32_t lo_flags = 1u << 16;
+      const uint32_t b_lo0 = ((w_base >> 4) & 0x3FFFu) | lo_flags;
+      constexpr uint32_t b_tap = (uint32_t)(48 * SUBROW) >> 4;
+      const uint32_t a_lo0 = ((slots_base >> 4) & 0x3FFFu) | lo_flags;
+      const uint32_t a_step = (uint32_t)p.slot_bytes >> 4;
+      mbar_wait(smem_u32(&w_bar), 0);
+      uint32_t slot = 0, phase = 0, a_plane = a_lo0;
+      PairRing r0{0u, 0u};                                // ring position of accumulator plane g = out[pl-1]
+      for (int q = pair0; q < npairs; q += pstep) {
+        for (int pl = 0; pl < p.D; ++pl) {
+          const PairRing r1 = pr_next(r0), r2 = pr_next(r1);
+          mbar_wait(smem_u32(&full_bar[slot]), phase);
+          if (pl == 0) {
+            mbar_wait(smem_u32(&acc_empty_bar[r0.i]), r0.ph ^ 1u);
+            mbar_wait(smem_u32(&acc_empty_bar[r1.i]), r1.ph ^ 1u);
+          }
+          mbar_wait(smem_u32(&acc_empty_bar[r2.i]), r2.ph ^ 1u);
+          tcgen05_fence_after();
+          const uint32_t d0 = tmem_base + r0.i * (uint32_t)CP;          // positions i, i+1, i+2 (14, 15 = mirrors of 0, 1)
+          if (elect_one()) {
+#pragma unroll
+            for (int t2 = 0; t2 < K * K; ++t2)
+#pragma unroll
+              for (int k = 0; k < KSTEPS; ++k)
+                umma_bf16_pair(d0, desc64(desc_hi, a_plane + (uint32_t)((((t2 / K) * WPT + (t2 % K)) * SUBROW) >> 4) + 2u * k),
+                               desc64(desc_hi, b_lo0 + (uint32_t)t2 * b_tap + 2u * k), idesc);
+            umma_commit_pair(smem_u32(&empty_bar[slot]));                 // plane consumed (both CTAs)
+            umma_commit_pair(smem_u32(&acc_full_bar[r0.i]));              // out[pl-1] complete
+            if (pl == p.D - 1) {                                          // column tail: out[D-1], out[D]
+              umma_commit_pair(smem_u32(&acc_full_bar[r1.i]));
+              umma_commit_pair(smem_u32(&acc_full_bar[r2.i]));
+            }
+          }
+          __syncwarp();
+          a_plane += a_step;
+          if (++slot == (uint32_t)p.nslots) { slot = 0; phase ^= 1u; a_plane = a_lo0; }
+          r0 = r1;
+        }
+        r0 = pr_next(pr_next(r0));                        // acc_per_col = D + 2
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..9 of both CTAs; two groups drain alternate planes) =====================
+    const int quad = warp & 3;
+    const uint32_t grp = (uint32_t)(warp - 2) >> 2;
+    const int row = quad * 32 + lane;
+    const int r_w = row % p.WP, r_h = row / p.WP;
+    const float m1 = p.epi.residual_mode == 1 ? 1.f : 0.f, m2 = p.epi.residual_mode == 2 ? 1.f : 0.f;
+    const float lo = p.epi.relu ? 0.f : -INFINITY;
+    float2 sc[CP / 2], bi[CP / 2];
+#pragma unroll
+    for (int j = 0; j < CP / 2; ++j) {
+      sc[j] = make_float2(s_scale[2 * j], s_scale[2 * j + 1]);
+      bi[j] = make_float2(s_bias[2 * j], s_bias[2 * j + 1]);
+    }
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const uint32_t empty0 = leader_addr(smem_u32(&acc_empty_bar[0]));
+    const int64_t plane_vox = (int64_t)p.H * p.W;
+    PairRing rg{0u, 0u};
+    uint32_t par = 0;
+    const bool out_f32 = p.epi.out_f32 != 0;
+    for (int q = pair0; q < npairs; q += pstep) {
+      const int col = 2 * q + (int)rank;
+      const bool ghost = col >= p.num_cols;               // odd column count: the last follower's results are dropped
+      const int colc = ghost ? p.num_cols - 1 : col;
+      const int tw = colc % p.tiles_w, rest = colc / p.tiles_w;
+      const int th = rest % p.tiles_h, n = rest / p.tiles_h;
+      const int ow = tw * p.TWv + r_w, oh = th * p.TH + r_h;
+      const bool in_range = !ghost && r_w < p.TWv && ow < p.W && oh < p.H;
+      int64_t vox = (((int64_t)n * p.D) * p.H + oh) * p.W + ow - plane_vox;       // accumulator plane a <-> output plane a - 1
+      for (uint32_t a = 0; a < acc_per_col; ++a, vox += plane_vox, rg = pr_next(rg), par ^= 1u) {
+        if (par != grp) continue;
+        const bool real = a >= 1u && a <= (uint32_t)p.D;
+        uint4 rq[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rq[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (RES && in_range && real) {                    // issued before the wait: overlaps the MMAs of this plane
+          const uint4* rp = reinterpret_cast<const uint4*>(p.epi.residual + vox * p.epi.res_cstride + p.epi.res_coffset);
+          if (aligned32(rp)) { ldg256(rp, rq[0], rq[1]); ldg256(rp + 2, rq[2], rq[3]); }
+          else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) rq[i] = __ldg(rp + i);
+          }
+        }
+        mbar_wait(smem_u32(&acc_full_bar[rg.i]), rg.ph);
+        tcgen05_fence_after();
+        const uint32_t taddr = lane_base + rg.i * (uint32_t)CP;
+        const bool mirrored = rg.i < 2u;                  // partial sums may also sit in the mirror block (position 14 + i)
+        const uint32_t maddr = lane_base + (kPairRing + rg.i) * (uint32_t)CP;
+        if (real) {
+#pragma unroll
+          for (int c0 = 0; c0 < CP; c0 += 16) {
+            uint32_t q0[16];
+            tmem_ld16(taddr + (uint32_t)c0, q0);
+            if (mirrored) {
+              uint32_t q1[16];
+              tmem_ld16(maddr + (uint32_t)c0, q1);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) q0[j] = __float_as_uint(__uint_as_float(q0[j]) + __uint_as_float(q1[j]));
+            } else {
+              tmem_ld_wait();
+            }
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float2 t = __ffma2_rn(make_float2(__uint_as_float(q0[2 * j]), __uint_as_float(q0[2 * j + 1])), sc[c0 / 2 + j],
+                                    bi[c0 / 2 + j]);
+              if (RES) {                                  // x += r*m1; x = max(x, lo); x += r*m2   (EpiFast semantics)
+                const uint4 rv = rq[c0 / 8 + (j >> 2)];   // channels c0 + 2j, c0 + 2j + 1
+                const uint32_t w = (j & 3) == 0 ? rv.x : ((j & 3) == 1 ? rv.y : ((j & 3) == 2 ? rv.z : rv.w));
+                const float2 r = make_float2(bf16_lo(w), bf16_hi(w));
+                t = __ffma2_rn(r, make_float2(m1, m1), t);
+                t = make_float2(fmaxf(t.x, lo), fmaxf(t.y, lo));
+                t = __ffma2_rn(r, make_float2(m2, m2), t);
+              } else {
+                t = make_float2(fmaxf(t.x, lo), fmaxf(t.y, lo));
+              }
+              v[2 * j] = t.x;
+              v[2 * j + 1] = t.y;
+            }
+            if (in_range && !out_f32) {
+              uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.epi.y) + vox * p.epi.out_cstride +
+                                                  p.epi.out_coffset + c0);
+              const uint4 o0 = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                          pack_bf16x2(v[6], v[7]));
+              const uint4 o1 = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
+                                          pack_bf16x2(v[14], v[15]));
+              if (aligned32(o)) stg256(o, o0, o1);
+              else { o[0] = o0; o[1] = o1; }
+            }
+            if (in_range && out_f32) {                    // fp32 rows (tests, module boundaries): same arithmetic, no rounding
+              float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.epi.y) + vox * p.epi.out_cstride +
+                                                    p.epi.out_coffset + c0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+          }
+        }
+#pragma unroll
+        for (uint32_t c = 0; c < (uint32_t)CP; c += 16u) tmem_st16_zero(taddr + c);   // ready for its next output plane
+        if (mirrored) {
+#pragma unroll
+          for (uint32_t c = 0; c < (uint32_t)CP; c += 16u) tmem_st16_zero(maddr + c);
+        }
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(empty0 + rg.i * 8u);
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                     // the peer may still be reading / signalling this CTA
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCOLS) : "memory");
+  }
+}
+
+// ==========================================================================================
 // v4: fused transposed convolution (k3, s2, p1, output_padding 1) -- all 8 output-parity classes
 // of an input tile in ONE kernel (the per-tap path above launches 8 kernels, each re-reading the
 // input through per-tap TMA boxes and writing a stride-2 quarter of the output).
@@ -2440,13 +2792,103 @@ int launch_halo(const void* x, const void* w_packed, const float* scale, const f
   return launch_status("conv3d_kdfuse_kernel");
 }
 
+// ---- v8 host side: CTA-pair kd-fused plane march; returns 1 when not eligible (caller tries v7, then v3).
+// Eligible: 3x3x3, stride 1, dilation 1, "same" padding, a 32-channel output (slice) on the lean epilogue path.
+int launch_kdpair(const void* x, const void* w_packed, const float* scale, const float* bias, const void* residual,
+                  void* y, const snvc_conv3d_desc& d, const ConvParams& cp_full, cudaStream_t stream, int cout0 = 0,
+                  int ncout = 0) {
+  const char* mode = getenv("SNVC_CONV_MODE");
+  if (mode && (mode[0] == 'h' || mode[0] == 'k')) return 1;            // SNVC_CONV_MODE=kw / kd / halo: v7 / v3 / v2 (A/B runs)
+  ConvParams cp = cp_full;
+  if (ncout > 0) {
+    cp.Cout = ncout; cp.CoutPad = round_up(ncout, 16);
+    cp.out_coffset += cout0; cp.res_coffset += cout0;
+    if (scale) scale += cout0;
+    if (bias) bias += cout0;
+  }
+  if (d.transposed || d.stride != 1 || d.kernel != 3 || d.dilation != 1 || d.pad != 1) return 1;
+  if (d.Do != d.Di || d.Ho != d.Hi || d.Wo != d.Wi) return 1;
+  if (cp.Cout != 32 || cp.CoutPad != 32 || cp.sigmoid || ((cp.out_cstride | cp.out_coffset) & 7) != 0) return 1;
+  if (d.Cin != 32 && d.Cin != 64) return 1;
+  if (sm_count() < 2) return 1;
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return fail(SNVC_E_DRIVER, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  HaloParams p{};
+  p.N = d.N; p.Cin = d.Cin; p.D = d.Di; p.H = d.Hi; p.W = d.Wi;
+  p.K = 3; p.dil = 1; p.pad = 1;
+  p.scale = scale; p.bias = bias;
+  p.epi.Cout = cp.Cout; p.epi.CoutPad = cp.CoutPad; p.epi.relu = cp.relu; p.epi.residual_mode = cp.residual_mode;
+  p.epi.sigmoid = 0; p.epi.out_f32 = cp.out_f32; p.epi.out_cstride = cp.out_cstride;
+  p.epi.out_coffset = cp.out_coffset; p.epi.res_cstride = cp.res_cstride; p.epi.res_coffset = cp.res_coffset;
+  p.epi.residual = (const __nv_bfloat16*)residual; p.epi.y = y;
+  p.w_rows_per_tap = cp_full.CoutPad; p.w_row0 = cout0;
+  p.sub_row_bytes = d.Cin * 2; p.nsub = 1;
+  const int row_bytes = d.Cin * 2, hw = 2;
+  p.w_tap_bytes = 48 * row_bytes;                        // this CTA's half of a tap's 96-row [kd=2|kd=1|kd=0] slab
+  const int w_total = round_up(9 * p.w_tap_bytes, 1024);
+  const int budget = 225 * 1024 - 1024 - w_total;
+  double best = -1;
+  for (int wp = 16; wp <= 64; wp <<= 1) {
+    const int twv = wp - hw, th = 128 / wp;
+    const int slot = round_up(((th + hw) * wp + 16) * row_bytes, 1024);   // + 16 rows: the kw-shifted windows of the last rows
+    if (budget < 4 * slot) continue;
+    const double eff = ((double)d.Wi / (ceil_div(d.Wi, twv) * wp)) * ((double)d.Hi / (ceil_div(d.Hi, th) * th));
+    if (eff > best) { best = eff; p.WP = wp; p.TH = th; p.TWv = twv; p.slot_bytes = slot; }
+  }
+  if (best < 0) return 1;
+  p.nslots = std::min(kMaxSlots, budget / p.slot_bytes);
+  p.sub_tile_bytes = p.slot_bytes;
+  p.w_sub_bytes = p.w_tap_bytes;
+  p.plane_bytes = (p.TH + hw) * p.WP * row_bytes;
+  p.tiles_h = (int)ceil_div(d.Hi, p.TH); p.tiles_w = (int)ceil_div(d.Wi, p.TWv);
+  const int64_t ncols = (int64_t)d.N * p.tiles_h * p.tiles_w;
+  SNVC_CHECK_ARG(ncols < (1ll << 31), "too many tile columns");
+  p.num_cols = (int)ncols;
+  const size_t smem = (size_t)w_total + (size_t)p.nslots * p.slot_bytes + 1024;
+
+  CUtensorMap map_x, map_w;
+  {
+    const cuuint64_t cs = (cuuint64_t)(d.in_cstride ? d.in_cstride : d.Cin) * 2;
+    cuuint64_t dims[5] = {(cuuint64_t)d.Cin, (cuuint64_t)d.Wi, (cuuint64_t)d.Hi, (cuuint64_t)d.Di, (cuuint64_t)d.N};
+    cuuint64_t strides[4] = {cs, (cuuint64_t)d.Wi * cs, (cuuint64_t)d.Hi * d.Wi * cs, (cuuint64_t)d.Di * d.Hi * d.Wi * cs};
+    cuuint32_t box[5] = {(cuuint32_t)d.Cin, (cuuint32_t)p.WP, (cuuint32_t)(p.TH + hw), 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const void* xbase = static_cast<const char*>(x) + (size_t)d.in_coffset * 2;
+    CUresult r = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(xbase), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_mode(row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail((int)r, "cuTensorMapEncodeTiled(x, kdpair) failed with CUresult %d", (int)r);
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)d.Cin, (cuuint64_t)27 * cp_full.CoutPad};
+    cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)d.Cin, 16};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_packed), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_mode(row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail((int)r, "cuTensorMapEncodeTiled(w, kdpair) failed with CUresult %d", (int)r);
+  }
+  void (*kern)(const CUtensorMap, const CUtensorMap, const HaloParams) = nullptr;
+#define SNVC_PAIR_W(KS, SR, RS)                                                                                   \
+  (p.WP == 16 ? conv3d_kdpair_kernel<KS, SR, RS, 16> : (p.WP == 32 ? conv3d_kdpair_kernel<KS, SR, RS, 32> : conv3d_kdpair_kernel<KS, SR, RS, 64>))
+  if (d.Cin == 32) kern = cp.residual_mode ? SNVC_PAIR_W(2, 64, true) : SNVC_PAIR_W(2, 64, false);
+  else kern = cp.residual_mode ? SNVC_PAIR_W(4, 128, true) : SNVC_PAIR_W(4, 128, false);
+#undef SNVC_PAIR_W
+  SNVC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int pairs = std::min((p.num_cols + 1) / 2, sm_count() / 2);
+  if (const char* mg = getenv("SNVC_CONV_MAXGRID")) pairs = std::max(1, std::min(pairs, atoi(mg)));   // tests: force ring wrap-around
+  kern<<<2 * pairs, kPairThreads, smem, stream>>>(map_x, map_w, p);
+  return launch_status("conv3d_kdpair_kernel");
+}
+
 // ---- v7 host side: kw+kd-fused plane march; returns 1 when not eligible (caller uses the kd-fused kernel).
 // Eligible: 3x3x3, stride 1, dilation 1, "same" padding, a 32-channel output (slice) on the lean epilogue path.
 int launch_kwfuse(const void* x, const void* w_packed, const float* scale, const float* bias, const void* residual,
                   void* y, const snvc_conv3d_desc& d, const ConvParams& cp_full, cudaStream_t stream, int cout0 = 0,
                   int ncout = 0) {
   const char* mode = getenv("SNVC_CONV_MODE");
-  if (mode && (mode[0] == 'h' || mode[0] == 'k')) return 1;            // SNVC_CONV_MODE=kd / halo: v3 / v2 (A/B runs)
+  if (mode && (mode[0] == 'h' || (mode[0] == 'k' && mode[1] == 'd'))) return 1;   // SNVC_CONV_MODE=kd / halo: v3 / v2 (A/B runs)
   ConvParams cp = cp_full;
   if (ncout > 0) {
     cp.Cout = ncout; cp.CoutPad = round_up(ncout, 16);
@@ -2868,6 +3310,8 @@ extern "C" int snvc_conv3d_fwd(const void* x, const void* w_packed, const float*
       if (r != 1) return r;
       r = launch_bigk(x, w_packed, scale, bias, residual, y, d, p, stream);
       if (r != 1) return r;
+      r = launch_kdpair(x, w_packed, scale, bias, residual, y, d, p, stream);
+      if (r != 1) return r;
       r = launch_kwfuse(x, w_packed, scale, bias, residual, y, d, p, stream);
       if (r != 1) return r;
       r = launch_halo(x, w_packed, scale, bias, residual, y, d, p, stream, 0);
@@ -2876,6 +3320,9 @@ extern "C" int snvc_conv3d_fwd(const void* x, const void* w_packed, const float*
       // 32-channel output slices (the input, at most half resolution on this path, is read twice from L2/HBM)
       if (p.CoutPad == 64 && d.Cout == 64 && d.dilation == 1 && d.kernel == 3 && d.stride == 1 &&
           ((p.out_cstride | p.out_coffset) & 7) == 0) {
+        r = launch_kdpair(x, w_packed, scale, bias, residual, y, d, p, stream, 0, 32);
+        if (r == 0) r = launch_kdpair(x, w_packed, scale, bias, residual, y, d, p, stream, 32, 32);
+        if (r != 1) return r;
         r = launch_kwfuse(x, w_packed, scale, bias, residual, y, d, p, stream, 0, 32);
         if (r == 0) r = launch_kwfuse(x, w_packed, scale, bias, residual, y, d, p, stream, 32, 32);
         if (r != 1) return r;

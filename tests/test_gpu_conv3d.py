@@ -151,6 +151,7 @@ def test_conv_kw_kd_fused_plane_march(monkeypatch):
     W = 40 / 14 -> 16), Cin 32 / 64, the 64 -> 64 output slices, every residual mode, ragged H / W edges, depths 1 and 2,
     and -- grid clamped -- several tile columns per CTA with depths that are not multiples of 5, so the accumulator
     ring wraps at every phase."""
+    monkeypatch.setenv("SNVC_CONV_MODE", "kw")
     monkeypatch.setenv("SNVC_CONV_MAXGRID", "2")
     _case(32, 32, 3, 1, 1, 1, False, (13, 10, 60), N=2, relu=True, residual_mode=1)
     _case(64, 32, 3, 1, 1, 1, False, (7, 16, 40), relu=True)
@@ -159,6 +160,29 @@ def test_conv_kw_kd_fused_plane_march(monkeypatch):
     _case(32, 32, 3, 1, 1, 1, False, (1, 8, 30))
     _case(64, 32, 3, 1, 1, 1, False, (2, 5, 33), residual_mode=1)
     _case(32, 32, 3, 1, 1, 1, False, (24, 4, 31), relu=True)
+
+
+def test_conv_cta_pair_plane_march(monkeypatch):
+    """v8 kernel (the default for 32-channel output slices): tcgen05.mma.cta_group::2 over a cluster of two CTAs, each
+    marching its own tile column with half of every weight slab; 14-block accumulator ring with two mirror blocks.
+    Depths beyond 14 (the ring and its mirrors wrap), an ODD number of tile columns (the last follower is a ghost),
+    all three row pitches (W = 60 -> 32, W = 40 -> 16, W = 124 -> 64), Cin 32 / 64, the 64 -> 64 output slices, every
+    residual mode, ragged edges, depth 1 / 2; first with the natural grid, then clamped to 1 and 2 pairs so that each
+    pair walks many columns."""
+    cases = [dict(a=(32, 32, 3, 1, 1, 1, False, (24, 4, 30)), k=dict(N=3, relu=True)),                     # 3 columns
+             dict(a=(32, 32, 3, 1, 1, 1, False, (17, 10, 60)), k=dict(N=2, relu=True, residual_mode=1)),
+             dict(a=(64, 32, 3, 1, 1, 1, False, (15, 16, 40)), k=dict(relu=True)),
+             dict(a=(64, 64, 3, 1, 1, 1, False, (6, 12, 44)), k=dict(relu=True, residual_mode=1)),
+             dict(a=(32, 32, 3, 1, 1, 1, False, (9, 9, 14)), k=dict(N=3, residual_mode=2, relu=True)),
+             dict(a=(64, 32, 3, 1, 1, 1, False, (30, 3, 124)), k=dict(relu=True, residual_mode=1)),
+             dict(a=(32, 32, 3, 1, 1, 1, False, (1, 8, 30)), k=dict()),
+             dict(a=(64, 32, 3, 1, 1, 1, False, (2, 5, 33)), k=dict(residual_mode=1))]
+    for c in cases[:3]:
+        _case(*c["a"], **c["k"])
+    for clamp in ("1", "2"):
+        monkeypatch.setenv("SNVC_CONV_MAXGRID", clamp)
+        for c in cases:
+            _case(*c["a"], **c["k"])
 
 
 def test_conv_kd_fused_kernel_still_green(monkeypatch):
