@@ -30,7 +30,12 @@ sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 PAIRS_PER_GPU = 8
 FEAT_C, FEAT_H, FEAT_W, DEPTH_BINS = 32, 96, 312, 48
 TRUNK_GFLOP_PER_PAIR = 491.90          # BASELINE.md section 3 (sum 2*k^3*Cin*Cout*V_out)
-CV_BYTES_PER_PAIR_BF16 = 191_692_992   # fp32 in -> bf16 NDHWC out
+CV_BYTES_PER_PAIR_BF16 = 191_692_992   # fp32 in -> bf16 NDHWC out (full 64-channel volume)
+# split form (the product path): features in, right-half volume + three left planes out
+CV_BYTES_PER_PAIR_SPLIT = 2 * FEAT_C * FEAT_H * FEAT_W * 4 + DEPTH_BINS * 4 + (DEPTH_BINS + 3) * FEAT_H * FEAT_W * FEAT_C * 2
+CONV1_GFLOP_FULL = 2 * 27 * 64 * 32 * DEPTH_BINS * FEAT_H * FEAT_W * 1e-9      # dres0.conv1 on 64 channels, per pair (159.0)
+CONV1_GFLOP_RIGHT = CONV1_GFLOP_FULL / 2                                        # its right-half launch (79.5)
+ADDEND_GFLOP = 2 * 27 * 32 * 32 * 3 * FEAT_H * FEAT_W * 1e-9                   # the 3-plane addend convolution (5.0)
 LIFT_VOX = 192 * 20 * 304
 
 
@@ -53,6 +58,8 @@ def workload_config(world, eager=False):
             "pairs_per_gpu_per_step": PAIRS_PER_GPU, "parallelism": f"pair-sharded x{world}, no collective",
             "launch": "eager (one Python launch per kernel)" if eager else
                       "CUDA-graph replay (GraphedHotPath, 4 stage graphs, inputs copied device-to-device per step)",
+            "cost_volume_form": "split (default): the depth-invariant left half of the 64-channel volume is kept as 3 planes "
+                                "and enters dres0.conv1 as an addend; SNVC_SPLIT_CV=0 materialises the full volume",
             "l2": "inputs rotate over 4 sets (245 MB) and each step streams >3 GB of intermediates; "
                   "both exceed the 126 MB L2"}
 
@@ -267,7 +274,7 @@ def run_ours(args, rank, world, local_rank):
                  torch.from_numpy(KITTI_P2[None].repeat(B, 0).copy()).pin_memory()) for _ in range(NH)]
         Z, Y, X = model.zs.numel(), model.ys.numel(), model.xs.numel()
         h_out = [torch.empty((B, Z, Y, X, 32), dtype=out_dtype).pin_memory() for _ in range(NH)]
-        pipe = HostPipeline(model, depth=2, out_dtype=out_dtype, layout_out=layout_out)
+        pipe = HostPipeline(model, depth=2, out_dtype=out_dtype, layout_out=layout_out, graphed=not args.eager)
         e2e_steps = max(4, min(K, 20))
         for i in range(3):
             pipe.submit(*h_in[i % NH], h_out[i % NH])
@@ -298,10 +305,14 @@ def run_ours(args, rank, world, local_rank):
         peaks = measured_peaks()
         pairs = world * B * K
         value = pairs / (elapsed_ms * 1e-3)
-        trunk_tflops = TRUNK_GFLOP_PER_PAIR * 1e-3 * B * K / (trunk_ms * 1e-3)
-        conv1_gflop = 2 * 27 * 64 * 32 * DEPTH_BINS * FEAT_H * FEAT_W * 1e-9      # dres0.conv1, per pair (159.0)
+        split = graphed is not None and graphed.split
+        # executed FLOPs: the split first layer convolves the depth-constant left half once (3 planes) instead of 48 times
+        trunk_gflop = TRUNK_GFLOP_PER_PAIR - (CONV1_GFLOP_FULL - CONV1_GFLOP_RIGHT) if split else TRUNK_GFLOP_PER_PAIR
+        trunk_tflops = trunk_gflop * 1e-3 * B * K / (trunk_ms * 1e-3)
+        conv1_gflop = CONV1_GFLOP_RIGHT if split else CONV1_GFLOP_FULL
         conv1_tflops = conv1_gflop * 1e-3 * B * K / (conv1_ms * 1e-3)
-        cv_gbs = CV_BYTES_PER_PAIR_BF16 * B * K / (cv_ms * 1e-3) / 1e9
+        cv_bytes = CV_BYTES_PER_PAIR_SPLIT if split else CV_BYTES_PER_PAIR_BF16
+        cv_gbs = cv_bytes * B * K / (cv_ms * 1e-3) / 1e9
         lift_gbs = lift_bytes_per_pair(2) * B * K / (lift_ms * 1e-3) / 1e9
         traffic = roofline_traffic()
         cpu_v, cpu_spp, cpu_threads = cpu_reference_pairs_per_s(2, 1) if world == 1 and not args.no_cpu_baseline \
@@ -316,19 +327,26 @@ def run_ours(args, rank, world, local_rank):
                     "h2d_bytes_per_step": int(2 * B * FEAT_C * FEAT_H * FEAT_W * 4 + B * DEPTH_BINS * 4 + B * 48),
                     "d2h_bytes_per_step": int(B * LIFT_VOX * 32 * 2), "steps": e2e_steps,
                     "api": "snvc_b200.models.stereonet.HostPipeline.submit (pinned host buffers; H2D / compute / D2H "
-                           "on three streams, 2 slots)"},
+                           "on three streams, 2 slots" + ("" if args.eager else ", one CUDA-graph replay per batch") + ")"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor",
-                         "kernel": "conv3d_kwfuse_kernel<4,128> (dres0.conv1 3x3x3 64->32, 1 launch / step)",
+                         "kernel": ("conv3d_kdpair_kernel<2,64,addend> (dres0.conv1 3x3x3 on the split cost volume: right half "
+                                    "32->32 + depth-invariant addend, 1 launch / step)") if split else
+                                   "conv3d_kdpair_kernel<4,128> (dres0.conv1 3x3x3 64->32, 1 launch / step)",
                          "achieved": conv1_tflops, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                          "frac": conv1_tflops / peaks["tf_sustained"],
-                         "traffic": traffic.get("dres0.conv1_dram_bytes_per_launch"),
+                         "traffic": traffic.get("dres0.conv1_split_dram_bytes_per_launch" if split else
+                                                "dres0.conv1_dram_bytes_per_launch"),
                          "algorithmic_flop_per_launch": conv1_gflop * 1e9 * B,
                          "peak_source": peaks["source"] + " (sustained bf16, kernel timed inside a long step)",
                          "share_of_step": conv1_ms / elapsed_ms},
-            "stages": {"cost_volume": {"ms_per_step": cv_ms / K, "achieved_gbs": cv_gbs, "frac_hbm": cv_gbs / peaks["hbm"]},
+            "stages": {"cost_volume": {"ms_per_step": cv_ms / K, "achieved_gbs": cv_gbs, "frac_hbm": cv_gbs / peaks["hbm"],
+                                       "bytes_per_pair": cv_bytes,
+                                       "form": "split: right-half volume + 3 left planes (+ the 3-plane addend conv, 5 GFLOP/pair)"
+                                               if split else "full 64-channel volume"},
                        "trunk": {"ms_per_step": trunk_ms / K, "achieved_tflops": trunk_tflops,
-                                 "frac_tensor": trunk_tflops / peaks["tf_sustained"], "share_of_step": trunk_ms / elapsed_ms},
+                                 "frac_tensor": trunk_tflops / peaks["tf_sustained"], "share_of_step": trunk_ms / elapsed_ms,
+                                 "executed_gflop_per_pair": trunk_gflop, "reference_gflop_per_pair": TRUNK_GFLOP_PER_PAIR},
                        "lift": {"ms_per_step": lift_ms / K, "achieved_gbs": lift_gbs, "frac_hbm": lift_gbs / peaks["hbm"]}},
         }
         if cpu_v is not None:

@@ -67,6 +67,16 @@ int snvc_cost_volume_fwd(const void* left, const void* right, const void* shift,
                          int64_t N, int64_t C, int64_t IH, int64_t IW, int64_t D, int32_t downsample,
                          int32_t dtype, int32_t out_dtype, int32_t out_layout, void* stream);
 
+/* A1, split form for the tcgen05 trunk (f32 in, bf16 NDHWC out).  The left half of the cost volume is a pure
+ * broadcast over depth (BuildCostVolume_cuda.cu:84-86: cost[n,c,d,ph,pw] = left[n,c,ih,iw]), so it is written ONCE:
+ * right_vol   : [N, D, IH/ds, IW/ds, C]  = channels [C, 2C) of the NDHWC volume above (the shifted right features)
+ * left_planes : [N, 3, IH/ds, IW/ds, C]  = the left features, channels-last bf16, on three identical planes -- the
+ *               input of the 3-plane convolution that yields the depth-invariant addend of snvc_conv3d_fwd_addend.
+ * Together they carry exactly the information of the [N,D,H,W,2C] volume; half the bytes are written. */
+int snvc_cost_volume_split_fwd(const void* left, const void* right, const void* shift, void* right_vol,
+                               void* left_planes, int64_t N, int64_t C, int64_t IH, int64_t IW, int64_t D,
+                               int32_t downsample, void* stream);
+
 /* A1b  cost volume, backward (deterministic, atomics-free).
  * Replaces build_cost_volume_backward(grad, shift, downsample)
  *   BuildCostVolume.cpp:29-43,47;  BuildCostVolume_cuda.cu:259-303 (host), :152-205 (kernel)
@@ -179,6 +189,16 @@ int snvc_conv3d_pack_weights(const float* w, void* w_packed, int32_t Cin, int32_
  * y = act( scale * conv(x) + bias [+ residual] ) [+ residual] */
 int snvc_conv3d_fwd(const void* x, const void* w_packed, const float* scale, const float* bias,
                     const void* residual, void* y, const snvc_conv3d_desc* desc, void* stream);
+/* Same, with a depth-invariant addend:  y = act( scale * (conv(x) + addend[n, v(d), h, w, :]) + bias ),
+ * v(d) = 0 for output plane d = 0, 2 for d = Do-1, 1 otherwise;  addend: fp32 [N, 3, Ho, Wo, Cout].
+ * This is how the first trunk layer (convbn_3d(2C, C) on the cost volume, submodule.py:32-50 applied to
+ * build_cost_volume's output) consumes the SPLIT cost volume: conv over all 2C channels = conv of the right half
+ * (x = right_vol, w = the [C, 2C) input-channel slice of the weights) + the convolution of the depth-constant left
+ * half, which is the same for every interior output plane and is computed once by a 3-plane snvc_conv3d_fwd
+ * (zero padding in depth gives plane 0 / 1 / 2 the tap sets of d = 0 / interior / D-1).  Exact algebra; only the
+ * fp32 summation order differs.  Supported: 3x3x3, stride 1, pad 1, Cin = Cout = 32, Di >= 2, no residual. */
+int snvc_conv3d_fwd_addend(const void* x, const void* w_packed, const float* scale, const float* bias,
+                           const float* addend, void* y, const snvc_conv3d_desc* desc, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * N1  projection of the instance sampling grid into the left / right ROI frames.

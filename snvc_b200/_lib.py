@@ -26,6 +26,7 @@ _SIGS = {
     "snvc_last_error": ([], ctypes.c_char_p),
     "snvc_launch_count": ([], _i64),
     "snvc_cost_volume_fwd": ([_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _p], _i32),
+    "snvc_cost_volume_split_fwd": ([_p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i32, _p], _i32),
     "snvc_cost_volume_bwd": ([_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _p], _i32),
     "snvc_cost_volume_xlow": ([_p, _p, _i64, _i64, _i64, _i32, _p], _i32),
     "snvc_roi_voxel_sample_workspace_bytes": ([_i64, _i64, _i64, _i64], _i64),
@@ -44,6 +45,7 @@ _SIGS = {
     "snvc_conv3d_packed_weight_bytes": ([_i32, _i32, _i32], _i64),
     "snvc_conv3d_pack_weights": ([_p, _p, _i32, _i32, _i32, _i32, _p], _i32),
     "snvc_conv3d_fwd": ([_p, _p, _p, _p, _p, _p, ctypes.POINTER(ConvDesc), _p], _i32),
+    "snvc_conv3d_fwd_addend": ([_p, _p, _p, _p, _p, _p, ctypes.POINTER(ConvDesc), _p], _i32),
     "snvc_ncdhw_f32_to_ndhwc_bf16": ([_p, _p, _i64, _i64, _i64, _p], _i32),
     "snvc_ndhwc_bf16_to_ncdhw_f32": ([_p, _p, _i64, _i64, _i64, _p], _i32),
     "snvc_scale_by_occupancy": ([_p, _p, _p, _i64, _i32, _i32, _i32, _p], _i32),

@@ -50,9 +50,11 @@ class PackedConv3d:
         return N, f(Di), f(Hi), f(Wi)
 
     def __call__(self, x, *, relu=False, residual=None, residual_mode=0, sigmoid=False, out_dtype=torch.bfloat16,
-                 out=None, out_coffset=0, res_coffset=0, in_coffset=0):
+                 out=None, out_coffset=0, res_coffset=0, in_coffset=0, addend=None):
         """x [N,D,H,W,Cin] bf16 -> y [N,Do,Ho,Wo,Cout] (or the channel slice [out_coffset, +Cout) of `out`).
-        `in_coffset` / `res_coffset` select channel slices of wider x / residual buffers."""
+        `in_coffset` / `res_coffset` select channel slices of wider x / residual buffers.
+        `addend` (fp32 [N,3,Ho,Wo,Cout]): depth-invariant term added to the accumulator before scale / bias
+        (snvc_conv3d_fwd_addend; plane 0 / 1 / 2 for output depth 0 / interior / last)."""
         _lib.require_cuda(x)
         if x.dtype != torch.bfloat16 or not x.is_contiguous() or x.shape[-1] < in_coffset + self.cin:
             raise RuntimeError(f"conv3d: x must be contiguous NDHWC bf16 with >= {in_coffset + self.cin} channels, "
@@ -76,6 +78,18 @@ class PackedConv3d:
                           out_cstride=out.shape[-1], out_coffset=out_coffset,
                           res_cstride=residual.shape[-1] if residual is not None else 0, res_coffset=res_coffset,
                           in_cstride=x.shape[-1], in_coffset=in_coffset)
+        if addend is not None:
+            if residual is not None or sigmoid:
+                raise RuntimeError("conv3d: addend cannot be combined with a residual or sigmoid")
+            if addend.dtype != torch.float32 or tuple(addend.shape) != (N, 3, Ho, Wo, self.cout) or not addend.is_contiguous():
+                raise RuntimeError(f"conv3d: addend must be contiguous fp32 [N,3,Ho,Wo,Cout], got {tuple(addend.shape)} {addend.dtype}")
+            with torch.cuda.device(x.device):
+                st = _lib.lib().snvc_conv3d_fwd_addend(x.data_ptr(), self.packed.data_ptr(),
+                                                       self.scale.data_ptr() if self.scale is not None else None,
+                                                       self.bias.data_ptr() if self.bias is not None else None,
+                                                       addend.data_ptr(), out.data_ptr(), ctypes.byref(d), _lib.stream_ptr())
+            _lib.check(st, "snvc_conv3d_fwd_addend")
+            return out
         with torch.cuda.device(x.device):
             st = _lib.lib().snvc_conv3d_fwd(x.data_ptr(), self.packed.data_ptr(),
                                             self.scale.data_ptr() if self.scale is not None else None,

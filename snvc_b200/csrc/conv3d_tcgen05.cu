@@ -25,6 +25,8 @@
 #include <algorithm>
 #include <cstdlib>
 #include <mutex>
+#include <tuple>
+#include <vector>
 
 #include "common.cuh"
 
@@ -551,6 +553,7 @@ struct HaloParams {
   int tma_store, stage_bytes;  // staged epilogue (kd-fused kernel): two swizzled output tiles of stage_bytes each
   const float* scale;
   const float* bias;
+  const float* addend;         // v8 only: fp32 [N,3,H,W,Cout] added to the accumulator (first / interior / last plane)
   EpiParams epi;
 };
 
@@ -1373,7 +1376,11 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
 // did not fit the uniform register file; ptxas built them in vector registers and moved them over with R2UR, ~20
 // instructions and 70-90 cycles per UTCHMMA.2CTA -- more than the 51-cycle MMA itself (first version: 32->32 layers
 // 620 us, slower than v7).
-template <int KSTEPS, int SUBROW, bool RES, int WPT>
+// ADD: a per-(h, w, channel) fp32 addend joins the accumulator before scale / bias -- the contribution of input
+// channels that do not vary with depth (the left half of the plane-sweep cost volume), computed once as a 3-plane
+// convolution: plane 0 / 1 / 2 of `addend` = the sums an output plane at depth 0 / interior / D-1 needs (the depth
+// padding removes one kd tap at either end).  The interior rows stay in registers for the whole column.
+template <int KSTEPS, int SUBROW, bool RES, int WPT, bool ADD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 conv3d_kdpair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                      const __grid_constant__ HaloParams p) {
@@ -1535,7 +1542,22 @@ conv3d_kdpair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     PairRing rg{0u, 0u};
     uint32_t par = 0;
     const bool out_f32 = p.epi.out_f32 != 0;
+    uint4 rqn[4];
+    bool have_next = false;
+    auto load_res = [&](uint4 (&r)[4], bool on, int64_t v) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) r[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (on) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.epi.residual + v * p.epi.res_cstride + p.epi.res_coffset);
+        if (aligned32(rp)) { ldg256(rp, r[0], r[1]); ldg256(rp + 2, r[2], r[3]); }
+        else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) r[i] = __ldg(rp + i);
+        }
+      }
+    };
     for (int q = pair0; q < npairs; q += pstep) {
+      have_next = false;
       const int col = 2 * q + (int)rank;
       const bool ghost = col >= p.num_cols;               // odd column count: the last follower's results are dropped
       const int colc = ghost ? p.num_cols - 1 : col;
@@ -1544,19 +1566,34 @@ conv3d_kdpair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
       const int ow = tw * p.TWv + r_w, oh = th * p.TH + r_h;
       const bool in_range = !ghost && r_w < p.TWv && ow < p.W && oh < p.H;
       int64_t vox = (((int64_t)n * p.D) * p.H + oh) * p.W + ow - plane_vox;       // accumulator plane a <-> output plane a - 1
+      float addm[ADD ? CP : 1];
+      const float* arow = nullptr;                        // this thread's row of addend plane 0 (planes are plane_vox*CP apart)
+      if (ADD) {
+        arow = p.addend + ((((int64_t)n * 3) * p.H + oh) * p.W + ow) * CP;
+#pragma unroll
+        for (int j = 0; j < CP; j += 4) {
+          const float4 t = in_range ? __ldg(reinterpret_cast<const float4*>(arow + plane_vox * CP + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          addm[j] = t.x; addm[j + 1] = t.y; addm[j + 2] = t.z; addm[j + 3] = t.w;
+        }
+      }
       for (uint32_t a = 0; a < acc_per_col; ++a, vox += plane_vox, rg = pr_next(rg), par ^= 1u) {
         if (par != grp) continue;
         const bool real = a >= 1u && a <= (uint32_t)p.D;
+        // residual rows: fetched one plane of this group AHEAD (plane a + 2), so that their HBM / L2 latency is covered
+        // by a whole plane of MMAs (fetched just before the wait they cost the residual layer 130 us of 580)
         uint4 rq[4];
+        if (RES) {
+          if (have_next) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) rq[i] = make_uint4(0u, 0u, 0u, 0u);
-        if (RES && in_range && real) {                    // issued before the wait: overlaps the MMAs of this plane
-          const uint4* rp = reinterpret_cast<const uint4*>(p.epi.residual + vox * p.epi.res_cstride + p.epi.res_coffset);
-          if (aligned32(rp)) { ldg256(rp, rq[0], rq[1]); ldg256(rp + 2, rq[2], rq[3]); }
-          else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) rq[i] = __ldg(rp + i);
+            for (int i = 0; i < 4; ++i) rq[i] = rqn[i];
+          } else {
+            load_res(rq, in_range && real, vox);
           }
+          have_next = a + 2u < acc_per_col;
+          if (have_next) load_res(rqn, in_range && a + 2u <= (uint32_t)p.D, vox + 2 * plane_vox);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) rq[i] = make_uint4(0u, 0u, 0u, 0u);
         }
         mbar_wait(smem_u32(&acc_full_bar[rg.i]), rg.ph);
         tcgen05_fence_after();
@@ -1576,6 +1613,19 @@ conv3d_kdpair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
               for (int j = 0; j < 16; ++j) q0[j] = __float_as_uint(__uint_as_float(q0[j]) + __uint_as_float(q1[j]));
             } else {
               tmem_ld_wait();
+            }
+            if (ADD) {
+              const bool edge = a == 1u || a == (uint32_t)p.D;         // output plane 0 / D-1: their own addend planes
+              const float* ep = arow + (a == 1u ? 0 : 2 * plane_vox * CP) + c0;
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                float4 t = make_float4(addm[c0 + j], addm[c0 + j + 1], addm[c0 + j + 2], addm[c0 + j + 3]);
+                if (edge) t = in_range ? __ldg(reinterpret_cast<const float4*>(ep + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                q0[j] = __float_as_uint(__uint_as_float(q0[j]) + t.x);
+                q0[j + 1] = __float_as_uint(__uint_as_float(q0[j + 1]) + t.y);
+                q0[j + 2] = __float_as_uint(__uint_as_float(q0[j + 2]) + t.z);
+                q0[j + 3] = __float_as_uint(__uint_as_float(q0[j + 3]) + t.w);
+              }
             }
             float v[16];
 #pragma unroll
@@ -2796,9 +2846,10 @@ int launch_halo(const void* x, const void* w_packed, const float* scale, const f
 // Eligible: 3x3x3, stride 1, dilation 1, "same" padding, a 32-channel output (slice) on the lean epilogue path.
 int launch_kdpair(const void* x, const void* w_packed, const float* scale, const float* bias, const void* residual,
                   void* y, const snvc_conv3d_desc& d, const ConvParams& cp_full, cudaStream_t stream, int cout0 = 0,
-                  int ncout = 0) {
+                  int ncout = 0, const float* addend = nullptr) {
   const char* mode = getenv("SNVC_CONV_MODE");
-  if (mode && (mode[0] == 'h' || mode[0] == 'k')) return 1;            // SNVC_CONV_MODE=kw / kd / halo: v7 / v3 / v2 (A/B runs)
+  if (!addend && mode && (mode[0] == 'h' || mode[0] == 'k')) return 1;  // SNVC_CONV_MODE=kw / kd / halo: v7 / v3 / v2 (A/B runs)
+  if (addend && (d.Cin != 32 || cp_full.residual_mode || ncout > 0 || d.Di < 2)) return 1;
   ConvParams cp = cp_full;
   if (ncout > 0) {
     cp.Cout = ncout; cp.CoutPad = round_up(ncout, 16);
@@ -2816,7 +2867,7 @@ int launch_kdpair(const void* x, const void* w_packed, const float* scale, const
   HaloParams p{};
   p.N = d.N; p.Cin = d.Cin; p.D = d.Di; p.H = d.Hi; p.W = d.Wi;
   p.K = 3; p.dil = 1; p.pad = 1;
-  p.scale = scale; p.bias = bias;
+  p.scale = scale; p.bias = bias; p.addend = addend;
   p.epi.Cout = cp.Cout; p.epi.CoutPad = cp.CoutPad; p.epi.relu = cp.relu; p.epi.residual_mode = cp.residual_mode;
   p.epi.sigmoid = 0; p.epi.out_f32 = cp.out_f32; p.epi.out_cstride = cp.out_cstride;
   p.epi.out_coffset = cp.out_coffset; p.epi.res_cstride = cp.res_cstride; p.epi.res_coffset = cp.res_coffset;
@@ -2870,13 +2921,38 @@ int launch_kdpair(const void* x, const void* w_packed, const float* scale, const
     if (r != CUDA_SUCCESS) return fail((int)r, "cuTensorMapEncodeTiled(w, kdpair) failed with CUresult %d", (int)r);
   }
   void (*kern)(const CUtensorMap, const CUtensorMap, const HaloParams) = nullptr;
-#define SNVC_PAIR_W(KS, SR, RS)                                                                                   \
-  (p.WP == 16 ? conv3d_kdpair_kernel<KS, SR, RS, 16> : (p.WP == 32 ? conv3d_kdpair_kernel<KS, SR, RS, 32> : conv3d_kdpair_kernel<KS, SR, RS, 64>))
-  if (d.Cin == 32) kern = cp.residual_mode ? SNVC_PAIR_W(2, 64, true) : SNVC_PAIR_W(2, 64, false);
-  else kern = cp.residual_mode ? SNVC_PAIR_W(4, 128, true) : SNVC_PAIR_W(4, 128, false);
+#define SNVC_PAIR_W(KS, SR, RS, AD)                                                                               \
+  (p.WP == 16 ? conv3d_kdpair_kernel<KS, SR, RS, 16, AD>                                                          \
+              : (p.WP == 32 ? conv3d_kdpair_kernel<KS, SR, RS, 32, AD> : conv3d_kdpair_kernel<KS, SR, RS, 64, AD>))
+  if (addend) kern = SNVC_PAIR_W(2, 64, false, true);
+  else if (d.Cin == 32) kern = cp.residual_mode ? SNVC_PAIR_W(2, 64, true, false) : SNVC_PAIR_W(2, 64, false, false);
+  else kern = cp.residual_mode ? SNVC_PAIR_W(4, 128, true, false) : SNVC_PAIR_W(4, 128, false, false);
 #undef SNVC_PAIR_W
   SNVC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int pairs = std::min((p.num_cols + 1) / 2, sm_count() / 2);
+  // how many CTA pairs the device can hold at once for this kernel / shared-memory size (cached: the query is slow);
+  // a device that cannot co-schedule a pair (MIG slice, SM count 1) falls back to the single-CTA kernels
+  static std::mutex mu;
+  static std::vector<std::tuple<const void*, size_t, int, int>> cache;   // (kernel, smem, device, clusters)
+  int dev = 0, max_clusters = -1;
+  SNVC_CUDA_OK(cudaGetDevice(&dev));
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto& e : cache)
+      if (std::get<0>(e) == (const void*)kern && std::get<1>(e) == smem && std::get<2>(e) == dev) max_clusters = std::get<3>(e);
+    if (max_clusters < 0) {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(2 * (sm_count() / 2)); cfg.blockDim = dim3(kPairThreads); cfg.dynamicSmemBytes = smem;
+      cudaLaunchAttribute at{};
+      at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+      cfg.attrs = &at; cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, (const void*)kern, &cfg) != cudaSuccess) { n = 0; (void)cudaGetLastError(); }
+      max_clusters = n;
+      cache.emplace_back((const void*)kern, smem, dev, n);
+    }
+  }
+  if (max_clusters < 1) return 1;
+  int pairs = std::min((p.num_cols + 1) / 2, max_clusters);
   if (const char* mg = getenv("SNVC_CONV_MAXGRID")) pairs = std::max(1, std::min(pairs, atoi(mg)));   // tests: force ring wrap-around
   kern<<<2 * pairs, kPairThreads, smem, stream>>>(map_x, map_w, p);
   return launch_status("conv3d_kdpair_kernel");
@@ -3250,8 +3326,22 @@ extern "C" int snvc_conv3d_pack_weights(const float* w, void* w_packed, int32_t 
   return launch_status("pack_weights_kernel");
 }
 
+static int conv3d_fwd_impl(const void* x, const void* w_packed, const float* scale, const float* bias, const void* residual,
+                          const float* addend, void* y, const snvc_conv3d_desc* dp, void* stream_);
+
 extern "C" int snvc_conv3d_fwd(const void* x, const void* w_packed, const float* scale, const float* bias,
                                const void* residual, void* y, const snvc_conv3d_desc* dp, void* stream_) {
+  return conv3d_fwd_impl(x, w_packed, scale, bias, residual, nullptr, y, dp, stream_);
+}
+
+extern "C" int snvc_conv3d_fwd_addend(const void* x, const void* w_packed, const float* scale, const float* bias,
+                                      const float* addend, void* y, const snvc_conv3d_desc* dp, void* stream_) {
+  SNVC_CHECK_ARG(addend != nullptr && (reinterpret_cast<uintptr_t>(addend) & 15) == 0, "addend must be a 16-byte aligned pointer");
+  return conv3d_fwd_impl(x, w_packed, scale, bias, nullptr, addend, y, dp, stream_);
+}
+
+static int conv3d_fwd_impl(const void* x, const void* w_packed, const float* scale, const float* bias, const void* residual,
+                           const float* addend, void* y, const snvc_conv3d_desc* dp, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   SNVC_CHECK_ARG(dp != nullptr, "desc is null");
   const snvc_conv3d_desc& d = *dp;
@@ -3305,6 +3395,12 @@ extern "C" int snvc_conv3d_fwd(const void* x, const void* w_packed, const float*
     // measured on B200, UMMA swizzles on absolute smem address bits, so row-shifted windows of a
     // TMA-written tile need no base-offset correction (base offset = (addr>>7)&7 gives wrong results).
     const char* mode = getenv("SNVC_CONV_MODE");
+    if (addend) {
+      // depth-invariant addend: implemented by the CTA-pair kernel only (3x3x3 s1, Cin = Cout = 32, D >= 2, no residual)
+      const int r = launch_kdpair(x, w_packed, scale, bias, nullptr, y, d, p, stream, 0, 0, addend);
+      if (r == 1) return fail(SNVC_E_UNSUPPORTED, "snvc_conv3d_fwd_addend: needs a 3x3x3 stride-1 conv with Cin = Cout = 32, D >= 2");
+      return r;
+    }
     if (!(mode && mode[0] == 't')) {
       int r = launch_s2(x, w_packed, scale, bias, residual, y, d, p, stream);
       if (r != 1) return r;
@@ -3334,6 +3430,7 @@ extern "C" int snvc_conv3d_fwd(const void* x, const void* w_packed, const float*
     return launch_conv(x, w_packed, scale, bias, residual, y, d, p, stream);
   }
 
+  if (addend) return fail(SNVC_E_UNSUPPORTED, "snvc_conv3d_fwd_addend: transposed convolutions are not supported");
   // ConvTranspose3d(k=3, s=2, p=1, output_padding=1): out[o] += x[i] * W[k], o = 2i - 1 + k.
   //   even o = 2j   : k=1, i=j
   //   odd  o = 2j+1 : k=2, i=j   and   k=0, i=j+1

@@ -165,7 +165,8 @@ __device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src)
 // Staging uses 4-byte cp.async (no register round trip, all loads in flight at once).
 __global__ void __launch_bounds__(512)
 cv_ndhwc_bf16_kernel(const float* __restrict__ left, const float* __restrict__ right,
-                     const float* __restrict__ shift, __nv_bfloat16* __restrict__ cost, int C, int img_h,
+                     const float* __restrict__ shift, __nv_bfloat16* __restrict__ cost,
+                     __nv_bfloat16* __restrict__ left_planes /* split form: [N,3,H,W,C], else nullptr */, int C, int img_h,
                      int img_w, int D, int H, int W, int ds, int d_per_cta, int n_dsplit, int TW, int S, int mask) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int ph = blockIdx.x;
@@ -200,11 +201,27 @@ cv_ndhwc_bf16_kernel(const float* __restrict__ left, const float* __restrict__ r
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
   for (int i = threadIdx.x; i < dn; i += blockDim.x) sS[i] = -shift[(int64_t)n * D + d0 + i];
+  // Sample positions of every (column, bin) of this CTA, computed ONCE: x_low / x_high / lx depend on the column and
+  // the bin only, but the C/8 lanes of a column each recomputed them per bin (~10 of the ~21 instructions per lane and
+  // bin; with the left half gone the kernel was issue-bound at 48 % of the HBM peak).  Entry = {code, lx}; code = -1
+  // outside the image, else x_low | (x_high != x_low) << 30.
+  int2* sT = reinterpret_cast<int2*>(sS + ((d_per_cta + 1) & ~1));
+  for (int i = threadIdx.x; i < dn * tw; i += blockDim.x) {
+    const int dd = i / tw, wl = i - dd * tw;
+    int xl, xh;
+    float lx;
+    const bool ok = sample_pos<float>((pw0 + wl) * ds, -shift[(int64_t)n * D + d0 + dd], img_w, xl, xh, lx);
+    sT[i] = make_int2(ok ? (xl | (xh != xl ? 0x40000000 : 0)) : -1, __float_as_int(lx));
+  }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
   const int CG = C >> 3;                // 8-channel groups per view
-  const int C2 = 2 * C;
+  // split form (snvc_cost_volume_split_fwd): the volume holds the right half only (C channels per voxel) and the
+  // left half -- a pure broadcast over depth, BuildCostVolume_cuda.cu:84-86 -- is written once, as three planes
+  const bool split = left_planes != nullptr;
+  const int C2 = split ? C : 2 * C;
+  const int roff = split ? 0 : C;
   const int64_t dstride = (int64_t)H * W * C2;
   for (int pair = threadIdx.x; pair < tw * CG; pair += blockDim.x) {
     const int wl = pair / CG, cg = pair - wl * CG;
@@ -222,12 +239,18 @@ cv_ndhwc_bf16_kernel(const float* __restrict__ left, const float* __restrict__ r
     // and 0 or 2 instead of 4 LDS.128 are needed -- the shared-memory pipe, not HBM, was the busiest unit (ncu: 88 %).
     int cur_xl = -0x40000000, cur_xh = -0x40000000;
     float r0[8], r1[8];
+    if (split && dsplit == 0) {
+      __nv_bfloat16* lo = left_planes + ((((int64_t)n * 3) * H + ph) * W + pw) * C + cg * 8;
+#pragma unroll
+      for (int v = 0; v < 3; ++v) *reinterpret_cast<uint4*>(lo + (int64_t)v * H * W * C) = vl;
+    }
     for (int dd = 0; dd < dn; ++dd, o += dstride) {
-      *reinterpret_cast<uint4*>(o) = vl;                       // left half: broadcast over depth
-      int xl, xh;
-      float lx;
+      if (!split) *reinterpret_cast<uint4*>(o) = vl;           // left half: broadcast over depth
+      const int2 te = sT[dd * tw + wl];
+      const int xl = te.x & 0x3fffffff, xh = xl + ((te.x >> 30) & 1);
+      const float lx = __int_as_float(te.y);
       uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (sample_pos<float>(iw, sS[dd], img_w, xl, xh, lx)) {  // right half: 1-D interpolation along the row
+      if (te.x >= 0) {                                         // right half: 1-D interpolation along the row
         if (xl >= rlo) {
           if (xl != cur_xl || xh != cur_xh) {
             if (xl == cur_xh) {
@@ -263,7 +286,118 @@ cv_ndhwc_bf16_kernel(const float* __restrict__ left, const float* __restrict__ r
         for (int j = 0; j < 8; ++j) r[j] = __fmaf_rn(lx, r1[j], __fmul_rn(hx, r0[j]));
         v = make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7]));
       }
-      *reinterpret_cast<uint4*>(o + C) = v;
+      *reinterpret_cast<uint4*>(o + roff) = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Split form (snvc_cost_volume_split_fwd), whole rows in shared memory.  ncu on the kernel above in split mode: 248 M
+// warp instructions for 0.84 GB (issue slots 83 % busy, 48 % of the HBM peak) -- a lane owns a (column, 8 channels)
+// and walks the depth bins, so for every bin it re-derives which two right-image columns it needs, compares them with
+// the ones it holds, and re-loads or moves 16 registers on one of several paths.
+// Here a lane owns a (depth bin, 8 channels) and walks a STRIP of consecutive columns: for a fixed bin the sample
+// position advances by exactly one column per step, so the "high" sample of one step is the "low" sample of the
+// next and each step costs ONE shared-memory column (2 LDS.128), 8 FMUL + 8 FFMA, 4 packs and a 16-byte store.  The
+// per-(bin, column) positions (x_low, x_high, lx -- fp32 arithmetic in the reference's order, so the result stays
+// bit-identical) come from a table built once per CTA; the left planes are written by the CTAs of the first depth
+// split.  grid = (H, N, depth splits).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512)
+cv_split_bf16_kernel(const float* __restrict__ left, const float* __restrict__ right, const float* __restrict__ shift,
+                     __nv_bfloat16* __restrict__ right_vol, __nv_bfloat16* __restrict__ left_planes, int C, int img_h,
+                     int img_w, int D, int H, int W, int ds, int d_per_cta, int mask) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int ph = blockIdx.x, n = blockIdx.y, dsplit = blockIdx.z;
+  const int d0 = dsplit * d_per_cta;
+  const int dn = min(d_per_cta, D - d0);
+  if (dn <= 0) return;
+  const int lw = (W - 1) * ds + 1;                      // left columns [0, lw) (only staged by the first depth split)
+  const bool do_left = dsplit == 0;
+  float* sR = reinterpret_cast<float*>(smem_raw);       // [img_w][C], 16-byte chunks XOR-swizzled by column
+  float* sL = sR + (size_t)img_w * C;                   // [lw][C]
+  int2* sT = reinterpret_cast<int2*>(sL + (size_t)lw * C);   // [dn][W]: {code, lx}
+  const int ih = ph * ds;
+  const int64_t cstride = (int64_t)img_h * img_w;
+  const float* rrow = right + ((int64_t)n * C * img_h + ih) * img_w;
+  const float* lrow = left + ((int64_t)n * C * img_h + ih) * img_w;
+  // staging: a warp takes one channel at a time and runs along the row (coalesced 4-byte cp.async, no divisions)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  for (int c = warp; c < C; c += nwarp) {
+    for (int col = lane; col < img_w; col += 32) cp_async_4(&sR[swz(col, c, C, mask)], rrow + c * cstride + col);
+    if (do_left)
+      for (int col = lane; col < lw; col += 32) cp_async_4(&sL[swz(col, c, C, mask)], lrow + c * cstride + col);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int dd = warp; dd < dn; dd += nwarp) {
+    const float ns = -shift[(int64_t)n * D + d0 + dd];
+    for (int pw = lane; pw < W; pw += 32) {
+      int xl, xh;
+      float lx;
+      const bool ok = sample_pos<float>(pw * ds, ns, img_w, xl, xh, lx);
+      sT[dd * W + pw] = make_int2(ok ? (xl | (xh != xl ? 0x40000000 : 0)) : -1, __float_as_int(lx));
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  const int CG = C >> 3;                                // 8-channel groups
+  if (do_left) {                                        // left half: three identical planes, written once per row
+    for (int i = threadIdx.x; i < W * CG; i += blockDim.x) {
+      const int pw = i / CG, cg = i - pw * CG;
+      const int col = pw * ds;
+      const float4 a = *chunk_ptr(sL, col, 2 * cg, C, mask);
+      const float4 b = *chunk_ptr(sL, col, 2 * cg + 1, C, mask);
+      const uint4 vl = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+      __nv_bfloat16* lo = left_planes + ((((int64_t)n * 3) * H + ph) * W + pw) * C + cg * 8;
+#pragma unroll
+      for (int v = 0; v < 3; ++v) *reinterpret_cast<uint4*>(lo + (int64_t)v * H * W * C) = vl;
+    }
+  }
+  // right half: item = (bin, strip, channel group); the CG lanes of an item's pixel are adjacent (64-byte segments)
+  const int nstrips = max(1, (int)blockDim.x / (dn * CG));
+  // odd strip length: the 8 lane groups of a warp then sit on columns with 8 different (col & 7), i.e. 8 different
+  // swizzle phases -> every LDS.128 is served in the minimum 4 wavefronts (an even length -- 26 for KITTI -- measured
+  // 27 M bank conflicts per launch, L1 data pipe 85 % busy)
+  const int L = ((W + nstrips - 1) / nstrips) | 1;
+  const int items = dn * nstrips * CG;
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+    const int cg = it % CG;
+    const int t2 = it / CG;
+    const int strip = t2 % nstrips, dd = t2 / nstrips;
+    const int w_begin = strip * L, w_end = min(W, w_begin + L);
+    const int2* tab = sT + dd * W;
+    __nv_bfloat16* o = right_vol + ((((int64_t)n * D + d0 + dd) * H + ph) * W + w_begin) * C + cg * 8;
+    int cur_xh = -0x40000000;                           // column held in r1[]
+    float r0[8], r1[8];
+    for (int pw = w_begin; pw < w_end; ++pw, o += C) {
+      const int2 te = tab[pw];
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (te.x >= 0) {
+        const int xl = te.x & 0x3fffffff, xh = xl + ((te.x >> 30) & 1);
+        const float lx = __int_as_float(te.y);
+        if (xl == cur_xh) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r0[j] = r1[j];
+        } else {
+          *reinterpret_cast<float4*>(r0) = *chunk_ptr(sR, xl, 2 * cg, C, mask);
+          *reinterpret_cast<float4*>(r0 + 4) = *chunk_ptr(sR, xl, 2 * cg + 1, C, mask);
+        }
+        if (xh == xl) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r1[j] = r0[j];
+        } else {
+          *reinterpret_cast<float4*>(r1) = *chunk_ptr(sR, xh, 2 * cg, C, mask);
+          *reinterpret_cast<float4*>(r1 + 4) = *chunk_ptr(sR, xh, 2 * cg + 1, C, mask);
+        }
+        cur_xh = xh;
+        const float hx = __fsub_rn(1.f, lx);
+        float r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = __fmaf_rn(lx, r1[j], __fmul_rn(hx, r0[j]));
+        v = make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7]));
+      }
+      *reinterpret_cast<uint4*>(o) = v;
     }
   }
 }
@@ -333,6 +467,9 @@ __global__ void cv_xlow_kernel(const float* __restrict__ shift, int32_t* __restr
   }
 }
 
+int launch_cv_ndhwc(const void* left, const void* right, const void* shift, void* cost, void* left_planes, int64_t N,
+                    int64_t C, int64_t IH, int64_t IW, int64_t D, int ds, int64_t H, int64_t W, cudaStream_t stream);
+
 }  // namespace
 }  // namespace snvc
 
@@ -389,14 +526,57 @@ extern "C" int snvc_cost_volume_fwd(const void* left, const void* right, const v
   if (out_layout == SNVC_NDHWC) {
     if (!(dtype == SNVC_F32 && out_dtype == SNVC_BF16))
       return fail(SNVC_E_UNSUPPORTED, "NDHWC cost volume: supported types are f32 -> bf16");
-    SNVC_CHECK_ARG(C % 8 == 0, "NDHWC cost volume needs C %% 8 == 0 (got %lld)", (long long)C);
+    return launch_cv_ndhwc(left, right, shift, cost, nullptr, N, C, IH, IW, D, ds, H, W, stream);
+  }
+  return fail(SNVC_E_BADARG, "unknown out_layout %d", out_layout);
+}
+
+namespace snvc {
+namespace {
+int launch_cv_ndhwc(const void* left, const void* right, const void* shift, void* cost, void* left_planes, int64_t N,
+                    int64_t C, int64_t IH, int64_t IW, int64_t D, int ds, int64_t H, int64_t W, cudaStream_t stream) {
+  SNVC_CHECK_ARG(C % 8 == 0, "NDHWC cost volume needs C %% 8 == 0 (got %lld)", (long long)C);
+  if (left_planes && H <= 2147483647ll && N <= 65535 && !getenv("SNVC_CV_SPLIT_OLD")) {
+    // split form, whole rows staged: [img_w + (W-1)*ds+1 columns][C] fp32 + the sample table of one depth split
+    const size_t rows = ((size_t)IW + (size_t)((W - 1) * ds + 1)) * C * 4;
+    const size_t budget = 112 * 1024;                                   // two CTAs per SM
+    if (rows + (size_t)W * 8 <= 225 * 1024) {
+      int d_per = (int)D;
+      if (rows + (size_t)W * D * 8 > budget) d_per = (int)std::max<int64_t>(1, ((int64_t)std::max<size_t>(budget, rows + W * 8) - (int64_t)rows) / (W * 8));
+      // fill whole waves: more depth splits when the grid would leave SMs idle
+      const double wave = 2.0 * sm_count();
+      double best = -1;
+      int pick = (int)ceil_div(D, d_per);
+      for (int cand = (int)ceil_div(D, d_per); cand <= std::min<int64_t>(D, ceil_div(D, d_per) + 6); ++cand) {
+        const double x = (double)H * N * ceil_div(D, ceil_div(D, cand)) / wave;
+        const double eff = x / ceil(x) - 0.01 * cand;
+        if (eff > best + 1e-9) { best = eff; pick = cand; }
+      }
+      d_per = (int)ceil_div(D, pick);
+      const int dsplit = (int)ceil_div(D, d_per);
+      if (dsplit <= 65535) {
+        const size_t smem = rows + (size_t)W * d_per * 8;
+        if (smem > 48 * 1024)
+          SNVC_CUDA_OK(cudaFuncSetAttribute(cv_split_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int mask = 1;  // largest 2^k - 1 (k <= 3) with 2^k | C/4
+        while (mask < 7 && ((C / 4) % (2 * (mask + 1))) == 0) mask = 2 * mask + 1;
+        dim3 grid((unsigned)H, (unsigned)N, (unsigned)dsplit);
+        cv_split_bf16_kernel<<<grid, 512, smem, stream>>>((const float*)left, (const float*)right, (const float*)shift,
+                                                           (__nv_bfloat16*)cost, (__nv_bfloat16*)left_planes, (int)C, (int)IH,
+                                                           (int)IW, (int)D, (int)H, (int)W, ds, d_per, mask);
+        return launch_status("cv_split_bf16_kernel");
+      }
+    }
+  }
+  {
     SNVC_CHECK_ARG((reinterpret_cast<uintptr_t>(cost) & 15) == 0, "cost must be 16-byte aligned");
     SNVC_CHECK_ARG(H <= 2147483647ll && N <= 65535, "H/N too large");
     // w-tiling: whole row when it fits (KITTI 1/4-res: 2*312*32*4 = 78 KB -> 2 CTAs/SM)
     const size_t budget = 100 * 1024, hard = 200 * 1024;
     int TW = (int)W, S = 0;
     size_t row_bytes = (size_t)C * 4;
-    auto need = [&](int tw, int s) { return ((size_t)((tw - 1) * ds + 1) + (size_t)((tw - 1) * ds + 2 + s)) * row_bytes + (size_t)D * 4; };
+    // staged rows + the shifts (the per-(column, bin) sample table, 8 bytes per entry, is added once the depth split is known)
+    auto need = [&](int tw, int s) { return ((size_t)((tw - 1) * ds + 1) + (size_t)((tw - 1) * ds + 2 + s)) * row_bytes + (size_t)(D + 2) * 4; };
     if (need(TW, 0) > budget) {
       int ntile = 2;
       while (need((int)ceil_div(W, ntile), 0) > budget / 2 && ntile < W) ++ntile;
@@ -419,19 +599,37 @@ extern "C" int snvc_cost_volume_fwd(const void* left, const void* right, const v
       if (eff > best_eff + 1e-9) { best_eff = eff; dsplit = cand; }
     }
     int d_per = (int)ceil_div(D, dsplit);
+    // the sample table must fit next to the staged rows: split the depth further if it does not
+    while (d_per > 1 && smem + (size_t)TW * d_per * 8 > 225 * 1024) d_per = (d_per + 1) / 2;
     dsplit = (int)ceil_div(D, d_per);
+    smem += (size_t)TW * d_per * 8;
     SNVC_CHECK_ARG((int64_t)dsplit * wtiles <= 65535, "grid.z too large");
+    if (smem > 225 * 1024) return fail(SNVC_E_UNSUPPORTED, "cost volume tile does not fit shared memory");
     if (smem > 48 * 1024)
       SNVC_CUDA_OK(cudaFuncSetAttribute(cv_ndhwc_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int mask = 1;  // largest 2^k - 1 (k <= 3) with 2^k | C/4
     while (mask < 7 && ((C / 4) % (2 * (mask + 1))) == 0) mask = 2 * mask + 1;
     dim3 grid((unsigned)H, (unsigned)N, (unsigned)(dsplit * wtiles));
     cv_ndhwc_bf16_kernel<<<grid, 512, smem, stream>>>((const float*)left, (const float*)right, (const float*)shift,
-                                                       (__nv_bfloat16*)cost, (int)C, (int)IH, (int)IW, (int)D, (int)H,
-                                                       (int)W, ds, d_per, dsplit, TW, S, mask);
+                                                       (__nv_bfloat16*)cost, (__nv_bfloat16*)left_planes, (int)C, (int)IH,
+                                                       (int)IW, (int)D, (int)H, (int)W, ds, d_per, dsplit, TW, S, mask);
     return launch_status("cv_ndhwc_bf16_kernel");
   }
-  return fail(SNVC_E_BADARG, "unknown out_layout %d", out_layout);
+}
+}  // namespace
+}  // namespace snvc
+
+extern "C" int snvc_cost_volume_split_fwd(const void* left, const void* right, const void* shift, void* right_vol,
+                                          void* left_planes, int64_t N, int64_t C, int64_t IH, int64_t IW, int64_t D,
+                                          int32_t ds, void* stream_) {
+  SNVC_CHECK_ARG(ds >= 1, "downsample must be >= 1");
+  SNVC_CHECK_ARG(N >= 0 && C > 0 && IH >= 0 && IW >= 0 && D >= 0, "negative dimension");
+  SNVC_CHECK_ARG(IH % ds == 0 && IW % ds == 0, "IH and IW must be multiples of downsample");
+  const int64_t H = IH / ds, W = IW / ds;
+  if (N * C * D * H * W == 0) return 0;
+  SNVC_CHECK_ARG(left && right && shift && right_vol && left_planes, "null pointer");
+  SNVC_CHECK_ARG((reinterpret_cast<uintptr_t>(left_planes) & 15) == 0, "left_planes must be 16-byte aligned");
+  return launch_cv_ndhwc(left, right, shift, right_vol, left_planes, N, C, IH, IW, D, ds, H, W, (cudaStream_t)stream_);
 }
 
 extern "C" int snvc_cost_volume_bwd(const void* grad, const void* shift, void* grad_left, void* grad_right, int64_t N,

@@ -87,6 +87,29 @@ def build_cost_volume_ndhwc_bf16(left, right, shift, downsample=1):
     return _forward(left, right, shift, downsample, _lib.BF16, _lib.NDHWC)
 
 
+def build_cost_volume_split_bf16(left, right, shift, downsample=1):
+    """Split form of the NDHWC bf16 cost volume (snvc_cost_volume_split_fwd): the left half is a pure broadcast over
+    depth (BuildCostVolume_cuda.cu:84-86), so it is written once.  Returns
+    (right_vol [N,D,H,W,C] = channels [C,2C) of the full volume, left_planes [N,3,H,W,C] = the left features on three
+    identical planes, the input of the depth-invariant part of the first trunk convolution)."""
+    _lib.require_cuda(left, right, shift)
+    if left.dtype != torch.float32 or right.dtype != torch.float32:
+        raise RuntimeError("build_cost_volume_split_bf16: fp32 features only")
+    ds = int(downsample)
+    left, right, shift = left.contiguous(), right.contiguous(), shift.contiguous().float()
+    N, C, IH, IW = left.shape
+    D = shift.size(1)
+    H, W = IH // ds, IW // ds
+    right_vol = torch.empty((N, D, H, W, C), dtype=torch.bfloat16, device=left.device)
+    left_planes = torch.empty((N, 3, H, W, C), dtype=torch.bfloat16, device=left.device)
+    with torch.cuda.device(left.device):
+        st = _lib.lib().snvc_cost_volume_split_fwd(left.data_ptr(), right.data_ptr(), shift.data_ptr(),
+                                                   right_vol.data_ptr(), left_planes.data_ptr(), N, C, IH, IW, D, ds,
+                                                   _lib.stream_ptr())
+    _lib.check(st, "snvc_cost_volume_split_fwd")
+    return right_vol, left_planes
+
+
 def cost_volume_xlow(shift, IW, downsample=1):
     """Debug: x_low per (n, d, pw) computed by the kernel's own device code (-1 = outside)."""
     _lib.require_cuda(shift)

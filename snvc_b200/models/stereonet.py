@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from snvc_b200 import functional as SF
-from snvc_b200.extension.build_cost_volume import build_cost_volume_ndhwc_bf16
+from snvc_b200.extension.build_cost_volume import build_cost_volume_ndhwc_bf16, build_cost_volume_split_bf16
 from snvc_b200.models.submodule import _cbr, convbn_3d, hourglass
 
 
@@ -57,6 +57,49 @@ class GlobalHotPath(nn.Module):
         """dres0.conv1 (3x3x3, 2F -> ch): the single largest kernel of the path."""
         return self.dres0[0].fused(cost)
 
+    # ---- first layer on the SPLIT cost volume ------------------------------------------------------------------
+    def _split_plans(self):
+        """dres0.conv1 = convbn_3d(2F, ch) + ReLU split by input channel: (left part, no norm, fp32 out) and
+        (right part + folded BatchNorm).  Cached like _ConvNorm3d._plan; None when the layer is not eligible."""
+        from snvc_b200.conv import PackedConv3d
+        cn = self.dres0[0][0]                            # _ConvNorm3d(conv, norm)
+        conv, norm = cn[0], cn[1]
+        F2 = conv.weight.shape[1]
+        if isinstance(norm, nn.GroupNorm) or conv.weight.shape[0] != 32 or F2 != 64 or conv.kernel_size[0] != 3:
+            return None
+        if norm.training:
+            raise RuntimeError("snvc_b200 conv blocks are inference-only: call .eval() (BatchNorm uses running stats)")
+        vers = (conv.weight.data_ptr(), conv.weight._version, str(conv.weight.device), norm.weight._version,
+                norm.bias._version, norm.running_mean._version, norm.running_var._version)
+        plan = getattr(self, "_snvc_split_plan", None)
+        if plan is None or plan[0] != vers:
+            F = F2 // 2
+            plan = (vers, PackedConv3d(conv.weight[:, :F].contiguous(), None, stride=1, pad=1),
+                    PackedConv3d(conv.weight[:, F:].contiguous(), norm, stride=1, pad=1))
+            object.__setattr__(self, "_snvc_split_plan", plan)
+        return plan[1], plan[2]
+
+    def split_supported(self, depth_bins):
+        """The split first layer needs the CTA-pair conv kernel (default conv mode), >= 2 depth bins, 32 + 32 channels."""
+        import os
+        return depth_bins >= 2 and not os.environ.get("SNVC_CONV_MODE") and os.environ.get("SNVC_SPLIT_CV", "1") != "0" \
+            and self._split_plans() is not None
+
+    def trunk_head_split(self, right_vol, left_planes):
+        """dres0.conv1 on the split cost volume (build_cost_volume_split_bf16).  The left half of the volume does not
+        vary with depth, so its share of the 3x3x3 convolution is the same for every interior output plane: it is
+        computed ONCE as a 3-plane convolution of `left_planes` (zero padding in depth gives planes 0 / 1 / 2 the tap
+        sets of output depth 0 / interior / D-1) and enters the right half's convolution as an fp32 addend before the
+        folded BatchNorm and ReLU.  Same algebra as the 64-channel layer, half its FLOPs and half the volume bytes."""
+        return self.trunk_head_right(right_vol, self.trunk_head_addend(left_planes))
+
+    def trunk_head_addend(self, left_planes):
+        """[N,3,H,W,F] bf16 -> fp32 [N,3,H,W,ch]: the left half's share of dres0.conv1 for output depth 0 / interior / D-1."""
+        return self._split_plans()[0](left_planes, out_dtype=torch.float32)
+
+    def trunk_head_right(self, right_vol, addend):
+        return self._split_plans()[1](right_vol, relu=True, addend=addend)
+
     def trunk_tail(self, x):
         x = self.dres0[1].fused(x)
         x = self.dres1[1].fused(self.dres1[0].fused(x), residual=x, residual_mode=1)
@@ -69,8 +112,12 @@ class GlobalHotPath(nn.Module):
     def forward(self, left_feat, right_feat, shift, proj, out_dtype=torch.float32, layout_out="NCDHW"):
         """left_feat/right_feat [N,F,H,W] fp32, shift [N,D] fp32 (>= 0), proj [N,3,4] fp32
         -> lifted voxels [N,ch,Z,Y,X] (layout_out 'NCDHW') or [N,Z,Y,X,ch] ('NDHWC')."""
-        cost = build_cost_volume_ndhwc_bf16(left_feat, right_feat, shift, 1)
-        return self.lift(self.trunk(cost), proj, out_dtype, layout_out)
+        if self.split_supported(shift.shape[1]):
+            right_vol, left_planes = build_cost_volume_split_bf16(left_feat, right_feat, shift, 1)
+            feat = self.trunk_tail(self.trunk_head_split(right_vol, left_planes))
+        else:
+            feat = self.trunk(build_cost_volume_ndhwc_bf16(left_feat, right_feat, shift, 1))
+        return self.lift(feat, proj, out_dtype, layout_out)
 
 
 class GraphedHotPath:
@@ -82,8 +129,8 @@ class GraphedHotPath:
     batch are captured once -- the C ABI launches on the caller's stream, keeps no host state and never synchronises,
     so it is capturable as is -- and replayed with one `cudaGraphLaunch` per stage.
 
-    `stages=True` captures four graphs (cost volume | dres0.conv1 | rest of the trunk | lift) sharing one memory
-    pool, so a caller can record events between them (bench.py); `stages=False` captures one graph.
+    `stages=True` captures four graphs (cost volume [+ the 3-plane addend convolution of the split first layer] |
+    dres0.conv1 | rest of the trunk | lift) sharing one memory pool, so a caller can record events between them (bench.py); `stages=False` captures one graph.
     Inputs are copied into the graph's static buffers (`self.inputs`); the result is the static tensor `self.vox`
     (valid until the next replay).  `launches_per_replay` = kernels captured, from the library's launch counter."""
 
@@ -98,8 +145,18 @@ class GraphedHotPath:
                        torch.zeros((batch, depth_bins), device=dev), torch.zeros((batch, 3, 4), device=dev))
         self.inputs[3][:, 2, 2] = 1.0                       # a harmless projection for the warm-up pass
         l, r, sh, pr = self.inputs
-        fns = [lambda: setattr(self, "_cost", build_cost_volume_ndhwc_bf16(l, r, sh, 1)),
-               lambda: setattr(self, "_x1", model.trunk_head(self._cost)),
+        self.split = model.split_supported(depth_bins)
+        if self.split:
+            # the 3-plane addend convolution belongs to the first layer but is captured with the volume build, so that the
+            # "conv1" stage is the single large launch a caller may want to time on its own
+            def stage0():
+                self._cost = build_cost_volume_split_bf16(l, r, sh, 1)
+                self._addend = model.trunk_head_addend(self._cost[1])
+            stage1 = lambda: setattr(self, "_x1", model.trunk_head_right(self._cost[0], self._addend))
+        else:
+            stage0 = lambda: setattr(self, "_cost", build_cost_volume_ndhwc_bf16(l, r, sh, 1))
+            stage1 = lambda: setattr(self, "_x1", model.trunk_head(self._cost))
+        fns = [stage0, stage1,
                lambda: setattr(self, "_feat", model.trunk_tail(self._x1)),
                lambda: setattr(self, "vox", model.lift(self._feat, pr, out_dtype, layout_out))]
         if not stages:
@@ -182,13 +239,47 @@ class HostPipeline:
     `depth` slots so that the copies of batch i-1 / i+1 overlap the kernels of batch i (PCIe is full
     duplex).  `submit` enqueues one batch and returns immediately; `drain` waits for everything."""
 
-    def __init__(self, model, depth=2, out_dtype=torch.bfloat16, layout_out="NDHWC"):
+    def __init__(self, model, depth=2, out_dtype=torch.bfloat16, layout_out="NDHWC", graphed=True):
+        """`graphed`: every slot owns a `GraphedHotPath` (captured at the first batch of a new shape); the host then
+        issues three copies and one graph launch per batch instead of ~16 kernel launches, which keeps the pipeline
+        PCIe-bound when the host is busy (eager: 240 - 680 pairs/s for the same work, profiles/r01_ab_kw_kd.txt)."""
         self.model, self.depth, self.out_dtype, self.layout_out = model, depth, out_dtype, layout_out
         dev = next(model.parameters()).device
         self.dev = dev
+        self.graphed = graphed
         self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-        self.slots = [dict(inputs=None, computed=None, copied_out=None) for _ in range(depth)]
+        self.slots = [dict(inputs=None, computed=None, copied_out=None, graph=None, shape=None) for _ in range(depth)]
         self.n = 0
+
+    def _submit_graphed(self, slot, h_left, h_right, h_shift, h_proj, h_out):
+        cur = torch.cuda.current_stream(self.dev)
+        shape = (tuple(h_left.shape), tuple(h_shift.shape))
+        if slot["graph"] is None or slot["shape"] != shape:
+            self.drain()
+            N, C, H, W = h_left.shape
+            slot["graph"] = GraphedHotPath(self.model, N, C, (H, W), h_shift.shape[1], self.out_dtype, self.layout_out)
+            slot["shape"] = shape
+            slot["computed"] = slot["copied_out"] = None
+        g = slot["graph"]
+        with torch.cuda.stream(self.s_in):
+            if slot["computed"] is not None:          # the slot's previous inputs must have been consumed
+                self.s_in.wait_event(slot["computed"])
+            for d, h in zip(g.inputs, (h_left, h_right, h_shift, h_proj)):
+                d.copy_(h, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(self.s_in)
+        cur.wait_event(ready)
+        if slot["copied_out"] is not None:            # the slot's previous result must have left the device
+            cur.wait_event(slot["copied_out"])
+        vox = g.replay()
+        slot["computed"] = torch.cuda.Event()
+        slot["computed"].record(cur)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(slot["computed"])
+            h_out.copy_(vox, non_blocking=True)
+            slot["copied_out"] = torch.cuda.Event()
+            slot["copied_out"].record(self.s_out)
+        return slot["copied_out"]
 
     def submit(self, h_left, h_right, h_shift, h_proj, h_out):
         """All arguments are pinned host tensors; `h_out` receives the lifted voxels."""
@@ -197,6 +288,8 @@ class HostPipeline:
                 raise RuntimeError("HostPipeline.submit expects pinned host tensors")
         slot = self.slots[self.n % self.depth]
         self.n += 1
+        if self.graphed:
+            return self._submit_graphed(slot, h_left, h_right, h_shift, h_proj, h_out)
         cur = torch.cuda.current_stream(self.dev)
         with torch.cuda.stream(self.s_in):
             if slot["computed"] is not None:          # the slot's previous inputs must have been consumed

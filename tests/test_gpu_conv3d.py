@@ -185,6 +185,54 @@ def test_conv_cta_pair_plane_march(monkeypatch):
             _case(*c["a"], **c["k"])
 
 
+def _split_case(dhw, N=1, seed=0):
+    """First trunk layer on the split cost volume: a 64 -> 32 3x3x3 conv whose first 32 input channels do not vary
+    with depth == conv of the other 32 channels + a depth-invariant addend from a 3-plane conv of the constant half."""
+    from snvc_b200 import functional as F
+    from snvc_b200.conv import PackedConv3d
+    import types
+    D, H, W = dhw
+    left = synth.det_uniform((N, 32, 1, H, W), seed + 1)
+    right = synth.det_uniform((N, 32, D, H, W), seed + 2)
+    a = float(np.sqrt(3.0 / (64 * 27)))
+    w = synth.det_uniform((32, 64, 3, 3, 3), seed + 3, -a, a)
+    scale = synth.det_uniform((32,), seed + 4, 0.6, 1.4, bf16=False)
+    bias = synth.det_uniform((32,), seed + 5, -0.2, 0.2, bf16=False)
+    x = torch.cat([torch.from_numpy(left).expand(N, 32, D, H, W), torch.from_numpy(right)], 1)
+    ref = TF.conv3d(x, torch.from_numpy(w), padding=1)
+    ref = torch.relu(ref * torch.from_numpy(scale).view(1, -1, 1, 1, 1) + torch.from_numpy(bias).view(1, -1, 1, 1, 1)).numpy()
+    bn = types.SimpleNamespace(eps=0.0, weight=torch.from_numpy(scale).cuda(), bias=torch.from_numpy(bias).cuda(),
+                               running_mean=torch.zeros(32, device="cuda"), running_var=torch.ones(32, device="cuda"))
+    tw = torch.from_numpy(w).cuda()
+    p_left = PackedConv3d(tw[:, :32].contiguous(), None, stride=1, pad=1)
+    p_right = PackedConv3d(tw[:, 32:].contiguous(), bn, stride=1, pad=1)
+    left3 = F.to_ndhwc_bf16(torch.from_numpy(left).expand(N, 32, 3, H, W).contiguous().cuda())
+    xr = F.to_ndhwc_bf16(torch.from_numpy(right).cuda())
+    addend = p_left(left3, out_dtype=torch.float32)
+    for dt, tol in ((torch.float32, 1e-4), (torch.bfloat16, 6e-3)):
+        y = p_right(xr, relu=True, addend=addend, out_dtype=dt)
+        torch.cuda.synchronize()
+        e = _relerr(y.float().permute(0, 4, 1, 2, 3).cpu().numpy(), ref)
+        assert e <= tol, f"{dt}: rel err {e}"
+
+
+def test_conv_depth_invariant_addend(monkeypatch):
+    """snvc_conv3d_fwd_addend (CTA-pair kernel): depths 2 and 3 (every plane is an edge plane or the only interior one),
+    a depth beyond the 14-block ring, an odd column count, all three row pitches, ragged edges, clamped grid."""
+    _split_case((2, 8, 30))
+    _split_case((3, 5, 33), N=2)
+    _split_case((17, 10, 60), N=2)
+    monkeypatch.setenv("SNVC_CONV_MAXGRID", "1")
+    _split_case((20, 4, 30), N=3)
+    _split_case((9, 16, 40))
+    _split_case((6, 3, 124))
+    from snvc_b200.conv import PackedConv3d
+    p1 = PackedConv3d(torch.zeros(32, 32, 3, 3, 3, device="cuda"), None, stride=1, pad=1)
+    x = torch.zeros(1, 1, 4, 8, 32, dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(RuntimeError, match="D >= 2"):                               # a single depth plane is not supported
+        p1(x, addend=torch.zeros(1, 3, 4, 8, 32, device="cuda"))
+
+
 def test_conv_kd_fused_kernel_still_green(monkeypatch):
     """SNVC_CONV_MODE=kd keeps the v3 kernel (kd taps only) reachable for A/B runs; it also serves Cout = 16 / 64."""
     monkeypatch.setenv("SNVC_CONV_MODE", "kd")

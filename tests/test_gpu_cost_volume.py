@@ -49,6 +49,25 @@ def test_ndhwc_bf16_equals_rounded_oracle(shape, ds):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("shape,ds", [((2, 8, 6, 16), 1), ((1, 32, 5, 40), 1), ((2, 16, 8, 24), 2), ((1, 32, 96, 312), 1)])
+def test_split_form_equals_rounded_oracle(shape, ds):
+    """snvc_cost_volume_split_fwd: right_vol = channels [C, 2C) of the volume, left_planes = the depth-invariant left
+    half on three identical planes; both equal to the bf16-rounded oracle volume (and hence to the unsplit kernel)."""
+    N, C, H, W = shape
+    l, r = _rand(shape, 5), _rand(shape, 6)
+    s = np.tile(np.float32(EDGE_SHIFTS + [40.6, 17.3])[None], (N, 1))
+    want = synth.bf16_round(ocv.forward_c(l, r, s, ds, fma_mode=1))          # [N,2C,D,H,W]
+    rv, lp = _bcv().build_cost_volume_split_bf16(torch.from_numpy(l).cuda(), torch.from_numpy(r).cuda(),
+                                                 torch.from_numpy(s).cuda(), ds)
+    D = s.shape[1]
+    assert rv.shape == (N, D, H // ds, W // ds, C) and lp.shape == (N, 3, H // ds, W // ds, C)
+    assert np.array_equal(rv.float().permute(0, 4, 1, 2, 3).cpu().numpy(), want[:, C:])
+    lpn = lp.float().permute(0, 4, 1, 2, 3).cpu().numpy()
+    for v in range(3):
+        assert np.array_equal(lpn[:, :, v], want[:, :C, 0])
+    assert np.array_equal(want[:, :C, 0], want[:, :C, D - 1])                # the oracle's left half is a broadcast over depth
+
+
 def test_xlow_indices_bit_exact():
     s = np.float32([EDGE_SHIFTS, EDGE_SHIFTS[::-1]])
     for IW, ds in ((10, 1), (312, 1), (24, 2)):

@@ -156,6 +156,28 @@ def test_global_hot_path_vs_oracle_and_topk():
         assert np.array_equal(top_ref[:k], top_got[:k])
 
 
+def test_split_first_layer_matches_unsplit_path(monkeypatch):
+    """GlobalHotPath.forward on the split cost volume (right-half volume + depth-invariant addend, the default) against
+    the same model on the materialised 64-channel volume (SNVC_SPLIT_CV=0): same algebra, different fp32 summation
+    order -> equal within the bf16 tolerance of the path."""
+    from snvc_b200.models.stereonet import GlobalHotPath
+    geom, cfg = _small_global()
+    N, Fc, H, W = 2, 32, geom.IH // 4, geom.IW // 4
+    m = GlobalHotPath(cfg).eval()
+    m.load_state_dict(synth.det_state_dict(m, 41), strict=True)
+    m = m.cuda()
+    args = [torch.from_numpy(a).cuda() for a in (synth.det_uniform((N, Fc, H, W), 301), synth.det_uniform((N, Fc, H, W), 302),
+                                                  np.ascontiguousarray(geom.shifts(N)), np.stack([geom.P, geom.P]).astype(np.float32))]
+    with torch.no_grad():
+        assert m.split_supported(args[2].shape[1])
+        got = m(*args)
+        monkeypatch.setenv("SNVC_SPLIT_CV", "0")
+        assert not m.split_supported(args[2].shape[1])
+        want = m(*args)
+    err = float((got - want).abs().max() / want.abs().max())
+    assert err <= TOL, err
+
+
 @pytest.mark.parametrize("stages", [False, True])
 def test_graphed_hot_path_matches_eager_forward(stages):
     """GraphedHotPath (CUDA-graph replay of the captured launches, one graph or four stage graphs) returns bit for bit
@@ -184,9 +206,10 @@ def test_graphed_hot_path_matches_eager_forward(stages):
             assert torch.equal(g(lf, rf, shift, Ps), want)
 
 
-def test_host_pipeline_matches_direct_forward():
-    """HostPipeline (pinned host buffers, H2D / compute / D2H overlapped over 2 slots) returns, for every
-    submitted batch, exactly what the module's forward returns for that batch."""
+@pytest.mark.parametrize("graphed", [True, False])
+def test_host_pipeline_matches_direct_forward(graphed):
+    """HostPipeline (pinned host buffers, H2D / compute / D2H overlapped over 2 slots; one CUDA-graph replay per batch
+    or eager launches) returns, for every submitted batch, exactly what the module's forward returns for that batch."""
     from snvc_b200.models.stereonet import GlobalHotPath, HostPipeline
     geom, cfg = _small_global()
     N, Fc, H, W = 2, 32, geom.IH // 4, geom.IW // 4
@@ -199,7 +222,7 @@ def test_host_pipeline_matches_direct_forward():
                for i in range(5)]
     with torch.no_grad():
         want = [m(l.cuda(), r.cuda(), shift.cuda(), Ps.cuda(), torch.bfloat16, "NDHWC").cpu() for l, r in batches]
-        pipe = HostPipeline(m, depth=2)
+        pipe = HostPipeline(m, depth=2, graphed=graphed)
         outs = [torch.empty(want[0].shape, dtype=torch.bfloat16).pin_memory() for _ in batches]
         for (l, r), o in zip(batches, outs):
             pipe.submit(l.pin_memory(), r.pin_memory(), shift.pin_memory(), Ps.pin_memory(), o)

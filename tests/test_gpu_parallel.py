@@ -61,10 +61,21 @@ def _slab_run(rank, world, dev):
     return zlo, zhi, err, int(full.shape[2])
 
 
-def test_slab_world1_matches_unsplit():
+# Two conv paths.  "kw" (SNVC_CONV_MODE=kw, the single-CTA kernels): every accumulator receives its taps in the same
+# order whatever the launch geometry, so slab and unsplit runs are bit-identical and the bookkeeping is checked exactly.
+# Default (CTA-pair kernel): planes whose accumulator-ring index is 0 or 1 are summed as primary + mirror block, and
+# which planes those are depends on the plane's position in the CTA's march -- an fp32 re-association that flips a few
+# bf16 roundings (one ulp = 2^-8) after five layers; the bar is the bf16 tolerance of the path (1e-2).
+MODES = [("kw", 1e-6), (None, 1e-2)]
+
+
+@pytest.mark.parametrize("mode,tol", MODES)
+def test_slab_world1_matches_unsplit(mode, tol, monkeypatch):
+    if mode:
+        monkeypatch.setenv("SNVC_CONV_MODE", mode)
     zlo, zhi, err, Z = _slab_run(0, 1, torch.device("cuda", 0))
     assert (zlo, zhi) == (0, Z)
-    assert err <= 1e-6, err          # same kernels on the same planes: only the slab bookkeeping differs
+    assert err <= tol, err           # same planes, same weights: only the slab bookkeeping differs
 
 
 def _worker(rank, world, port, use_nccl, q):
@@ -80,8 +91,11 @@ def _worker(rank, world, port, use_nccl, q):
         dist.destroy_process_group()
 
 
-def test_slab_world2_matches_unsplit():
+@pytest.mark.parametrize("mode,tol", MODES)
+def test_slab_world2_matches_unsplit(mode, tol, monkeypatch):
     import torch.multiprocessing as mp
+    if mode:
+        monkeypatch.setenv("SNVC_CONV_MODE", mode)       # inherited by the spawned ranks
     use_nccl = torch.cuda.device_count() >= 2
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")
@@ -95,5 +109,5 @@ def test_slab_world2_matches_unsplit():
         assert p.exitcode == 0
     (_, lo0, hi0, e0, Z), (_, lo1, hi1, e1, _) = res
     assert lo0 == 0 and hi0 == lo1 and hi1 == Z and hi0 > 0 and hi1 > lo1
-    # identical kernels and inputs; slabs see identical planes after the exchange -> bf16-identical features
-    assert e0 <= 1e-6 and e1 <= 1e-6, (e0, e1)
+    # identical inputs; slabs see identical planes after the exchange ("kw": bf16-identical features)
+    assert e0 <= tol and e1 <= tol, (e0, e1)
