@@ -1380,6 +1380,36 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
 // channels that do not vary with depth (the left half of the plane-sweep cost volume), computed once as a 3-plane
 // convolution: plane 0 / 1 / 2 of `addend` = the sums an output plane at depth 0 / interior / D-1 needs (the depth
 // padding removes one kd tap at either end).  The interior rows stay in registers for the whole column.
+// Work units of the CTA-pair kernel.  A unit is a pair of tile columns and a range of output planes.  Whole columns are
+// dealt round-robin to the clusters; the columns of the last, partial round (2112 columns on 148 SMs: 14.27 rounds,
+// i.e. 5 % of every large layer spent with 108 SMs idle) are cut into `parts` depth ranges so that the round is
+// shared by (almost) all clusters.  A range [d0, d1) loads input planes [max(d0-1, 0), min(d1+1, D)) and, as at the
+// ends of a whole column, the first and last accumulator planes of the march are not outputs of this unit.
+struct PairUnit { int q, d0, d1, ip0, np; };
+struct PairSchedule {
+  int nclusters, full_units, parts, total, D;
+  __device__ __forceinline__ void init(int npairs, int nclusters_, int D_) {
+    nclusters = nclusters_; D = D_;
+    const int rounds = npairs / nclusters, rem = npairs - rounds * nclusters;
+    full_units = rounds * nclusters;
+    parts = rem > 0 ? min(min(nclusters / rem, 4), max(D / 4, 1)) : 1;   // at least 4 output planes per range
+    if (parts < 1) parts = 1;
+    total = full_units + rem * parts;
+  }
+  __device__ __forceinline__ PairUnit unit(int u) const {
+    PairUnit r;
+    if (u < full_units) { r.q = u; r.d0 = 0; r.d1 = D; }
+    else {
+      const int t = u - full_units, part = t % parts;
+      r.q = full_units + t / parts;
+      r.d0 = (int)((int64_t)D * part / parts); r.d1 = (int)((int64_t)D * (part + 1) / parts);
+    }
+    r.ip0 = max(r.d0 - 1, 0);
+    r.np = min(r.d1 + 1, D) - r.ip0;
+    return r;
+  }
+};
+
 template <int KSTEPS, int SUBROW, bool RES, int WPT, bool ADD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 conv3d_kdpair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
@@ -1400,9 +1430,10 @@ conv3d_kdpair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   const uint32_t rank = cluster_ctarank();
   const uint32_t w_base = (smem_u32(smem) + 1023u) & ~1023u;
   const uint32_t slots_base = w_base + (((uint32_t)(K * K * p.w_tap_bytes) + 1023u) & ~1023u);
-  const uint32_t acc_per_col = (uint32_t)p.D + 2u;        // accumulator planes per column: out[-1] .. out[D]
   const int npairs = (p.num_cols + 1) >> 1;
   const int pair0 = (int)(blockIdx.x >> 1), pstep = (int)(gridDim.x >> 1);
+  PairSchedule sched;
+  sched.init(npairs, pstep, p.D);
 
   if (threadIdx.x < 64) {
     s_scale[threadIdx.x] = (p.scale && threadIdx.x < p.epi.Cout) ? p.scale[threadIdx.x] : 1.f;
@@ -1459,12 +1490,13 @@ conv3d_kdpair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     __syncwarp();
     uint32_t slot = 0, phase = 0;
     uint32_t slot_addr = slots_base;
-    for (int q = pair0; q < npairs; q += pstep) {
-      const int col = min(2 * q + (int)rank, p.num_cols - 1);           // (odd column count: the last follower re-reads a column)
+    for (int u = pair0; u < sched.total; u += pstep) {
+      const PairUnit un = sched.unit(u);
+      const int col = min(2 * un.q + (int)rank, p.num_cols - 1);        // (odd column count: the last follower re-reads a column)
       const int tw = col % p.tiles_w, rest = col / p.tiles_w;
       const int th = rest % p.tiles_h, n = rest / p.tiles_h;
       const int w0 = tw * p.TWv - p.pad, h0 = th * p.TH - p.pad;
-      for (int ip = 0; ip < p.D; ++ip) {
+      for (int ip = un.ip0; ip < un.ip0 + un.np; ++ip) {
         mbar_wait(smem_u32(&empty_bar[slot]), phase ^ 1u);
         if (elect_one()) {
           const uint32_t fb = leader_addr(smem_u32(&full_bar[slot]));
@@ -1489,8 +1521,9 @@ conv3d_kdpair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
       mbar_wait(smem_u32(&w_bar), 0);
       uint32_t slot = 0, phase = 0, a_plane = a_lo0;
       PairRing r0{0u, 0u};                                // ring position of accumulator plane g = out[pl-1]
-      for (int q = pair0; q < npairs; q += pstep) {
-        for (int pl = 0; pl < p.D; ++pl) {
+      for (int u = pair0; u < sched.total; u += pstep) {
+        const int np = sched.unit(u).np;
+        for (int pl = 0; pl < np; ++pl) {
           const PairRing r1 = pr_next(r0), r2 = pr_next(r1);
           mbar_wait(smem_u32(&full_bar[slot]), phase);
           if (pl == 0) {
@@ -1509,7 +1542,7 @@ conv3d_kdpair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                                desc64(desc_hi, b_lo0 + (uint32_t)t2 * b_tap + 2u * k), idesc);
             umma_commit_pair(smem_u32(&empty_bar[slot]));                 // plane consumed (both CTAs)
             umma_commit_pair(smem_u32(&acc_full_bar[r0.i]));              // out[pl-1] complete
-            if (pl == p.D - 1) {                                          // column tail: out[D-1], out[D]
+            if (pl == np - 1) {                                           // end of the march: the last two accumulator planes
               umma_commit_pair(smem_u32(&acc_full_bar[r1.i]));
               umma_commit_pair(smem_u32(&acc_full_bar[r2.i]));
             }
@@ -1519,7 +1552,7 @@ conv3d_kdpair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
           if (++slot == (uint32_t)p.nslots) { slot = 0; phase ^= 1u; a_plane = a_lo0; }
           r0 = r1;
         }
-        r0 = pr_next(pr_next(r0));                        // acc_per_col = D + 2
+        r0 = pr_next(pr_next(r0));                        // np + 2 accumulator planes per unit
       }
     }
   } else {
@@ -1556,16 +1589,18 @@ conv3d_kdpair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         }
       }
     };
-    for (int q = pair0; q < npairs; q += pstep) {
+    for (int u = pair0; u < sched.total; u += pstep) {
+      const PairUnit un = sched.unit(u);
+      const uint32_t acc_per_unit = (uint32_t)un.np + 2u;
       have_next = false;
-      const int col = 2 * q + (int)rank;
+      const int col = 2 * un.q + (int)rank;
       const bool ghost = col >= p.num_cols;               // odd column count: the last follower's results are dropped
       const int colc = ghost ? p.num_cols - 1 : col;
       const int tw = colc % p.tiles_w, rest = colc / p.tiles_w;
       const int th = rest % p.tiles_h, n = rest / p.tiles_h;
       const int ow = tw * p.TWv + r_w, oh = th * p.TH + r_h;
       const bool in_range = !ghost && r_w < p.TWv && ow < p.W && oh < p.H;
-      int64_t vox = (((int64_t)n * p.D) * p.H + oh) * p.W + ow - plane_vox;       // accumulator plane a <-> output plane a - 1
+      int64_t vox = (((int64_t)n * p.D + un.ip0) * p.H + oh) * p.W + ow - plane_vox;   // accumulator plane a <-> output plane ip0 + a - 1
       float addm[ADD ? CP : 1];
       const float* arow = nullptr;                        // this thread's row of addend plane 0 (planes are plane_vox*CP apart)
       if (ADD) {
@@ -1576,9 +1611,10 @@ conv3d_kdpair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
           addm[j] = t.x; addm[j + 1] = t.y; addm[j + 2] = t.z; addm[j + 3] = t.w;
         }
       }
-      for (uint32_t a = 0; a < acc_per_col; ++a, vox += plane_vox, rg = pr_next(rg), par ^= 1u) {
+      for (uint32_t a = 0; a < acc_per_unit; ++a, vox += plane_vox, rg = pr_next(rg), par ^= 1u) {
         if (par != grp) continue;
-        const bool real = a >= 1u && a <= (uint32_t)p.D;
+        const int od = un.ip0 + (int)a - 1;               // output plane of this accumulator plane
+        const bool real = od >= un.d0 && od < un.d1;
         // residual rows: fetched one plane of this group AHEAD (plane a + 2), so that their HBM / L2 latency is covered
         // by a whole plane of MMAs (fetched just before the wait they cost the residual layer 130 us of 580)
         uint4 rq[4];
@@ -1589,8 +1625,8 @@ conv3d_kdpair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
           } else {
             load_res(rq, in_range && real, vox);
           }
-          have_next = a + 2u < acc_per_col;
-          if (have_next) load_res(rqn, in_range && a + 2u <= (uint32_t)p.D, vox + 2 * plane_vox);
+          have_next = a + 2u < acc_per_unit;
+          if (have_next) load_res(rqn, in_range && od + 2 >= un.d0 && od + 2 < un.d1, vox + 2 * plane_vox);
         } else {
 #pragma unroll
           for (int i = 0; i < 4; ++i) rq[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -1615,8 +1651,8 @@ conv3d_kdpair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
               tmem_ld_wait();
             }
             if (ADD) {
-              const bool edge = a == 1u || a == (uint32_t)p.D;         // output plane 0 / D-1: their own addend planes
-              const float* ep = arow + (a == 1u ? 0 : 2 * plane_vox * CP) + c0;
+              const bool edge = od == 0 || od == p.D - 1;              // output plane 0 / D-1: their own addend planes
+              const float* ep = arow + (od == 0 ? 0 : 2 * plane_vox * CP) + c0;
 #pragma unroll
               for (int j = 0; j < 16; j += 4) {
                 float4 t = make_float4(addm[c0 + j], addm[c0 + j + 1], addm[c0 + j + 2], addm[c0 + j + 3]);

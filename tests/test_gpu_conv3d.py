@@ -183,6 +183,14 @@ def test_conv_cta_pair_plane_march(monkeypatch):
         monkeypatch.setenv("SNVC_CONV_MAXGRID", clamp)
         for c in cases:
             _case(*c["a"], **c["k"])
+    # depth-split tail units: the pair-columns left over after the whole rounds are cut into 2 / 3 / 4 depth ranges
+    monkeypatch.setenv("SNVC_CONV_MAXGRID", "2")                                            # 3 pairs on 2 clusters -> 2 ranges
+    _case(64, 32, 3, 1, 1, 1, False, (15, 16, 40), relu=True, residual_mode=1)
+    monkeypatch.setenv("SNVC_CONV_MAXGRID", "3")                                            # 4 pairs on 3 clusters -> 3 ranges
+    _case(32, 32, 3, 1, 1, 1, False, (13, 8, 60), N=2, relu=True, residual_mode=2)
+    monkeypatch.setenv("SNVC_CONV_MAXGRID", "4")                                            # 5 pairs on 4 clusters -> 4 ranges
+    _case(32, 32, 3, 1, 1, 1, False, (16, 4, 300), relu=True, residual_mode=1)
+    _case(64, 64, 3, 1, 1, 1, False, (18, 4, 270), relu=True)                               # 9 columns: ghost follower + ranges
 
 
 def _split_case(dhw, N=1, seed=0):
@@ -222,6 +230,10 @@ def test_conv_depth_invariant_addend(monkeypatch):
     _split_case((2, 8, 30))
     _split_case((3, 5, 33), N=2)
     _split_case((17, 10, 60), N=2)
+    monkeypatch.setenv("SNVC_CONV_MAXGRID", "3")                                            # 4 pairs on 3 clusters -> 3 depth ranges
+    _split_case((13, 8, 60), N=2)
+    monkeypatch.setenv("SNVC_CONV_MAXGRID", "4")                                            # 5 pairs on 4 clusters -> 4 depth ranges
+    _split_case((16, 4, 300))
     monkeypatch.setenv("SNVC_CONV_MAXGRID", "1")
     _split_case((20, 4, 30), N=3)
     _split_case((9, 16, 40))
