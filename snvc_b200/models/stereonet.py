@@ -276,13 +276,21 @@ class HostPipeline:
         slot["computed"].record(cur)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(slot["computed"])
-            h_out.copy_(vox, non_blocking=True)
+            if h_out.numel() == vox.numel():
+                h_out.copy_(vox, non_blocking=True)
+            else:
+                # result stays on the device (`slot["graph"].vox`, valid until the slot's next batch): only a digest --
+                # the first h_out.numel() values of every pair -- goes back, enough for the host to observe completion
+                h_out.copy_(vox.reshape(vox.shape[0], -1)[:, :h_out.numel() // vox.shape[0]].reshape(h_out.shape),
+                            non_blocking=True)
             slot["copied_out"] = torch.cuda.Event()
             slot["copied_out"].record(self.s_out)
         return slot["copied_out"]
 
     def submit(self, h_left, h_right, h_shift, h_proj, h_out):
-        """All arguments are pinned host tensors; `h_out` receives the lifted voxels."""
+        """All arguments are pinned host tensors; `h_out` receives the lifted voxels.  (Graphed pipelines only: an
+        `h_out` smaller than the voxel volume receives a per-pair digest instead and the volume stays on the device
+        for an on-device consumer -- the reference's own pipeline feeds it to the RPN without leaving the GPU.)"""
         for t in (h_left, h_right, h_shift, h_proj, h_out):
             if t.is_cuda or not t.is_pinned():
                 raise RuntimeError("HostPipeline.submit expects pinned host tensors")

@@ -268,5 +268,11 @@ def test_host_pipeline_matches_direct_forward(graphed):
         pipe.drain()
     for o, w in zip(outs, want):
         assert torch.equal(o.view(torch.int16), w.view(torch.int16))
+    if graphed:                                                             # result-on-device mode: a per-pair digest comes back
+        dig = torch.empty((N, 16), dtype=torch.bfloat16).pin_memory()
+        l, r = batches[2]
+        pipe.submit(l.pin_memory(), r.pin_memory(), shift.pin_memory(), Ps.pin_memory(), dig)
+        pipe.drain()
+        assert torch.equal(dig.view(torch.int16), want[2].reshape(N, -1)[:, :16].contiguous().view(torch.int16))
     with pytest.raises(RuntimeError):
         pipe.submit(batches[0][0], batches[0][1], shift, Ps, outs[0])       # pageable host memory is rejected
