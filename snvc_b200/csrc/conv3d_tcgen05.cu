@@ -1392,8 +1392,18 @@ struct PairSchedule {
     nclusters = nclusters_; D = D_;
     const int rounds = npairs / nclusters, rem = npairs - rounds * nclusters;
     full_units = rounds * nclusters;
-    parts = rem > 0 ? min(min(nclusters / rem, 4), max(D / 4, 1)) : 1;   // at least 4 output planes per range
-    if (parts < 1) parts = 1;
+    // depth ranges per leftover pair-column: the count that makes the leftover cheapest, in units of one whole round:
+    // ceil(rem * parts / nclusters) rounds of ranges that each cost (D / parts + 2) / D of a column (two extra planes of
+    // halo); ranges keep at least 4 output planes.  (20 leftovers on 74 clusters -> 3 ranges, 0.375 round instead of 1;
+    // 46 leftovers -> 3 ranges in two rounds, 0.75 instead of 1.)
+    parts = 1;
+    if (rem > 0) {
+      float best = 1e30f;
+      for (int c = 1; c <= 4 && D / c >= 4; ++c) {
+        const float cost = (float)((rem * c + nclusters - 1) / nclusters) * ((float)(D / c + 2) / (float)D);
+        if (cost < best * 0.999f) { best = cost; parts = c; }
+      }
+    }
     total = full_units + rem * parts;
   }
   __device__ __forceinline__ PairUnit unit(int u) const {
@@ -1599,7 +1609,7 @@ conv3d_kdpair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
       const int tw = colc % p.tiles_w, rest = colc / p.tiles_w;
       const int th = rest % p.tiles_h, n = rest / p.tiles_h;
       const int ow = tw * p.TWv + r_w, oh = th * p.TH + r_h;
-      const bool in_range = !ghost && r_w < p.TWv && ow < p.W && oh < p.H;
+      const bool in_range = !ghost && r_w < p.TWv && r_h < p.TH && ow < p.W && oh < p.H;   // (r_h < TH: 126-row tiles, pitch 42)
       int64_t vox = (((int64_t)n * p.D + un.ip0) * p.H + oh) * p.W + ow - plane_vox;   // accumulator plane a <-> output plane ip0 + a - 1
       float addm[ADD ? CP : 1];
       const float* arow = nullptr;                        // this thread's row of addend plane 0 (planes are plane_vox*CP apart)
@@ -2914,13 +2924,17 @@ int launch_kdpair(const void* x, const void* w_packed, const float* scale, const
   p.w_tap_bytes = 48 * row_bytes;                        // this CTA's half of a tap's 96-row [kd=2|kd=1|kd=0] slab
   const int w_total = round_up(9 * p.w_tap_bytes, 1024);
   const int budget = 225 * 1024 - 1024 - w_total;
+  // tile = TH rows of pitch WP (TH * WP <= 128 MMA rows, WP - 2 useful columns per row).  Besides the power-of-two
+  // pitches, 42 x 3 (126 rows): at W = 312 / 156 / 78 it uses 91 % of the MMA rows against 89 / 81 / 81 % for pitch 32
   double best = -1;
-  for (int wp = 16; wp <= 64; wp <<= 1) {
-    const int twv = wp - hw, th = 128 / wp;
+  const int cand[4][2] = {{16, 8}, {32, 4}, {64, 2}, {42, 3}};
+  for (int ci = 0; ci < 4; ++ci) {
+    const int wp = cand[ci][0], th = cand[ci][1], twv = wp - hw;
     const int slot = round_up(((th + hw) * wp + 16) * row_bytes, 1024);   // + 16 rows: the kw-shifted windows of the last rows
     if (budget < 4 * slot) continue;
-    const double eff = ((double)d.Wi / (ceil_div(d.Wi, twv) * wp)) * ((double)d.Hi / (ceil_div(d.Hi, th) * th));
-    if (eff > best) { best = eff; p.WP = wp; p.TH = th; p.TWv = twv; p.slot_bytes = slot; }
+    // useful voxels per issued MMA row
+    const double eff = ((double)d.Wi * d.Hi) / ((double)ceil_div(d.Wi, twv) * ceil_div(d.Hi, th) * 128.0);
+    if (eff > best * 1.005) { best = eff; p.WP = wp; p.TH = th; p.TWv = twv; p.slot_bytes = slot; }
   }
   if (best < 0) return 1;
   p.nslots = std::min(kMaxSlots, budget / p.slot_bytes);
@@ -2959,7 +2973,8 @@ int launch_kdpair(const void* x, const void* w_packed, const float* scale, const
   void (*kern)(const CUtensorMap, const CUtensorMap, const HaloParams) = nullptr;
 #define SNVC_PAIR_W(KS, SR, RS, AD)                                                                               \
   (p.WP == 16 ? conv3d_kdpair_kernel<KS, SR, RS, 16, AD>                                                          \
-              : (p.WP == 32 ? conv3d_kdpair_kernel<KS, SR, RS, 32, AD> : conv3d_kdpair_kernel<KS, SR, RS, 64, AD>))
+              : (p.WP == 32 ? conv3d_kdpair_kernel<KS, SR, RS, 32, AD>                                            \
+                            : (p.WP == 42 ? conv3d_kdpair_kernel<KS, SR, RS, 42, AD> : conv3d_kdpair_kernel<KS, SR, RS, 64, AD>)))
   if (addend) kern = SNVC_PAIR_W(2, 64, false, true);
   else if (d.Cin == 32) kern = cp.residual_mode ? SNVC_PAIR_W(2, 64, true, false) : SNVC_PAIR_W(2, 64, false, false);
   else kern = cp.residual_mode ? SNVC_PAIR_W(4, 128, true, false) : SNVC_PAIR_W(4, 128, false, false);

@@ -183,6 +183,11 @@ def test_conv_cta_pair_plane_march(monkeypatch):
         monkeypatch.setenv("SNVC_CONV_MAXGRID", clamp)
         for c in cases:
             _case(*c["a"], **c["k"])
+    # pitch-42 tiles (3 rows x 42 columns = 126 of the 128 MMA rows; chosen when they waste fewer rows): W = 40 / 78 with
+    # heights that are not multiples of 3, both Cin, residual, several columns per pair
+    _case(32, 32, 3, 1, 1, 1, False, (17, 9, 40), N=2, relu=True, residual_mode=1)
+    _case(64, 32, 3, 1, 1, 1, False, (5, 10, 78), relu=True)
+    _case(64, 64, 3, 1, 1, 1, False, (6, 7, 118), N=2, relu=True, residual_mode=2)
     # depth-split tail units: the pair-columns left over after the whole rounds are cut into 2 / 3 / 4 depth ranges
     monkeypatch.setenv("SNVC_CONV_MAXGRID", "2")                                            # 3 pairs on 2 clusters -> 2 ranges
     _case(64, 32, 3, 1, 1, 1, False, (15, 16, 40), relu=True, residual_mode=1)
@@ -230,6 +235,7 @@ def test_conv_depth_invariant_addend(monkeypatch):
     _split_case((2, 8, 30))
     _split_case((3, 5, 33), N=2)
     _split_case((17, 10, 60), N=2)
+    _split_case((6, 9, 40), N=2)                                                            # pitch-42 tiles
     monkeypatch.setenv("SNVC_CONV_MAXGRID", "3")                                            # 4 pairs on 3 clusters -> 3 depth ranges
     _split_case((13, 8, 60), N=2)
     monkeypatch.setenv("SNVC_CONV_MAXGRID", "4")                                            # 5 pairs on 4 clusters -> 4 depth ranges
