@@ -129,8 +129,8 @@ class GraphedHotPath:
     batch are captured once -- the C ABI launches on the caller's stream, keeps no host state and never synchronises,
     so it is capturable as is -- and replayed with one `cudaGraphLaunch` per stage.
 
-    `stages=True` captures four graphs (cost volume [+ the 3-plane addend convolution of the split first layer] |
-    dres0.conv1 | rest of the trunk | lift) sharing one memory pool, so a caller can record events between them (bench.py); `stages=False` captures one graph.
+    `stages=True` captures one graph per stage (`stage_names`: cost volume | [3-plane addend convolution of the split
+    first layer] | dres0.conv1 | rest of the trunk | lift) sharing one memory pool, so a caller can record events between them (bench.py); `stages=False` captures one graph.
     Inputs are copied into the graph's static buffers (`self.inputs`); the result is the static tensor `self.vox`
     (valid until the next replay).  `launches_per_replay` = kernels captured, from the library's launch counter."""
 
@@ -146,22 +146,23 @@ class GraphedHotPath:
         self.inputs[3][:, 2, 2] = 1.0                       # a harmless projection for the warm-up pass
         l, r, sh, pr = self.inputs
         self.split = model.split_supported(depth_bins)
+        tail = [lambda: setattr(self, "_feat", model.trunk_tail(self._x1)),
+                lambda: setattr(self, "vox", model.lift(self._feat, pr, out_dtype, layout_out))]
         if self.split:
-            # the 3-plane addend convolution belongs to the first layer but is captured with the volume build, so that the
+            # five stages: the 3-plane addend convolution is part of the first layer but gets its own graph, so that the
             # "conv1" stage is the single large launch a caller may want to time on its own
-            def stage0():
-                self._cost = build_cost_volume_split_bf16(l, r, sh, 1)
-                self._addend = model.trunk_head_addend(self._cost[1])
-            stage1 = lambda: setattr(self, "_x1", model.trunk_head_right(self._cost[0], self._addend))
+            fns = [lambda: setattr(self, "_cost", build_cost_volume_split_bf16(l, r, sh, 1)),
+                   lambda: setattr(self, "_addend", model.trunk_head_addend(self._cost[1])),
+                   lambda: setattr(self, "_x1", model.trunk_head_right(self._cost[0], self._addend))] + tail
+            self.stage_names = ["cost_volume", "conv1_addend", "conv1", "trunk_rest", "lift"]
         else:
-            stage0 = lambda: setattr(self, "_cost", build_cost_volume_ndhwc_bf16(l, r, sh, 1))
-            stage1 = lambda: setattr(self, "_x1", model.trunk_head(self._cost))
-        fns = [stage0, stage1,
-               lambda: setattr(self, "_feat", model.trunk_tail(self._x1)),
-               lambda: setattr(self, "vox", model.lift(self._feat, pr, out_dtype, layout_out))]
+            fns = [lambda: setattr(self, "_cost", build_cost_volume_ndhwc_bf16(l, r, sh, 1)),
+                   lambda: setattr(self, "_x1", model.trunk_head(self._cost))] + tail
+            self.stage_names = ["cost_volume", "conv1", "trunk_rest", "lift"]
         if not stages:
             parts = list(fns)
             fns = [lambda: [f() for f in parts]]
+            self.stage_names = ["all"]
         L = _lib.lib()
         with torch.no_grad():
             side = torch.cuda.Stream(dev)
