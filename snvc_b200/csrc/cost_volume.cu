@@ -306,17 +306,20 @@ cv_ndhwc_bf16_kernel(const float* __restrict__ left, const float* __restrict__ r
 __global__ void __launch_bounds__(512)
 cv_split_bf16_kernel(const float* __restrict__ left, const float* __restrict__ right, const float* __restrict__ shift,
                      __nv_bfloat16* __restrict__ right_vol, __nv_bfloat16* __restrict__ left_planes, int C, int img_h,
-                     int img_w, int D, int H, int W, int ds, int d_per_cta, int mask) {
+                     int img_w, int D, int H, int W, int ds, int d_per_cta, int mask, int mode) {
+  // mode 1: right half only (grid.z = depth splits; shared memory = one right row + the sample table -> 3 CTAs per SM);
+  // mode 2: left planes only (grid.z = 1; shared memory = one left row).  Two launches, so that the 40 KB left row does
+  // not sit in the shared memory of every depth split.
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int ph = blockIdx.x, n = blockIdx.y, dsplit = blockIdx.z;
   const int d0 = dsplit * d_per_cta;
-  const int dn = min(d_per_cta, D - d0);
-  if (dn <= 0) return;
-  const int lw = (W - 1) * ds + 1;                      // left columns [0, lw) (only staged by the first depth split)
-  const bool do_left = dsplit == 0;
-  float* sR = reinterpret_cast<float*>(smem_raw);       // [img_w][C], 16-byte chunks XOR-swizzled by column
-  float* sL = sR + (size_t)img_w * C;                   // [lw][C]
-  int2* sT = reinterpret_cast<int2*>(sL + (size_t)lw * C);   // [dn][W]: {code, lx}
+  const bool do_left = mode == 2, do_right = mode == 1;
+  const int dn = do_right ? min(d_per_cta, D - d0) : 0;
+  if (do_right && dn <= 0) return;
+  const int lw = (W - 1) * ds + 1;                      // left columns [0, lw)
+  float* sR = reinterpret_cast<float*>(smem_raw);       // [img_w][C], 16-byte chunks XOR-swizzled by column (mode 1)
+  float* sL = sR;                                       // [lw][C] (mode 2)
+  int2* sT = reinterpret_cast<int2*>(sR + (size_t)img_w * C);   // [dn][W]: {code, lx} (mode 1)
   const int ih = ph * ds;
   const int64_t cstride = (int64_t)img_h * img_w;
   const float* rrow = right + ((int64_t)n * C * img_h + ih) * img_w;
@@ -324,7 +327,8 @@ cv_split_bf16_kernel(const float* __restrict__ left, const float* __restrict__ r
   // staging: a warp takes one channel at a time and runs along the row (coalesced 4-byte cp.async, no divisions)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   for (int c = warp; c < C; c += nwarp) {
-    for (int col = lane; col < img_w; col += 32) cp_async_4(&sR[swz(col, c, C, mask)], rrow + c * cstride + col);
+    if (do_right)
+      for (int col = lane; col < img_w; col += 32) cp_async_4(&sR[swz(col, c, C, mask)], rrow + c * cstride + col);
     if (do_left)
       for (int col = lane; col < lw; col += 32) cp_async_4(&sL[swz(col, c, C, mask)], lrow + c * cstride + col);
   }
@@ -354,6 +358,7 @@ cv_split_bf16_kernel(const float* __restrict__ left, const float* __restrict__ r
       for (int v = 0; v < 3; ++v) *reinterpret_cast<uint4*>(lo + (int64_t)v * H * W * C) = vl;
     }
   }
+  if (!do_right) return;
   // right half: item = (bin, strip, channel group); the CG lanes of an item's pixel are adjacent (64-byte segments)
   const int nstrips = max(1, (int)blockDim.x / (dn * CG));
   // odd strip length: the 8 lane groups of a warp then sit on columns with 8 different (col & 7), i.e. 8 different
@@ -537,14 +542,15 @@ int launch_cv_ndhwc(const void* left, const void* right, const void* shift, void
                     int64_t C, int64_t IH, int64_t IW, int64_t D, int ds, int64_t H, int64_t W, cudaStream_t stream) {
   SNVC_CHECK_ARG(C % 8 == 0, "NDHWC cost volume needs C %% 8 == 0 (got %lld)", (long long)C);
   if (left_planes && H <= 2147483647ll && N <= 65535 && !getenv("SNVC_CV_SPLIT_OLD")) {
-    // split form, whole rows staged: [img_w + (W-1)*ds+1 columns][C] fp32 + the sample table of one depth split
-    const size_t rows = ((size_t)IW + (size_t)((W - 1) * ds + 1)) * C * 4;
-    const size_t budget = 112 * 1024;                                   // two CTAs per SM
+    // split form, whole rows staged: the right row [img_w][C] fp32 + the sample table of one depth split (the left planes
+    // are a second, small launch of the same kernel)
+    const size_t rows = (size_t)IW * C * 4;
+    const size_t budget = 74 * 1024;                                    // three CTAs per SM
     if (rows + (size_t)W * 8 <= 225 * 1024) {
       int d_per = (int)D;
       if (rows + (size_t)W * D * 8 > budget) d_per = (int)std::max<int64_t>(1, ((int64_t)std::max<size_t>(budget, rows + W * 8) - (int64_t)rows) / (W * 8));
       // fill whole waves: more depth splits when the grid would leave SMs idle
-      const double wave = 2.0 * sm_count();
+      const double wave = (rows + (size_t)W * d_per * 8 <= budget ? 3.0 : 2.0) * sm_count();
       double best = -1;
       int pick = (int)ceil_div(D, d_per);
       for (int cand = (int)ceil_div(D, d_per); cand <= std::min<int64_t>(D, ceil_div(D, d_per) + 6); ++cand) {
@@ -560,10 +566,18 @@ int launch_cv_ndhwc(const void* left, const void* right, const void* shift, void
           SNVC_CUDA_OK(cudaFuncSetAttribute(cv_split_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int mask = 1;  // largest 2^k - 1 (k <= 3) with 2^k | C/4
         while (mask < 7 && ((C / 4) % (2 * (mask + 1))) == 0) mask = 2 * mask + 1;
+        const size_t smem_left = (size_t)((W - 1) * ds + 1) * C * 4;
+        if (std::max(smem, smem_left) > 48 * 1024)
+          SNVC_CUDA_OK(cudaFuncSetAttribute(cv_split_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)std::max(smem, smem_left)));
+        cv_split_bf16_kernel<<<dim3((unsigned)H, (unsigned)N, 1), 512, smem_left, stream>>>(
+            (const float*)left, (const float*)right, (const float*)shift, (__nv_bfloat16*)cost, (__nv_bfloat16*)left_planes,
+            (int)C, (int)IH, (int)IW, (int)D, (int)H, (int)W, ds, d_per, mask, 2);
+        if (int e = launch_status("cv_split_bf16_kernel")) return e;
         dim3 grid((unsigned)H, (unsigned)N, (unsigned)dsplit);
         cv_split_bf16_kernel<<<grid, 512, smem, stream>>>((const float*)left, (const float*)right, (const float*)shift,
                                                            (__nv_bfloat16*)cost, (__nv_bfloat16*)left_planes, (int)C, (int)IH,
-                                                           (int)IW, (int)D, (int)H, (int)W, ds, d_per, mask);
+                                                           (int)IW, (int)D, (int)H, (int)W, ds, d_per, mask, 1);
         return launch_status("cv_split_bf16_kernel");
       }
     }
