@@ -373,37 +373,50 @@ cv_split_bf16_kernel(const float* __restrict__ left, const float* __restrict__ r
     const int w_begin = strip * L, w_end = min(W, w_begin + L);
     const int2* tab = sT + dd * W;
     __nv_bfloat16* o = right_vol + ((((int64_t)n * D + d0 + dd) * H + ph) * W + w_begin) * C + cg * 8;
-    int cur_xh = -0x40000000;                           // column held in r1[]
-    float r0[8], r1[8];
-    for (int pw = w_begin; pw < w_end; ++pw, o += C) {
+    // Two register sets that swap roles every step (the step is unrolled by two), so that the column shared by two
+    // consecutive steps is never moved; values as packed fp32 pairs: one FMUL2 + one FFMA2 per two channels, the same
+    // roundings as the scalar hx*v1 then fma(lx, v2, .) (ncu on the first version: 88 instructions per warp step,
+    // issue slots 79 % busy -- the kernel was issue-bound at 64 % of the HBM peak).
+    int held = -0x40000000;                             // column held in the set that is "high" after the last step
+    float2 ra[4], rb[4];
+    auto load_col = [&](float2 (&dst)[4], int col) {
+      const float4 a = *chunk_ptr(sR, col, 2 * cg, C, mask), b = *chunk_ptr(sR, col, 2 * cg + 1, C, mask);
+      dst[0] = make_float2(a.x, a.y); dst[1] = make_float2(a.z, a.w); dst[2] = make_float2(b.x, b.y); dst[3] = make_float2(b.z, b.w);
+    };
+    // one step: `lo` must end up holding column xl, `hi` column xh; on entry `lo` holds column `held` (the previous
+    // step's high column), `hi` is free
+    auto step = [&](float2 (&lo)[4], float2 (&hi)[4], int pw, __nv_bfloat16* op) {
       const int2 te = tab[pw];
       uint4 v = make_uint4(0u, 0u, 0u, 0u);
       if (te.x >= 0) {
         const int xl = te.x & 0x3fffffff, xh = xl + ((te.x >> 30) & 1);
         const float lx = __int_as_float(te.y);
-        if (xl == cur_xh) {
+        if (xl != held) load_col(lo, xl);
+        if (xh != xl) load_col(hi, xh);
+        else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) r0[j] = r1[j];
-        } else {
-          *reinterpret_cast<float4*>(r0) = *chunk_ptr(sR, xl, 2 * cg, C, mask);
-          *reinterpret_cast<float4*>(r0 + 4) = *chunk_ptr(sR, xl, 2 * cg + 1, C, mask);
+          for (int j = 0; j < 4; ++j) hi[j] = lo[j];
         }
-        if (xh == xl) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) r1[j] = r0[j];
-        } else {
-          *reinterpret_cast<float4*>(r1) = *chunk_ptr(sR, xh, 2 * cg, C, mask);
-          *reinterpret_cast<float4*>(r1 + 4) = *chunk_ptr(sR, xh, 2 * cg + 1, C, mask);
-        }
-        cur_xh = xh;
+        held = xh;
         const float hx = __fsub_rn(1.f, lx);
-        float r[8];
+        const float2 lx2 = make_float2(lx, lx), hx2 = make_float2(hx, hx);
+        float2 r[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = __fmaf_rn(lx, r1[j], __fmul_rn(hx, r0[j]));
-        v = make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7]));
+        for (int j = 0; j < 4; ++j) r[j] = __ffma2_rn(lx2, hi[j], __fmul2_rn(hx2, lo[j]));
+        v = make_uint4(pack_bf16x2(r[0].x, r[0].y), pack_bf16x2(r[1].x, r[1].y), pack_bf16x2(r[2].x, r[2].y),
+                       pack_bf16x2(r[3].x, r[3].y));
+      } else {
+        held = -0x40000000;                             // nothing usable is held (hi was not written)
       }
-      *reinterpret_cast<uint4*>(o) = v;
+      *reinterpret_cast<uint4*>(op) = v;
+    };
+    int pw = w_begin;
+    for (; pw + 1 < w_end; pw += 2, o += 2 * C) {
+      step(ra, rb, pw, o);                              // after it: rb holds the high column
+      step(rb, ra, pw + 1, o + C);                      // rb is the low set now; after it: ra holds the high column
+      // restore the invariant "the set passed as `lo` next holds `held`": the next pair starts with (ra, rb) again
     }
+    if (pw < w_end) step(ra, rb, pw, o);
   }
 }
 
@@ -566,6 +579,9 @@ int launch_cv_ndhwc(const void* left, const void* right, const void* shift, void
           SNVC_CUDA_OK(cudaFuncSetAttribute(cv_split_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int mask = 1;  // largest 2^k - 1 (k <= 3) with 2^k | C/4
         while (mask < 7 && ((C / 4) % (2 * (mask + 1))) == 0) mask = 2 * mask + 1;
+        // (ncu: with the default carve-out only two of the 70 KB CTAs were resident per SM)
+        SNVC_CUDA_OK(cudaFuncSetAttribute(cv_split_bf16_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                          (int)cudaSharedmemCarveoutMaxShared));
         const size_t smem_left = (size_t)((W - 1) * ds + 1) * C * 4;
         if (std::max(smem, smem_left) > 48 * 1024)
           SNVC_CUDA_OK(cudaFuncSetAttribute(cv_split_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
