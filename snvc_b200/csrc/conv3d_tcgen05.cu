@@ -20,6 +20,17 @@
 // output stride of 2.
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
 // Persistent: grid = min(#tiles, #SMs), static round-robin tile schedule.
+//
+// The text above describes the first (per-tap) kernel, still the fallback for 1^3, stride-2 Cin = 64 and odd shapes.
+// The layers that carry the FLOPs run on the plane-march kernels further down, each introduced by its own header:
+//   v2 conv3d_halo_kernel     one TMA load per input plane, taps = shifted windows of the same tile
+//   v3 conv3d_kdfuse_kernel   + the 3 depth taps fused into N (TMEM accumulator ring)
+//   v4 conv3d_deconv_kernel   transposed conv, 8 parity classes in one march, staged TMA epilogue
+//   v5 conv3d_s2_kernel       stride 2 on "pair rows"
+//   v6 conv3d_bigk_kernel     5^3 / 7^3 with streamed weights
+//   v7 conv3d_kwfuse_kernel   + the 3 kw taps fused into N, row shift undone by shuffles in the epilogue
+//   v8 conv3d_kdpair_kernel   v3 over a CTA pair (tcgen05.mma.cta_group::2): the default for 32-channel output slices
+// snvc_conv3d_fwd (bottom of the file) picks the most specific eligible kernel.
 #include <cuda.h>
 
 #include <algorithm>
