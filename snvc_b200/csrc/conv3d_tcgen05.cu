@@ -1434,7 +1434,7 @@ struct PairSchedule {
 template <int KSTEPS, int SUBROW, bool RES, int WPT, bool ADD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 conv3d_kdpair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
-                     const __grid_constant__ HaloParams p) {
+                     const __grid_constant__ CUtensorMap map_r, const __grid_constant__ HaloParams p) {
   constexpr int K = 3, CP = 32;
   constexpr uint32_t TCOLS = 512;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -1445,12 +1445,21 @@ conv3d_kdpair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   __shared__ __align__(8) uint64_t acc_empty_bar[kPairRing];
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float s_scale[64], s_bias[64];
+  // RES: the residual tile of every output plane (the 128 accumulator rows x 64 bytes, same row order as the TMEM lanes)
+  // arrives by TMA in a ring of kResSlots swizzled tiles and is read with conflict-free LDS.128.  Fetched by the
+  // epilogue threads themselves (two LDG.256 of 32 different rows per warp) the residual rows cost 234 L1 wavefronts
+  // per plane on the pipe that also feeds the UMMA operands: ncu had the residual layer at 89 % of that pipe, tensor
+  // pipe 65 %, 0.56 ms against 0.43 ms for the same layer without a residual.
+  constexpr uint32_t kResSlots = 4, kResTile = 128u * 64u;
+  __shared__ __align__(8) uint64_t res_full_bar[kResSlots];
+  __shared__ __align__(8) uint64_t res_empty_bar[kResSlots];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const uint32_t w_base = (smem_u32(smem) + 1023u) & ~1023u;
-  const uint32_t slots_base = w_base + (((uint32_t)(K * K * p.w_tap_bytes) + 1023u) & ~1023u);
+  const uint32_t res_base = w_base + (((uint32_t)(K * K * p.w_tap_bytes) + 1023u) & ~1023u);
+  const uint32_t slots_base = res_base + (RES ? kResSlots * kResTile : 0u);
   const int npairs = (p.num_cols + 1) >> 1;
   const int pair0 = (int)(blockIdx.x >> 1), pstep = (int)(gridDim.x >> 1);
   PairSchedule sched;
@@ -1463,11 +1472,16 @@ conv3d_kdpair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    if (RES) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_r) : "memory");
     for (int s = 0; s < p.nslots; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 2);               // leader's copy: one arrive + tx per CTA
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
     mbar_init(smem_u32(&w_bar), 2);
+    for (uint32_t b = 0; b < kResSlots; ++b) {
+      mbar_init(smem_u32(&res_full_bar[b]), 1);
+      mbar_init(smem_u32(&res_empty_bar[b]), 4);          // the four warps of the group that drains the plane
+    }
     for (uint32_t b = 0; b < kPairRing; ++b) {
       mbar_init(smem_u32(&acc_full_bar[b]), 1);
       mbar_init(smem_u32(&acc_empty_bar[b]), 8);          // leader's copy: one arrive per epilogue warp of the draining group, both CTAs
@@ -1511,6 +1525,7 @@ conv3d_kdpair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     __syncwarp();
     uint32_t slot = 0, phase = 0;
     uint32_t slot_addr = slots_base;
+    uint32_t rslot = 0, rphase = 0;
     for (int u = pair0; u < sched.total; u += pstep) {
       const PairUnit un = sched.unit(u);
       const int col = min(2 * un.q + (int)rank, p.num_cols - 1);        // (odd column count: the last follower re-reads a column)
@@ -1527,6 +1542,16 @@ conv3d_kdpair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         __syncwarp();
         slot_addr += (uint32_t)p.slot_bytes;
         if (++slot == (uint32_t)p.nslots) { slot = 0; phase ^= 1u; slot_addr = slots_base; }
+        if (RES && ip >= un.d0 && ip < un.d1) {           // residual tile of OUTPUT plane ip (this CTA's own barriers)
+          mbar_wait(smem_u32(&res_empty_bar[rslot]), rphase ^ 1u);
+          if (elect_one()) {
+            const uint32_t rb = smem_u32(&res_full_bar[rslot]);
+            mbar_expect_tx(rb, (uint32_t)(p.WP * p.TH * 64));       // the box: WP x TH rows (126 of the 128 for pitch 42)
+            tma_load_5d(res_base + rslot * kResTile, &map_r, rb, 0, tw * p.TWv, th * p.TH, ip, n);
+          }
+          __syncwarp();
+          if (++rslot == kResSlots) { rslot = 0; rphase ^= 1u; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -1596,24 +1621,10 @@ conv3d_kdpair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     PairRing rg{0u, 0u};
     uint32_t par = 0;
     const bool out_f32 = p.epi.out_f32 != 0;
-    uint4 rqn[4];
-    bool have_next = false;
-    auto load_res = [&](uint4 (&r)[4], bool on, int64_t v) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) r[i] = make_uint4(0u, 0u, 0u, 0u);
-      if (on) {
-        const uint4* rp = reinterpret_cast<const uint4*>(p.epi.residual + v * p.epi.res_cstride + p.epi.res_coffset);
-        if (aligned32(rp)) { ldg256(rp, r[0], r[1]); ldg256(rp + 2, r[2], r[3]); }
-        else {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) r[i] = __ldg(rp + i);
-        }
-      }
-    };
+    uint32_t rslot = 0, rphase = 0;                       // residual ring position of the next REAL plane (both groups count all)
     for (int u = pair0; u < sched.total; u += pstep) {
       const PairUnit un = sched.unit(u);
       const uint32_t acc_per_unit = (uint32_t)un.np + 2u;
-      have_next = false;
       const int col = 2 * un.q + (int)rank;
       const bool ghost = col >= p.num_cols;               // odd column count: the last follower's results are dropped
       const int colc = ghost ? p.num_cols - 1 : col;
@@ -1633,24 +1644,19 @@ conv3d_kdpair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         }
       }
       for (uint32_t a = 0; a < acc_per_unit; ++a, vox += plane_vox, rg = pr_next(rg), par ^= 1u) {
-        if (par != grp) continue;
         const int od = un.ip0 + (int)a - 1;               // output plane of this accumulator plane
         const bool real = od >= un.d0 && od < un.d1;
-        // residual rows: fetched one plane of this group AHEAD (plane a + 2), so that their HBM / L2 latency is covered
-        // by a whole plane of MMAs (fetched just before the wait they cost the residual layer 130 us of 580)
+        const uint32_t my_rslot = rslot, my_rphase = rphase;
+        if (RES && real) { if (++rslot == kResSlots) { rslot = 0; rphase ^= 1u; } }
+        if (par != grp) continue;
         uint4 rq[4];
-        if (RES) {
-          if (have_next) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) rq[i] = rqn[i];
-          } else {
-            load_res(rq, in_range && real, vox);
-          }
-          have_next = a + 2u < acc_per_unit;
-          if (have_next) load_res(rqn, in_range && od + 2 >= un.d0 && od + 2 < un.d1, vox + 2 * plane_vox);
-        } else {
+        for (int i = 0; i < 4; ++i) rq[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (RES && real) {                                // this thread's row of the plane's residual tile
+          mbar_wait(smem_u32(&res_full_bar[my_rslot]), my_rphase);
+          const uint32_t tile = res_base + my_rslot * kResTile;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) rq[i] = make_uint4(0u, 0u, 0u, 0u);
+          for (int i = 0; i < 4; ++i) rq[i] = lds_v4(tile + swz<64>((uint32_t)row, (uint32_t)i));
         }
         mbar_wait(smem_u32(&acc_full_bar[rg.i]), rg.ph);
         tcgen05_fence_after();
@@ -1730,6 +1736,11 @@ conv3d_kdpair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(empty0 + rg.i * 8u);
+        // The residual slot is released only here, after every lane has USED its rows: an arrive issued right behind the
+        // LDS can overtake them (neither the arrive's release nor __syncwarp waits for another lane's outstanding
+        // shared-memory loads), and a producer that is blocked on exactly this slot -- as it is for the first tiles of a
+        // launch -- then overwrites rows that are still being read (seen as stale 1 KB box rows on cold first launches).
+        if (RES && real && lane == 0) mbar_arrive(smem_u32(&res_empty_bar[my_rslot]));
       }
     }
   }
@@ -2934,7 +2945,9 @@ int launch_kdpair(const void* x, const void* w_packed, const float* scale, const
   const int row_bytes = d.Cin * 2, hw = 2;
   p.w_tap_bytes = 48 * row_bytes;                        // this CTA's half of a tap's 96-row [kd=2|kd=1|kd=0] slab
   const int w_total = round_up(9 * p.w_tap_bytes, 1024);
-  const int budget = 225 * 1024 - 1024 - w_total;
+  const int res_total = cp.residual_mode ? 4 * 128 * 64 : 0;           // residual ring: 4 tiles of 128 rows x 64 bytes
+  if (cp.residual_mode && (cp.res_cstride % 8 || cp.res_coffset % 8 || (reinterpret_cast<uintptr_t>(residual) & 15))) return 1;
+  const int budget = 225 * 1024 - 1024 - w_total - res_total;
   // tile = TH rows of pitch WP (TH * WP <= 128 MMA rows, WP - 2 useful columns per row).  Besides the power-of-two
   // pitches, 42 x 3 (126 rows): at W = 312 / 156 / 78 it uses 91 % of the MMA rows against 89 / 81 / 81 % for pitch 32
   double best = -1;
@@ -2956,9 +2969,9 @@ int launch_kdpair(const void* x, const void* w_packed, const float* scale, const
   const int64_t ncols = (int64_t)d.N * p.tiles_h * p.tiles_w;
   SNVC_CHECK_ARG(ncols < (1ll << 31), "too many tile columns");
   p.num_cols = (int)ncols;
-  const size_t smem = (size_t)w_total + (size_t)p.nslots * p.slot_bytes + 1024;
+  const size_t smem = (size_t)w_total + (size_t)res_total + (size_t)p.nslots * p.slot_bytes + 1024;
 
-  CUtensorMap map_x, map_w;
+  CUtensorMap map_x, map_w, map_r;
   {
     const cuuint64_t cs = (cuuint64_t)(d.in_cstride ? d.in_cstride : d.Cin) * 2;
     cuuint64_t dims[5] = {(cuuint64_t)d.Cin, (cuuint64_t)d.Wi, (cuuint64_t)d.Hi, (cuuint64_t)d.Di, (cuuint64_t)d.N};
@@ -2971,6 +2984,22 @@ int launch_kdpair(const void* x, const void* w_packed, const float* scale, const
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail((int)r, "cuTensorMapEncodeTiled(x, kdpair) failed with CUresult %d", (int)r);
   }
+  if (cp.residual_mode) {
+    // the residual's 32-channel slice viewed as (C, W, H, D, N); box = the accumulator rows of a plane tile (WP x TH, the
+    // wasted columns included, so that tile row == TMEM lane); clipped edges are zero-filled and never stored
+    const cuuint64_t cs = (cuuint64_t)cp.res_cstride * 2;
+    cuuint64_t dims[5] = {32, (cuuint64_t)d.Wi, (cuuint64_t)d.Hi, (cuuint64_t)d.Di, (cuuint64_t)d.N};
+    cuuint64_t strides[4] = {cs, (cuuint64_t)d.Wi * cs, (cuuint64_t)d.Hi * d.Wi * cs, (cuuint64_t)d.Di * d.Hi * d.Wi * cs};
+    cuuint32_t box[5] = {32, (cuuint32_t)p.WP, (cuuint32_t)p.TH, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const void* rbase = static_cast<const char*>(residual) + (size_t)cp.res_coffset * 2;
+    CUresult r = enc(&map_r, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(rbase), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail((int)r, "cuTensorMapEncodeTiled(residual, kdpair) failed with CUresult %d", (int)r);
+  } else {
+    map_r = map_x;                                       // (unused)
+  }
   {
     cuuint64_t dims[2] = {(cuuint64_t)d.Cin, (cuuint64_t)27 * cp_full.CoutPad};
     cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
@@ -2981,7 +3010,7 @@ int launch_kdpair(const void* x, const void* w_packed, const float* scale, const
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail((int)r, "cuTensorMapEncodeTiled(w, kdpair) failed with CUresult %d", (int)r);
   }
-  void (*kern)(const CUtensorMap, const CUtensorMap, const HaloParams) = nullptr;
+  void (*kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const HaloParams) = nullptr;
 #define SNVC_PAIR_W(KS, SR, RS, AD)                                                                               \
   (p.WP == 16 ? conv3d_kdpair_kernel<KS, SR, RS, 16, AD>                                                          \
               : (p.WP == 32 ? conv3d_kdpair_kernel<KS, SR, RS, 32, AD>                                            \
@@ -3016,7 +3045,7 @@ int launch_kdpair(const void* x, const void* w_packed, const float* scale, const
   if (max_clusters < 1) return 1;
   int pairs = std::min((p.num_cols + 1) / 2, max_clusters);
   if (const char* mg = getenv("SNVC_CONV_MAXGRID")) pairs = std::max(1, std::min(pairs, atoi(mg)));   // tests: force ring wrap-around
-  kern<<<2 * pairs, kPairThreads, smem, stream>>>(map_x, map_w, p);
+  kern<<<2 * pairs, kPairThreads, smem, stream>>>(map_x, map_w, map_r, p);
   return launch_status("conv3d_kdpair_kernel");
 }
 
