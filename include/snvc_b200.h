@@ -260,6 +260,21 @@ int snvc_scale_by_occupancy(const void* vimg, const float* occ, void* dst, int64
 int snvc_avgpool_to_bev(const void* x, float* bev, int64_t N, int64_t Dh, int64_t H, int64_t W, int32_t C,
                         int32_t pool, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Host return of a row-masked volume (end-to-end path of the global branch).
+ * Replaces the blocking dense `.cpu()` the reference's driver does on its outputs
+ * (tools/inference_agnostic.py:396) for the lifted voxel grid: rows with valid[r] != 0 are copied to their dense
+ * position in `dst_host_mapped`, rows that were valid in the batch this host buffer held before (prev_valid[r] != 0)
+ * and are not now are zero-filled, all other rows are already zero in the buffer and do not move.  prev_valid is
+ * updated to valid.  A first use of a host buffer passes prev_valid = all ones (every row is written).
+ * src [rows, row_bytes] device; valid, prev_valid [rows] uint8 device; dst_host_mapped: PINNED host memory
+ * (cudaHostAlloc / cudaHostRegister; device-addressable under UVA), same shape as src; row_bytes in {16,32,64,128};
+ * max_blocks: grid size cap (0 = 2 per SM) -- a small grid leaves the SMs to the kernels of the next batch;
+ * moved_bytes: optional device counter (atomicAdd of the bytes written to the host), may be NULL. */
+int snvc_masked_rows_to_host(const void* src, const uint8_t* valid, uint8_t* prev_valid, void* dst_host_mapped,
+                             int64_t rows, int32_t row_bytes, int32_t max_blocks, unsigned long long* moved_bytes,
+                             void* stream);
+
 #ifdef __cplusplus
 }
 #endif

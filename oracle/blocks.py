@@ -137,3 +137,92 @@ class Vernier3D(nn.Module):
         voxel = self.pool_3d(self.conv4(voxel))
         N, Fc, H, W, L = voxel.shape
         return voxel.reshape(N, -1, W, L), occupancy.squeeze(1)
+
+
+# ------------------------------------------------------------------------------------------------ 2-D BEV blocks (N2)
+def _norm2d(ch, gn, groups=32):
+    return nn.GroupNorm(groups, ch) if gn else nn.BatchNorm2d(ch)
+
+
+def convbn(cin, cout, kernel_size, stride, pad, dilation, gn=False, groups=32):
+    """submodule.py:11-29."""
+    return nn.Sequential(
+        nn.Conv2d(cin, cout, kernel_size=kernel_size, stride=stride, padding=dilation if dilation > 1 else pad,
+                  dilation=dilation, bias=False),
+        _norm2d(cout, gn, groups))
+
+
+def _cbr2d(cin, cout, stride, gn=False):
+    """submodule.py:183-195 (get_hg_down_sample_2d) / :321-322: convbn 3x3 + ReLU."""
+    return nn.Sequential(convbn(cin, cout, 3, stride, 1, 1, gn=gn), nn.ReLU(inplace=True))
+
+
+def _deconvbn_2d(cin, cout, gn):
+    """submodule.py:210-221, 335-345: ConvTranspose2d(k3,s2,p1,op1,bias=False) + norm."""
+    return nn.Sequential(nn.ConvTranspose2d(cin, cout, kernel_size=3, padding=1, output_padding=1, stride=2, bias=False),
+                         _norm2d(cout, gn))
+
+
+class Hourglass2d(nn.Module):
+    """submodule.py:317-361 (class ``hourglass2d``)."""
+
+    def __init__(self, inplanes, gn=False):
+        super().__init__()
+        c2 = inplanes * 2
+        self.conv1 = _cbr2d(inplanes, c2, 2, gn)
+        self.conv2 = convbn(c2, c2, 3, 1, 1, 1, gn=gn)
+        self.conv3 = _cbr2d(c2, c2, 2, gn)
+        self.conv4 = _cbr2d(c2, c2, 1, gn)
+        self.conv5 = _deconvbn_2d(c2, c2, gn)
+        self.conv6 = _deconvbn_2d(c2, inplanes, gn)
+
+    def forward(self, x, presqu, postsqu):
+        out = self.conv1(x)
+        pre = self.conv2(out)
+        pre = F.relu(pre + postsqu) if postsqu is not None else F.relu(pre)
+        out = self.conv4(self.conv3(pre))
+        post = F.relu(self.conv5(out) + (presqu if presqu is not None else pre))
+        return self.conv6(post), pre, post
+
+
+class Hourglass2dDownsample16(nn.Module):
+    """submodule.py:270-315 (class ``hourglass2d_downsample_16``)."""
+
+    def __init__(self, inplanes, gn=False):
+        super().__init__()
+        c2 = inplanes * 2
+        self.conv1 = _cbr2d(inplanes, c2, 2, gn)
+        self.conv2 = _cbr2d(c2, c2, 1, gn)
+        for i in (3, 5, 7):
+            setattr(self, f"conv{i}", _cbr2d(c2, c2, 2, gn))
+            setattr(self, f"conv{i + 1}", _cbr2d(c2, c2, 1, gn))
+        for i in (9, 10, 11):
+            setattr(self, f"conv{i}", _deconvbn_2d(c2, c2, gn))
+        self.conv12 = _deconvbn_2d(c2, inplanes, gn)
+
+    def forward(self, x):
+        o2 = self.conv2(self.conv1(x))
+        o4 = self.conv4(self.conv3(o2))
+        o6 = self.conv6(self.conv5(o4))
+        o8 = self.conv8(self.conv7(o6))
+        o10 = self.conv10(self.conv9(o8) + o6)
+        o11 = self.conv11(o10 + o4)
+        return self.conv12(o11 + o2)
+
+
+class VernierBevTail(nn.Module):
+    """The 2-D BEV tail of VernierScale (BEV_type2 / BEV_type3) up to the part heatmaps: layers vernier.py:289-314,
+    forward vernier.py:440-445: conv5 (convbn 3x3 + ReLU) -> hm1 (hourglass2d[_downsample_16]) -> permute(0,1,3,2) -> hm2.
+    Attribute names equal the reference's (conv5, hm1, hm2)."""
+
+    def __init__(self, dim_height=256, num_parts=9, n_sample_w=128, gn=False):
+        super().__init__()
+        self.n_sample_w = n_sample_w
+        self.conv5 = nn.Sequential(convbn(dim_height, 64, 3, 1, 1, 1, gn=gn), nn.ReLU(inplace=True))
+        self.hm1 = Hourglass2d(64, gn) if n_sample_w <= 16 else Hourglass2dDownsample16(64, gn)
+        self.hm2 = nn.Conv2d(64, num_parts, 3, 1, 1, bias=False)
+
+    def forward(self, voxel_bev):
+        x = self.conv5(voxel_bev)
+        x = self.hm1(x, None, None)[0] if self.n_sample_w <= 16 else self.hm1(x)
+        return self.hm2(x.permute(0, 1, 3, 2))

@@ -50,6 +50,7 @@ _SIGS = {
     "snvc_ndhwc_bf16_to_ncdhw_f32": ([_p, _p, _i64, _i64, _i64, _p], _i32),
     "snvc_scale_by_occupancy": ([_p, _p, _p, _i64, _i32, _i32, _i32, _p], _i32),
     "snvc_avgpool_to_bev": ([_p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _p], _i32),
+    "snvc_masked_rows_to_host": ([_p, _p, _p, _p, _i64, _i32, _i32, _p, _p], _i32),
 }
 
 EXPORTS = tuple(_SIGS)

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsnvc_b200.so")
-SOURCES = ["common.cu", "cost_volume.cu", "voxel_sample.cu", "elementwise.cu", "grid_proj.cu", "depth_head.cu", "nms_bev.cu", "conv3d_tcgen05.cu"]
+SOURCES = ["common.cu", "cost_volume.cu", "voxel_sample.cu", "elementwise.cu", "grid_proj.cu", "depth_head.cu", "nms_bev.cu", "host_return.cu", "conv3d_tcgen05.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

@@ -92,11 +92,11 @@ def build_cost_volume_split_bf16(left, right, shift, downsample=1):
     depth (BuildCostVolume_cuda.cu:84-86), so it is written once.  Returns
     (right_vol [N,D,H,W,C] = channels [C,2C) of the full volume, left_planes [N,3,H,W,C] = the left features on three
     identical planes, the input of the depth-invariant part of the first trunk convolution)."""
-    _lib.require_cuda(left, right, shift)
-    if left.dtype != torch.float32 or right.dtype != torch.float32:
+    _check_inputs(left, right, shift)
+    if left.dtype != torch.float32:
         raise RuntimeError("build_cost_volume_split_bf16: fp32 features only")
     ds = int(downsample)
-    left, right, shift = left.contiguous(), right.contiguous(), shift.contiguous().float()
+    left, right, shift = left.contiguous(), right.contiguous(), shift.contiguous()
     N, C, IH, IW = left.shape
     D = shift.size(1)
     H, W = IH // ds, IW // ds

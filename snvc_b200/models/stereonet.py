@@ -105,19 +105,27 @@ class GlobalHotPath(nn.Module):
         x = self.dres1[1].fused(self.dres1[0].fused(x), residual=x, residual_mode=1)
         return self.hg.fused(x, out_residual=x)[0]
 
-    def lift(self, vol, proj, out_dtype=torch.float32, layout_out="NCDHW"):
+    def lift(self, vol, proj, out_dtype=torch.float32, layout_out="NCDHW", return_valid=False):
         return SF.frustum_lift(vol, proj, self.zs, self.ys, self.xs, self.cv_range, self.align_corners,
-                               layout_in="NDHWC", out_dtype=out_dtype, layout_out=layout_out)
+                               layout_in="NDHWC", out_dtype=out_dtype, layout_out=layout_out, return_valid=return_valid)
 
-    def forward(self, left_feat, right_feat, shift, proj, out_dtype=torch.float32, layout_out="NCDHW"):
+    def forward(self, left_feat, right_feat, shift, proj, out_dtype=torch.float32, layout_out="NCDHW", return_valid=False):
         """left_feat/right_feat [N,F,H,W] fp32, shift [N,D] fp32 (>= 0), proj [N,3,4] fp32
-        -> lifted voxels [N,ch,Z,Y,X] (layout_out 'NCDHW') or [N,Z,Y,X,ch] ('NDHWC')."""
+        -> lifted voxels [N,ch,Z,Y,X] (layout_out 'NCDHW') or [N,Z,Y,X,ch] ('NDHWC'); with `return_valid` also the
+        in-frustum mask [N,Z,Y,X] uint8 (voxels with valid == 0 are exactly zero on every channel)."""
         if self.split_supported(shift.shape[1]):
-            right_vol, left_planes = build_cost_volume_split_bf16(left_feat, right_feat, shift, 1)
-            feat = self.trunk_tail(self.trunk_head_split(right_vol, left_planes))
+            try:
+                right_vol, left_planes = build_cost_volume_split_bf16(left_feat, right_feat, shift, 1)
+                feat = self.trunk_tail(self.trunk_head_split(right_vol, left_planes))
+            except RuntimeError as e:
+                # the addend form exists on the CTA-pair kernel only; where cluster launches are unavailable (MIG slice,
+                # < 2 SMs) it reports SNVC_E_UNSUPPORTED (-2) and the materialised 64-channel volume is used instead
+                if "(-2)" not in str(e):
+                    raise
+                feat = self.trunk(build_cost_volume_ndhwc_bf16(left_feat, right_feat, shift, 1))
         else:
             feat = self.trunk(build_cost_volume_ndhwc_bf16(left_feat, right_feat, shift, 1))
-        return self.lift(feat, proj, out_dtype, layout_out)
+        return self.lift(feat, proj, out_dtype, layout_out, return_valid)
 
 
 class GraphedHotPath:
@@ -147,7 +155,7 @@ class GraphedHotPath:
         l, r, sh, pr = self.inputs
         self.split = model.split_supported(depth_bins)
         tail = [lambda: setattr(self, "_feat", model.trunk_tail(self._x1)),
-                lambda: setattr(self, "vox", model.lift(self._feat, pr, out_dtype, layout_out))]
+                lambda: self._set_lift(model.lift(self._feat, pr, out_dtype, layout_out, return_valid=True))]
         if self.split:
             # five stages: the 3-plane addend convolution is part of the first layer but gets its own graph, so that the
             # "conv1" stage is the single large launch a caller may want to time on its own
@@ -181,6 +189,9 @@ class GraphedHotPath:
                 pool = g.pool()
                 self.graphs.append(g)
             self.launches_per_replay = int(L.snvc_launch_count() - n0)
+
+    def _set_lift(self, res):
+        self.vox, self.valid = res                          # voxels + in-frustum mask [N,Z,Y,X] uint8 (static tensors)
 
     def load(self, left_feat, right_feat, shift, proj):
         for d, s in zip(self.inputs, (left_feat, right_feat, shift, proj)):
@@ -235,22 +246,66 @@ class HostPipeline:
 
     The reference moves every batch with blocking `.cuda()` / `.cpu()` calls around the model
     (tools/inference_agnostic.py:389-395, 605-640).  On B200 the lifted volume of 8 pairs is 0.6 GB, so
-    the device-to-host copy (PCIe) takes longer than the whole hot path; this front end therefore runs
+    the device-to-host transfer (PCIe) takes longer than the whole hot path; this front end therefore runs
     three streams -- host-to-device, compute (the caller's current stream), device-to-host -- over
-    `depth` slots so that the copies of batch i-1 / i+1 overlap the kernels of batch i (PCIe is full
-    duplex).  `submit` enqueues one batch and returns immediately; `drain` waits for everything."""
+    `depth` slots so that the transfers of batch i-1 / i+1 overlap the kernels of batch i (PCIe is full
+    duplex).  `submit` enqueues one batch and returns immediately; `drain` waits for everything.
 
-    def __init__(self, model, depth=2, out_dtype=torch.bfloat16, layout_out="NDHWC", graphed=True):
+    Return path (`sparse_return=True`, the default): 42 % of the KITTI voxel grid lies outside the camera frustum and is
+    exactly zero, so only the in-frustum voxel rows cross PCIe: `snvc_masked_rows_to_host` writes them straight into the
+    caller's pinned buffer at their dense positions and zero-fills only rows that held data from the batch the buffer
+    received before (a per-buffer device-side mask remembers which rows are non-zero; the first use of a buffer writes
+    every row).  After `drain()` / the returned event the host buffer equals the dense tensor bit for bit.  Contract:
+    a host output buffer that has been submitted must not be written by anyone else between submits; call
+    `forget(h_out)` (or pass a fresh buffer) if it was.  `sparse_return=False` is the plain dense `cudaMemcpyAsync`."""
+
+    def __init__(self, model, depth=2, out_dtype=torch.bfloat16, layout_out="NDHWC", graphed=True, sparse_return=True,
+                 return_blocks=0):
         """`graphed`: every slot owns a `GraphedHotPath` (captured at the first batch of a new shape); the host then
         issues three copies and one graph launch per batch instead of ~16 kernel launches, which keeps the pipeline
-        PCIe-bound when the host is busy (eager: 240 - 680 pairs/s for the same work, profiles/r01_ab_kw_kd.txt)."""
+        PCIe-bound when the host is busy (eager: 240 - 680 pairs/s for the same work, profiles/r01_ab_kw_kd.txt).
+        `return_blocks`: grid size of the return kernel (0 = library default)."""
         self.model, self.depth, self.out_dtype, self.layout_out = model, depth, out_dtype, layout_out
         dev = next(model.parameters()).device
         self.dev = dev
         self.graphed = graphed
+        self.sparse_return = bool(sparse_return) and layout_out == "NDHWC"
+        self.return_blocks = int(return_blocks)
         self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         self.slots = [dict(inputs=None, computed=None, copied_out=None, graph=None, shape=None) for _ in range(depth)]
         self.n = 0
+        self._prev_valid = {}                                # host buffer (data_ptr, numel) -> device mask of its non-zero rows
+        self.moved_bytes = torch.zeros((), dtype=torch.int64, device=dev)   # bytes the return kernel wrote to the host
+
+    def forget(self, h_out=None):
+        """Drop what the pipeline knows about the contents of `h_out` (all buffers if None): its next use rewrites every row."""
+        if h_out is None:
+            self._prev_valid.clear()
+        else:
+            self._prev_valid.pop((h_out.data_ptr(), h_out.numel()), None)
+
+    def _return(self, vox, valid, h_out):
+        """Enqueue the device-to-host return of `vox` on the current stream (the pipeline's output stream)."""
+        from snvc_b200 import _lib
+        if h_out.numel() != vox.numel():
+            # result stays on the device (valid until the slot's next batch): only a digest -- the first
+            # h_out.numel() values of every pair -- goes back, enough for the host to observe completion
+            h_out.copy_(vox.reshape(vox.shape[0], -1)[:, :h_out.numel() // vox.shape[0]].reshape(h_out.shape), non_blocking=True)
+            return
+        row_bytes = vox.shape[-1] * vox.element_size()
+        if not self.sparse_return or valid is None or row_bytes not in (16, 32, 64, 128) or h_out.dtype != vox.dtype:
+            h_out.copy_(vox, non_blocking=True)
+            return
+        key = (h_out.data_ptr(), h_out.numel())
+        prev = self._prev_valid.get(key)
+        if prev is None or prev.numel() != valid.numel():
+            prev = torch.ones(valid.numel(), dtype=torch.uint8, device=self.dev)     # unknown contents: write every row
+            self._prev_valid[key] = prev
+        with torch.cuda.device(self.dev):
+            st = _lib.lib().snvc_masked_rows_to_host(vox.data_ptr(), valid.data_ptr(), prev.data_ptr(), h_out.data_ptr(),
+                                                     valid.numel(), row_bytes, self.return_blocks,
+                                                     self.moved_bytes.data_ptr(), _lib.stream_ptr())
+        _lib.check(st, "snvc_masked_rows_to_host")
 
     def _submit_graphed(self, slot, h_left, h_right, h_shift, h_proj, h_out):
         cur = torch.cuda.current_stream(self.dev)
@@ -277,21 +332,15 @@ class HostPipeline:
         slot["computed"].record(cur)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(slot["computed"])
-            if h_out.numel() == vox.numel():
-                h_out.copy_(vox, non_blocking=True)
-            else:
-                # result stays on the device (`slot["graph"].vox`, valid until the slot's next batch): only a digest --
-                # the first h_out.numel() values of every pair -- goes back, enough for the host to observe completion
-                h_out.copy_(vox.reshape(vox.shape[0], -1)[:, :h_out.numel() // vox.shape[0]].reshape(h_out.shape),
-                            non_blocking=True)
+            self._return(vox, g.valid, h_out)
             slot["copied_out"] = torch.cuda.Event()
             slot["copied_out"].record(self.s_out)
         return slot["copied_out"]
 
     def submit(self, h_left, h_right, h_shift, h_proj, h_out):
-        """All arguments are pinned host tensors; `h_out` receives the lifted voxels.  (Graphed pipelines only: an
-        `h_out` smaller than the voxel volume receives a per-pair digest instead and the volume stays on the device
-        for an on-device consumer -- the reference's own pipeline feeds it to the RPN without leaving the GPU.)"""
+        """All arguments are pinned host tensors; `h_out` receives the lifted voxels.  (An `h_out` smaller than the voxel
+        volume receives a per-pair digest instead and the volume stays on the device for an on-device consumer -- the
+        reference's own pipeline feeds it to the RPN without leaving the GPU.)"""
         for t in (h_left, h_right, h_shift, h_proj, h_out):
             if t.is_cuda or not t.is_pinned():
                 raise RuntimeError("HostPipeline.submit expects pinned host tensors")
@@ -311,13 +360,14 @@ class HostPipeline:
             ready = torch.cuda.Event()
             ready.record(self.s_in)
         cur.wait_event(ready)
-        vox = self.model(*slot["inputs"], self.out_dtype, self.layout_out)
+        vox, valid = self.model(*slot["inputs"], self.out_dtype, self.layout_out, return_valid=True)
         slot["computed"] = torch.cuda.Event()
         slot["computed"].record(cur)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(slot["computed"])
-            h_out.copy_(vox, non_blocking=True)
+            self._return(vox, valid, h_out)
             vox.record_stream(self.s_out)
+            valid.record_stream(self.s_out)
             slot["copied_out"] = torch.cuda.Event()
             slot["copied_out"].record(self.s_out)
         return slot["copied_out"]

@@ -7,6 +7,7 @@ are not stored: they are regenerated bit-identically from tests/golden/synth.py.
 Reference entry points exercised:
   snvc.models.submodule.hourglass                 (submodule.py:85-168)   bn and gn
   snvc.models.submodule.hourglass_downsample_16   (submodule.py:223-268)
+  snvc.models.submodule.hourglass2d / hourglass2d_downsample_16   (submodule.py:317-361, 270-315)
   snvc.models.vernier.VernierScale.construct_voxel        (vernier.py:323-360)
   snvc.models.vernier.VernierScale.predict_3d_heatmaps    (vernier.py:414-458), BEV_type3
 """
@@ -42,6 +43,18 @@ def case_hourglass(gn):
     out2, pre2, post2 = m(x, pre.clone(), post.clone())
     return dict(out=out.numpy(), pre=pre.numpy(), post=post.numpy(),
                 out2=out2.numpy(), pre2=pre2.numpy(), post2=post2.numpy())
+
+
+def case_hourglass2d():
+    """submodule.hourglass2d (:317-361) and hourglass2d_downsample_16 (:270-315), the 2-D BEV hourglasses."""
+    m = ref_sub.hourglass2d(64, gn=False).eval()
+    m.load_state_dict(synth.det_state_dict(m, 51), strict=True)
+    x = torch.from_numpy(synth.det_uniform((1, 64, 24, 16), 103))
+    out, pre, post = m(x, None, None)
+    m16 = ref_sub.hourglass2d_downsample_16(64, gn=False).eval()
+    m16.load_state_dict(synth.det_state_dict(m16, 52), strict=True)
+    x16 = torch.from_numpy(synth.det_uniform((1, 64, 48, 32), 104))
+    return dict(out=out.numpy(), pre=pre.numpy(), post=post.numpy(), out16=m16(x16).numpy())
 
 
 def case_hg16():
@@ -84,6 +97,15 @@ def case_vernier():
         setattr(sub, p, getattr(m, p))
     new = synth.det_state_dict(sub, 31)
     sd.update(new)
+    # the 2-D BEV tail (conv5 / hm1 / hm2, vernier.py:289-314) and the coordinate head (:68-93) get deterministic
+    # weights as well, so that `ncf` / `coordinates` below are reproducible from synth.py alone
+    tail = torch.nn.Module()
+    for p in ("conv5", "hm1", "hm2"):
+        setattr(tail, p, getattr(m, p))
+    sd.update(synth.det_state_dict(tail, 33))
+    head = torch.nn.Module()
+    head.coord_head = m.coord_head
+    sd.update(synth.det_state_dict(head, 35))
     m.load_state_dict(sd, strict=True)
     N, P = 1, nh * nw * nl
     lf = torch.from_numpy(synth.det_uniform((N, 32, 16, 16), 201))
@@ -136,7 +158,7 @@ def case_grid_proj():
 
 if __name__ == "__main__":
     cases = {"hourglass_bn": lambda: case_hourglass(False), "hourglass_gn": lambda: case_hourglass(True),
-             "hg16_bn": case_hg16, "vernier_bev3": case_vernier, "grid_proj": case_grid_proj}
+             "hg16_bn": case_hg16, "hourglass2d_bn": case_hourglass2d, "vernier_bev3": case_vernier, "grid_proj": case_grid_proj}
     if len(sys.argv) > 1:
         cases = {k: v for k, v in cases.items() if k in sys.argv[1:]}
     for name, fn in cases.items():

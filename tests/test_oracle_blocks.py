@@ -68,3 +68,22 @@ def test_vernier3d_matches_reference(golden):
     bev, occ = m(vox)
     _close(bev, g["voxel_bev"], 2e-5)
     _close(occ, g["occupancy"], 2e-5)
+
+
+def test_hourglass2d_matches_reference(golden):
+    g = golden("hourglass2d_bn")
+    m = blocks.Hourglass2d(64).eval()
+    m.load_state_dict(synth.det_state_dict(m, 51), strict=True)
+    out, pre, post = m(torch.from_numpy(synth.det_uniform((1, 64, 24, 16), 103)), None, None)
+    _close(out, g["out"]); _close(pre, g["pre"]); _close(post, g["post"])
+    m16 = blocks.Hourglass2dDownsample16(64).eval()
+    m16.load_state_dict(synth.det_state_dict(m16, 52), strict=True)
+    _close(m16(torch.from_numpy(synth.det_uniform((1, 64, 48, 32), 104))), g["out16"])
+
+
+def test_vernier_bev_tail_matches_reference(golden):
+    """conv5 -> hm1 -> permute -> hm2 on the reference's own voxel_BEV reproduces the reference's heatmaps (`ncf`)."""
+    g = golden("vernier_bev3")
+    tail = blocks.VernierBevTail(128, 9, n_sample_w=32).eval()
+    tail.load_state_dict(synth.det_state_dict(tail, 33), strict=True)
+    _close(tail(torch.from_numpy(g["voxel_bev"])), g["ncf"], 2e-5)
