@@ -201,6 +201,61 @@ int snvc_conv3d_fwd_addend(const void* x, const void* w_packed, const float* sca
                            const float* addend, void* y, const snvc_conv3d_desc* desc, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * A2a  GroupNorm variant of convbn_3d / convbn (`gn=True` -> nn.GroupNorm(32, C): snvc/models/submodule.py:28,49,135,146).
+ * x [N, S, C] fp32 channels-last (the convolution's fp32 result, S = D*H*W or H*W); gamma, beta [C] (NULL = 1 / 0);
+ * y = act( GN(x) [+ residual] ) [+ residual] written as bf16 | fp32 into the channel slice [out_coffset, +C) of rows of
+ * out_cstride channels; residual: bf16 rows of res_cstride channels.  workspace: snvc_group_norm_workspace_bytes bytes.
+ * Three launches (partial sums without atomics, finalize, apply): deterministic. */
+int64_t snvc_group_norm_workspace_bytes(int64_t N, int64_t S, int32_t C);
+int snvc_group_norm_fwd(const float* x, const float* gamma, const float* beta, const void* residual, void* y,
+                        void* workspace, int64_t N, int64_t S, int32_t C, int32_t groups, float eps, int32_t relu,
+                        int32_t residual_mode, int32_t sigmoid, int32_t out_dtype, int32_t out_cstride,
+                        int32_t out_coffset, int32_t res_cstride, int32_t res_coffset, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * N2  2-D convolutions of the BEV tails (tcgen05 / TMEM implicit GEMM with a K loop over taps x 64-channel chunks).
+ * Replaces the cuDNN calls behind nn.Conv2d / nn.ConvTranspose2d + BatchNorm2d(eval) + ReLU + skip adds of
+ *   convbn                      snvc/models/submodule.py:11-29
+ *   hourglass2d                 snvc/models/submodule.py:317-361
+ *   hourglass2d_downsample_16   snvc/models/submodule.py:270-315 (helpers :183-195, :210-221)
+ *   conv5 / hm1 / hm2           snvc/models/vernier.py:289-314, 440-445
+ * Activations NHWC bf16; Cin any multiple of 8 >= 64 (or 16 / 32 / 48), Cout <= 256.
+ */
+typedef struct snvc_conv2d_desc {
+  int32_t N;
+  int32_t Cin, Cout;
+  int32_t Hi, Wi;            /* input spatial extent */
+  int32_t Ho, Wo;            /* output spatial extent */
+  int32_t kernel;            /* square kernel size k (1 or 3) */
+  int32_t stride;            /* 1 or 2 */
+  int32_t pad;
+  int32_t dilation;
+  int32_t transposed;        /* 1: ConvTranspose2d(k=3, s=2, p=1, output_padding=1) */
+  int32_t relu;
+  int32_t residual_mode;     /* 0 none, 1 add before ReLU, 2 add after ReLU */
+  int32_t sigmoid;
+  int32_t out_dtype;         /* SNVC_BF16 | SNVC_F32 */
+  int32_t out_cstride;       /* channel stride of y's innermost dim (>= Cout); 0 -> Cout */
+  int32_t out_coffset;
+  int32_t res_cstride;       /* same for the residual tensor; 0 -> Cout */
+  int32_t res_coffset;
+  int32_t in_cstride;        /* channel stride of x's innermost dim (>= Cin); 0 -> Cin */
+  int32_t in_coffset;        /* first channel read inside that stride (multiple of 8) */
+  int32_t reserved[2];
+} snvc_conv2d_desc;
+
+/* w: Conv2d [Cout,Cin,k,k] fp32 (transposed=0) or ConvTranspose2d [Cin,Cout,k,k] fp32 (transposed=1), DEVICE pointer.
+ * w_packed: [k*k][ceil(Cin/cc)][Cout_pad][cc] bf16, cc = 64 (Cin >= 64) | 32 | 16, Cout_pad = roundup(Cout,16),
+ * zero-padded in both channel dimensions. */
+int64_t snvc_conv2d_packed_weight_bytes(int32_t Cin, int32_t Cout, int32_t kernel);
+int snvc_conv2d_pack_weights(const float* w, void* w_packed, int32_t Cin, int32_t Cout, int32_t kernel,
+                             int32_t transposed, void* stream);
+/* x [N,Hi,Wi,Cin] bf16; scale,bias [Cout] fp32 (folded eval-mode BatchNorm2d; NULL = 1 / 0); residual: NHWC bf16 with the
+ * output's spatial shape, or NULL; y: NHWC.   y = act( scale * conv(x) + bias [+ residual] ) [+ residual] */
+int snvc_conv2d_fwd(const void* x, const void* w_packed, const float* scale, const float* bias,
+                    const void* residual, void* y, const snvc_conv2d_desc* desc, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * N1  projection of the instance sampling grid into the left / right ROI frames.
  * Replaces refinementDataset._generate_grid_proj, the per-proposal numpy float64 loop upstream of A3
  *   snvc/dataset/KITTIRefinement_dataset.py:847-868 (_to_cam :828-845, _init_3d_grid :267-282)
@@ -259,6 +314,12 @@ int snvc_scale_by_occupancy(const void* vimg, const float* occ, void* dst, int64
  * x [N,Dh,H,W,C] bf16 NDHWC -> bev [N, C*(Dh/pool), H, W] fp32 (channel index c*(Dh/pool)+dh). */
 int snvc_avgpool_to_bev(const void* x, float* bev, int64_t N, int64_t Dh, int64_t H, int64_t W, int32_t C,
                         int32_t pool, void* stream);
+/* Same pooling, emitted channels-last in bf16 for the 2-D tensor-core convs, over either of the first two spatial axes:
+ * x [N,S0,S1,S2,C] bf16 -> bev [N, R0, S2, C*Q] bf16 with Q = S_axis/pool (<= 8), R0 = the other of (S0, S1), channel index
+ * c*Q + q.  axis 0: the instance branch (pool the height axis nh, vernier.py:436-438); axis 1: the global branch's lifted
+ * grid [N,Z,Y,X,C] pooled over Y (restated RPN side). */
+int snvc_avgpool_to_bev_nhwc(const void* x, void* bev, int64_t N, int64_t S0, int64_t S1, int64_t S2, int32_t C,
+                             int32_t pool, int32_t axis, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Host return of a row-masked volume (end-to-end path of the global branch).

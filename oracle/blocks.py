@@ -226,3 +226,35 @@ class VernierBevTail(nn.Module):
         x = self.conv5(voxel_bev)
         x = self.hm1(x, None, None)[0] if self.n_sample_w <= 16 else self.hm1(x)
         return self.hm2(x.permute(0, 1, 3, 2))
+
+
+class RPN3DHead(nn.Module):
+    """Restated RPN side of the global branch, plain torch: the shipped blocks convbn_3d
+    (submodule.py:32-50), hourglass (:85-168), AvgPool3d + reshape to BEV (vernier.py:289,436-438), convbn (:11-29),
+    hourglass2d (:317-361) and 3x3 Conv2d heads with the output conventions of RPN3DLoss (loss3d.py:84-103,253-275).
+    Input: lifted voxels [N, C, Z, Y, X]; the pooled axis is Y."""
+
+    def __init__(self, channels=32, n_y=20, pool=4, bev_dim=64, num_angles=4, num_classes=1, reg_dim=7, gn=False):
+        super().__init__()
+        A = num_angles * num_classes
+        self.pool = pool
+        self.rpn3d_conv = _cbr(channels, channels, 3, 1, 1, gn=gn)
+        self.rpn3d_conv2 = Hourglass(channels, gn=gn)
+        self.rpn3d_conv3 = _cbr2d(channels * (n_y // pool), bev_dim, 1, gn)
+        self.rpn3d_conv4 = Hourglass2d(bev_dim, gn=gn)
+        self.rpn3d_cls_convs = _cbr2d(bev_dim, bev_dim, 1, gn)
+        self.rpn3d_bbox_convs = _cbr2d(bev_dim, bev_dim, 1, gn)
+        self.bbox_cls = nn.Conv2d(bev_dim, A, 3, 1, 1)
+        self.bbox_reg = nn.Conv2d(bev_dim, A * reg_dim, 3, 1, 1)
+        self.bbox_centerness = nn.Conv2d(bev_dim, A, 3, 1, 1)
+
+    def forward(self, vox):
+        x = self.rpn3d_conv(vox)
+        x = self.rpn3d_conv2(x, None, None)[0] + x
+        x = x.permute(0, 1, 3, 2, 4)                                   # [N, C, Y, Z, X]: pool the height axis
+        x = F.avg_pool3d(x, (self.pool, 1, 1), stride=(self.pool, 1, 1))
+        N, C, Yq, Z, X = x.shape
+        b = self.rpn3d_conv3(x.reshape(N, C * Yq, Z, X))
+        b = self.rpn3d_conv4(b, None, None)[0] + b
+        c, r = self.rpn3d_cls_convs(b), self.rpn3d_bbox_convs(b)
+        return self.bbox_cls(c), self.bbox_reg(r), self.bbox_centerness(r)

@@ -20,8 +20,10 @@
  * See DESIGN.md "parity pinning".
  *
  * `fma_mode`: the reference is compiled by nvcc with the default -fmad=true, so
- * `w1*v1 + w2*v2 + w3*v3 + w4*v4` becomes  fma(w4,v4, fma(w3,v3, fma(w2,v2, w1*v1))).
- * fma_mode=1 reproduces that contraction (bit-exact target for the CUDA kernel);
+ * `w1*v1 + w2*v2 + w3*v3 + w4*v4` becomes  fma(w4,v4, fma(w3,v3, fma(w1,v1, w2*v2))): the SECOND product is the
+ * rounded one (SASS of the reference kernel as built by oracle/build_ref.py: FMUL v2*w2; FFMA v1,w1; FFMA v3,w3;
+ * FFMA v4,w4 -- same order in the fp64 instantiation).  fma_mode=1 reproduces that contraction and is checked bit
+ * for bit against the reference op on the GPU (tests/test_gpu_ref_pin.py);
  * fma_mode=0 rounds every product and sum separately (what a plain C/NumPy
  * transcription gives; differs by <= 1 ulp).
  *
@@ -57,8 +59,8 @@
     volatile T w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;                    \
     /* .cu:58 */                                                                          \
     if (fma_mode) {                                                                       \
-      volatile T t = w1 * v1;                                                             \
-      t = FMA(w2, v2, t);                                                                 \
+      volatile T t = w2 * v2;                                                             \
+      t = FMA(w1, v1, t);                                                                 \
       t = FMA(w3, v3, t);                                                                 \
       t = FMA(w4, v4, t);                                                                 \
       return t;                                                                           \

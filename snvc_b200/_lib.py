@@ -21,6 +21,13 @@ class ConvDesc(ctypes.Structure):
         "res_cstride", "res_coffset", "in_cstride", "in_coffset")] + [("reserved", _i32 * 2)]
 
 
+class Conv2dDesc(ctypes.Structure):
+    _fields_ = [(n, _i32) for n in (
+        "N", "Cin", "Cout", "Hi", "Wi", "Ho", "Wo", "kernel", "stride", "pad", "dilation", "transposed", "relu",
+        "residual_mode", "sigmoid", "out_dtype", "out_cstride", "out_coffset", "res_cstride", "res_coffset",
+        "in_cstride", "in_coffset")] + [("reserved", _i32 * 2)]
+
+
 _SIGS = {
     "snvc_version": ([], _i32),
     "snvc_last_error": ([], ctypes.c_char_p),
@@ -46,10 +53,16 @@ _SIGS = {
     "snvc_conv3d_pack_weights": ([_p, _p, _i32, _i32, _i32, _i32, _p], _i32),
     "snvc_conv3d_fwd": ([_p, _p, _p, _p, _p, _p, ctypes.POINTER(ConvDesc), _p], _i32),
     "snvc_conv3d_fwd_addend": ([_p, _p, _p, _p, _p, _p, ctypes.POINTER(ConvDesc), _p], _i32),
+    "snvc_group_norm_workspace_bytes": ([_i64, _i64, _i32], _i64),
+    "snvc_group_norm_fwd": ([_p, _p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _f] + [_i32] * 8 + [_p], _i32),
+    "snvc_conv2d_packed_weight_bytes": ([_i32, _i32, _i32], _i64),
+    "snvc_conv2d_pack_weights": ([_p, _p, _i32, _i32, _i32, _i32, _p], _i32),
+    "snvc_conv2d_fwd": ([_p, _p, _p, _p, _p, _p, ctypes.POINTER(Conv2dDesc), _p], _i32),
     "snvc_ncdhw_f32_to_ndhwc_bf16": ([_p, _p, _i64, _i64, _i64, _p], _i32),
     "snvc_ndhwc_bf16_to_ncdhw_f32": ([_p, _p, _i64, _i64, _i64, _p], _i32),
     "snvc_scale_by_occupancy": ([_p, _p, _p, _i64, _i32, _i32, _i32, _p], _i32),
     "snvc_avgpool_to_bev": ([_p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _p], _i32),
+    "snvc_avgpool_to_bev_nhwc": ([_p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _p], _i32),
     "snvc_masked_rows_to_host": ([_p, _p, _p, _p, _i64, _i32, _i32, _p, _p], _i32),
 }
 

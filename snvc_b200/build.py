@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsnvc_b200.so")
-SOURCES = ["common.cu", "cost_volume.cu", "voxel_sample.cu", "elementwise.cu", "grid_proj.cu", "depth_head.cu", "nms_bev.cu", "host_return.cu", "conv3d_tcgen05.cu"]
+SOURCES = ["common.cu", "cost_volume.cu", "voxel_sample.cu", "elementwise.cu", "grid_proj.cu", "depth_head.cu", "nms_bev.cu", "host_return.cu", "group_norm.cu", "conv2d_tcgen05.cu", "conv3d_tcgen05.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 
@@ -44,9 +44,10 @@ def build(force=False, verbose=False):
     for s in srcs:
         o = os.path.join(HERE, "build", os.path.basename(s) + ".o")
         objs.append(o)
+        headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
         if not force and os.path.exists(o) and os.path.getmtime(o) > max(
-                os.path.getmtime(s), os.path.getmtime(os.path.join(CSRC, "common.cuh")),
-                os.path.getmtime(os.path.join(HERE, "..", "include", "snvc_b200.h"))):
+                [os.path.getmtime(s), os.path.getmtime(os.path.join(HERE, "..", "include", "snvc_b200.h"))] +
+                [os.path.getmtime(h) for h in headers]):
             continue
         cmd = [_nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -10,7 +10,10 @@
 //                        (halves the dominant write stream).
 // Arithmetic is written with explicit round-to-nearest intrinsics so that the result is
 // bit-identical to the nvcc-compiled reference expression  w1*v1 + w2*v2 + w3*v3 + w4*v4
-// (-fmad=true => fma(w2,v2, w1*v1); the w3/w4 terms are exact zeros because y is an integer).
+// as nvcc contracts it with its default -fmad=true: fma(w1, v1, w2*v2) -- the SECOND product is rounded, the first
+// is fused (read off the SASS of the reference kernel compiled by oracle/build_ref.py: FMUL v2*w2; FFMA v1*w1 + .;
+// tests/test_gpu_ref_pin.py compares against that build bit for bit); the w3/w4 terms are exact zeros because y is
+// an integer.
 #include <cmath>
 
 #include "common.cuh"
@@ -53,7 +56,7 @@ __device__ __forceinline__ bool sample_pos(int iw, T neg_shift, int img_w, int& 
 template <typename T>
 __device__ __forceinline__ T interp(T lx, T v1, T v2) {
   T hx = Arith<T>::sub((T)1, lx);
-  return Arith<T>::fma(lx, v2, Arith<T>::mul(hx, v1));
+  return Arith<T>::fma(hx, v1, Arith<T>::mul(lx, v2));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -283,7 +286,7 @@ cv_ndhwc_bf16_kernel(const float* __restrict__ left, const float* __restrict__ r
         const float hx = __fsub_rn(1.f, lx);
         float r[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = __fmaf_rn(lx, r1[j], __fmul_rn(hx, r0[j]));
+        for (int j = 0; j < 8; ++j) r[j] = __fmaf_rn(hx, r0[j], __fmul_rn(lx, r1[j]));
         v = make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7]));
       }
       *reinterpret_cast<uint4*>(o + roff) = v;
@@ -375,7 +378,7 @@ cv_split_bf16_kernel(const float* __restrict__ left, const float* __restrict__ r
     __nv_bfloat16* o = right_vol + ((((int64_t)n * D + d0 + dd) * H + ph) * W + w_begin) * C + cg * 8;
     // Two register sets that swap roles every step (the step is unrolled by two), so that the column shared by two
     // consecutive steps is never moved; values as packed fp32 pairs: one FMUL2 + one FFMA2 per two channels, the same
-    // roundings as the scalar hx*v1 then fma(lx, v2, .) (ncu on the first version: 88 instructions per warp step,
+    // roundings as the scalar lx*v2 then fma(hx, v1, .) (ncu on the first version: 88 instructions per warp step,
     // issue slots 79 % busy -- the kernel was issue-bound at 64 % of the HBM peak).
     int held = -0x40000000;                             // column held in the set that is "high" after the last step
     float2 ra[4], rb[4];
@@ -402,7 +405,7 @@ cv_split_bf16_kernel(const float* __restrict__ left, const float* __restrict__ r
         const float2 lx2 = make_float2(lx, lx), hx2 = make_float2(hx, hx);
         float2 r[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) r[j] = __ffma2_rn(lx2, hi[j], __fmul2_rn(hx2, lo[j]));
+        for (int j = 0; j < 4; ++j) r[j] = __ffma2_rn(hx2, lo[j], __fmul2_rn(lx2, hi[j]));
         v = make_uint4(pack_bf16x2(r[0].x, r[0].y), pack_bf16x2(r[1].x, r[1].y), pack_bf16x2(r[2].x, r[2].y),
                        pack_bf16x2(r[3].x, r[3].y));
       } else {

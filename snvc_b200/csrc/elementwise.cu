@@ -82,10 +82,72 @@ avgpool_bev_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ bev,
   }
 }
 
+// x [N,S0,S1,S2,C] bf16 -> bev [N, R0, R2, C*Q] bf16 (NHWC for the 2-D tensor-core convs), Q = S_axis / pool,
+// channel index c*Q + q (the reference's reshape of the pooled NCDHW tensor: vernier.py:436-438).
+// One thread per (n, r0, r2, 8-channel group): `pool` 16-byte loads per q, Q results per channel kept in registers and
+// written as one run of Q consecutive bf16 per channel.
+template <int AXIS>
+__global__ void __launch_bounds__(256)
+avgpool_bev_nhwc_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ bev, int64_t total, int S0, int S1,
+                        int S2, int C, int pool) {
+  const int CG = C >> 3;
+  const int Sax = AXIS == 0 ? S0 : S1;
+  const int Q = Sax / pool;
+  const int R0 = AXIS == 0 ? S1 : S0;
+  const float inv = 1.f / (float)pool;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % CG);
+    int64_t t = i / CG;
+    const int r2 = (int)(t % S2); t /= S2;
+    const int r0 = (int)(t % R0);
+    const int64_t n = t / R0;
+    float acc[8][8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (q >= Q) break;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[q][j] = 0.f;
+      for (int k = 0; k < pool; ++k) {
+        const int a = q * pool + k;
+        const int64_t vox = AXIS == 0 ? (((n * S0 + a) * S1 + r0) * S2 + r2) : (((n * S0 + r0) * S1 + a) * S2 + r2);
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + vox * C + cg * 8));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[q][2 * j] += bf16_lo(w[j]); acc[q][2 * j + 1] += bf16_hi(w[j]); }
+      }
+    }
+    __nv_bfloat16* o = bev + ((n * R0 + r0) * S2 + r2) * ((int64_t)C * Q) + (int64_t)cg * 8 * Q;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (q < Q) o[j * Q + q] = __float2bfloat16_rn(acc[q][j] * inv);
+  }
+}
+
 }  // namespace
 }  // namespace snvc
 
 using namespace snvc;
+
+extern "C" int snvc_avgpool_to_bev_nhwc(const void* x, void* bev, int64_t N, int64_t S0, int64_t S1, int64_t S2, int32_t C,
+                                        int32_t pool, int32_t axis, void* stream) {
+  if (N * S0 * S1 * S2 == 0) return 0;
+  SNVC_CHECK_ARG(x && bev, "null pointer");
+  SNVC_CHECK_ARG(axis == 0 || axis == 1, "axis must be 0 or 1");
+  const int64_t Sax = axis == 0 ? S0 : S1;
+  SNVC_CHECK_ARG(pool >= 1 && Sax % pool == 0 && Sax / pool <= 8, "pooled axis must be a multiple of pool with at most 8 windows");
+  SNVC_CHECK_ARG(C % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "C must be a multiple of 8 and x 16-byte aligned");
+  const int64_t total = N * (axis == 0 ? S1 : S0) * S2 * (C / 8);
+  const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), (int64_t)sm_count() * 16);
+  if (axis == 0)
+    avgpool_bev_nhwc_kernel<0><<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)bev, total, (int)S0,
+                                                                        (int)S1, (int)S2, C, pool);
+  else
+    avgpool_bev_nhwc_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)bev, total, (int)S0,
+                                                                        (int)S1, (int)S2, C, pool);
+  return launch_status("avgpool_bev_nhwc_kernel");
+}
 
 extern "C" int snvc_ncdhw_f32_to_ndhwc_bf16(const float* src, void* dst, int64_t N, int64_t C, int64_t S, void* stream) {
   if (N * C * S == 0) return 0;

@@ -234,6 +234,43 @@ def depth_regression_from_logits(logits, depth_values, out_size, align_corners=T
     return out
 
 
+# ------------------------------------------------------------------------------------ GroupNorm (gn=True blocks)
+def group_norm_act(x, norm, *, relu=False, residual=None, residual_mode=0, sigmoid=False, out_dtype=torch.bfloat16,
+                   out=None, out_coffset=0, res_coffset=0):
+    """nn.GroupNorm `norm` (+ skip add, ReLU, sigmoid) on a channels-last fp32 tensor x [N, ..., C] (the fp32 result of a
+    bias-free conv: convbn_3d / convbn with gn=True, submodule.py:28,49) -> [N, ..., C] `out_dtype`, or the channel slice
+    [out_coffset, +C) of `out`.  residual: bf16 channels-last; mode 1 = add before ReLU, 2 = after."""
+    _lib.require_cuda(x)
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        raise RuntimeError("group_norm_act: contiguous channels-last fp32 input expected")
+    N, C = x.shape[0], x.shape[-1]
+    S = x.numel() // (N * C) if N * C else 0
+    if out is None:
+        out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    elif tuple(out.shape[:-1]) != tuple(x.shape[:-1]) or not out.is_contiguous() or out.shape[-1] < out_coffset + C \
+            or out.dtype not in (torch.bfloat16, torch.float32):
+        raise RuntimeError("group_norm_act: bad `out` tensor")
+    if residual is not None:
+        if residual_mode == 0:
+            residual_mode = 1
+        if residual.dtype != torch.bfloat16 or tuple(residual.shape[:-1]) != tuple(x.shape[:-1]) or not residual.is_contiguous() \
+                or residual.shape[-1] < res_coffset + C:
+            raise RuntimeError("group_norm_act: residual must be contiguous channels-last bf16 with the input's spatial shape")
+    L = _lib.lib()
+    ws = torch.empty(max(16, L.snvc_group_norm_workspace_bytes(N, S, C)), dtype=torch.uint8, device=x.device)
+    g = norm.weight.detach().float().contiguous() if norm.weight is not None else None
+    b = norm.bias.detach().float().contiguous() if norm.bias is not None else None
+    with torch.cuda.device(x.device):
+        st = L.snvc_group_norm_fwd(x.data_ptr(), g.data_ptr() if g is not None else None, b.data_ptr() if b is not None else None,
+                                   residual.data_ptr() if residual is not None else None, out.data_ptr(), ws.data_ptr(), N, S, C,
+                                   int(norm.num_groups), float(norm.eps), int(relu),
+                                   int(residual_mode if residual is not None else 0), int(sigmoid),
+                                   _lib.BF16 if out.dtype == torch.bfloat16 else _lib.F32, out.shape[-1], out_coffset,
+                                   residual.shape[-1] if residual is not None else 0, res_coffset, _lib.stream_ptr())
+    _lib.check(st, "snvc_group_norm_fwd")
+    return out
+
+
 # ------------------------------------------------------------------------------------ layouts
 def to_ndhwc_bf16(x):
     """[N,C,D,H,W] fp32 -> [N,D,H,W,C] bf16."""

@@ -241,6 +241,115 @@ class DepthHead(nn.Module):
                                                self.align_corners)
 
 
+class RPN3DHead(nn.Module):
+    """RPN side of the global branch, downstream of the lift (restated wiring of the DSGN lineage,
+    README.md:68, out of blocks the reference ships):
+        rpn3d_conv   = convbn_3d(C, C, 3, 1, 1) + ReLU          submodule.py:32-50          on the lifted grid [N,Z,Y,X,C]
+        rpn3d_conv2  = hourglass(C)(x, None, None)[0] + x       submodule.py:85-168
+        rpn3d_pool   = AvgPool3d((4,1,1)) over Y, reshape to BEV [N, C*Y/4, Z, X]   (the op of vernier.py:289,436-438)
+        rpn3d_conv3  = convbn(C*Y/4, B, 3, 1, 1, 1) + ReLU      submodule.py:11-29
+        rpn3d_conv4  = hourglass2d(B)(x, None, None)[0] + x     submodule.py:317-361
+        cls / reg towers = convbn(B, B) + ReLU; heads bbox_cls [A*K], bbox_reg [A*R], bbox_centerness [A*K] = Conv2d 3x3
+    with A = cfg.num_angles, K = cfg.num_classes, R = 24 | 7 (cfg.box_corner_parameters), the output conventions RPN3DLoss
+    consumes (loss3d.py:84-103,253-275); BEV cell (z, x) <-> compute_locations_bev (torch_utils.py:77-98).
+    Everything runs on the tcgen05 kernels: 3-D convs, the Y-pool into channels-last BEV, 2-D convs with the K loop over
+    the 160 BEV channels."""
+
+    def __init__(self, cfg, channels=32, n_y=20, pool=4):
+        super().__init__()
+        from snvc_b200.models.submodule import _cbr2d, hourglass2d
+        gn = bool(getattr(cfg, "GN", False))
+        B = 2 * int(getattr(cfg, "RPN_CONVDIM", 32))
+        self.pool = pool
+        self.num_angles, self.num_classes = int(getattr(cfg, "num_angles", 4)), int(getattr(cfg, "num_classes", 1))
+        self.reg_dim = 24 if getattr(cfg, "box_corner_parameters", False) else 7
+        A = self.num_angles * self.num_classes
+        self.rpn3d_conv = _cbr(channels, channels, 3, 1, 1, gn=gn)
+        self.rpn3d_conv2 = hourglass(channels, gn=gn)
+        self.rpn3d_conv3 = _cbr2d(channels * (n_y // pool), B, 1, gn)
+        self.rpn3d_conv4 = hourglass2d(B, gn=gn)
+        self.rpn3d_cls_convs = _cbr2d(B, B, 1, gn)
+        self.rpn3d_bbox_convs = _cbr2d(B, B, 1, gn)
+        self.bbox_cls = nn.Conv2d(B, A, 3, 1, 1)
+        self.bbox_reg = nn.Conv2d(B, A * self.reg_dim, 3, 1, 1)
+        self.bbox_centerness = nn.Conv2d(B, A, 3, 1, 1)
+
+    def _head(self, conv):
+        from snvc_b200.conv import PackedConv2d
+        vers = (conv.weight.data_ptr(), conv.weight._version, conv.bias._version, str(conv.weight.device))
+        cache = self.__dict__.get("_heads", {})
+        hit = cache.get(id(conv))
+        if hit is None or hit[0] != vers:
+            hit = (vers, PackedConv2d(conv.weight, None, bias=conv.bias, stride=1, pad=1))
+            cache = dict(cache)
+            cache[id(conv)] = hit
+            object.__setattr__(self, "_heads", cache)
+        return hit[1]
+
+    def bev_features(self, vox):
+        """vox [N,Z,Y,X,C] bf16 channels-last (the lifted grid) -> BEV features [N,Z,X,B] bf16 channels-last."""
+        from snvc_b200 import _lib
+        x = self.rpn3d_conv.fused(vox)
+        x = self.rpn3d_conv2.fused(x, out_residual=x)[0]
+        N, Z, Y, X, C = x.shape
+        bev = torch.empty((N, Z, X, C * (Y // self.pool)), dtype=torch.bfloat16, device=x.device)
+        with torch.cuda.device(x.device):
+            st = _lib.lib().snvc_avgpool_to_bev_nhwc(x.data_ptr(), bev.data_ptr(), N, Z, Y, X, C, self.pool, 1, _lib.stream_ptr())
+        _lib.check(st, "snvc_avgpool_to_bev_nhwc")
+        b = self.rpn3d_conv3.fused(bev)
+        return self.rpn3d_conv4.fused(b, out_residual=b)[0]
+
+    def forward(self, vox):
+        """-> (bbox_cls [N,A*K,Z,X], bbox_reg [N,A*R,Z,X], bbox_centerness [N,A*K,Z,X]) fp32, NCHW views of channels-last
+        results (what RPN3DLoss / the proposal decoder index)."""
+        b = self.bev_features(vox)
+        c, r = self.rpn3d_cls_convs.fused(b), self.rpn3d_bbox_convs.fused(b)
+        cls = self._head(self.bbox_cls)(c, out_dtype=torch.float32)
+        reg = self._head(self.bbox_reg)(r, out_dtype=torch.float32)
+        ctr = self._head(self.bbox_centerness)(r, out_dtype=torch.float32)
+        return cls.permute(0, 3, 1, 2), reg.permute(0, 3, 1, 2), ctr.permute(0, 3, 1, 2)
+
+
+def decode_proposals(bbox_cls, bbox_reg, bbox_centerness, cfg, anchor_size=(1.56, 1.6, 3.9), anchor_y=1.0, pre_nms=512,
+                     iou_thresh=0.25):
+    """BEV head outputs -> rotated-NMS'd proposals per pair, entirely on the device (no host synchronisation): scores
+    sigmoid(cls) * sigmoid(centerness) per (cell, angle anchor), the `pre_nms` best are decoded as
+    [x + dx, y_a + dy, z + dz, h * e^dh, w * e^dw, l * e^dl, angle_a + dtheta] around compute_locations_bev
+    (torch_utils.py:77-98; 7-parameter regression, loss3d.py:101) and passed to the rotated BEV NMS (snvc_nms_bev, N4).
+    Returns (boxes [N, pre_nms, 7] in score order, scores [N, pre_nms], keep [N, pre_nms] int64 kept positions padded
+    with -1, num_keep [N] int32).  Restated decoder: the reference ships the heads' loss, not a decoder."""
+    N, AK, Z, X = bbox_cls.shape
+    A = AK
+    dev = bbox_cls.device
+    zs = voxel_centres(cfg.Z_MIN, cfg.Z_MAX, cfg.VOXEL_Z_SIZE).to(dev)
+    xs = voxel_centres(cfg.X_MIN, cfg.X_MAX, cfg.VOXEL_X_SIZE).to(dev)
+    angles = torch.arange(A, device=dev, dtype=torch.float32) * (np.pi / A)
+    score = (torch.sigmoid(bbox_cls) * torch.sigmoid(bbox_centerness)).reshape(N, -1)          # [N, A*Z*X]
+    k = min(pre_nms, score.shape[1])
+    top, idx = score.topk(k, dim=1)
+    a = idx // (Z * X)
+    cell = idx % (Z * X)
+    zi, xi = cell // X, cell % X
+    reg = bbox_reg.reshape(N, A, -1, Z * X)                                                      # [N, A, R, Z*X]
+    R = reg.shape[2]
+    sel = reg[torch.arange(N, device=dev)[:, None], a, :, cell]                                  # [N, k, R]
+    if R != 7:
+        raise RuntimeError("decode_proposals: 7-parameter regression expected (cfg.box_corner_parameters = False)")
+    h0, w0, l0 = anchor_size
+    boxes = torch.stack([xs[xi] + sel[..., 0], anchor_y + sel[..., 1], zs[zi] + sel[..., 2],
+                         l0 * torch.exp(sel[..., 5].clamp(-2, 2)), w0 * torch.exp(sel[..., 4].clamp(-2, 2)),
+                         h0 * torch.exp(sel[..., 3].clamp(-2, 2)), angles[a] + sel[..., 6]], dim=-1)
+    # BEV NMS works on [x, y(bev) = z, z, dx, dy, dz, heading]: put the ground-plane axes first
+    bev_boxes = torch.stack([boxes[..., 0], boxes[..., 2], boxes[..., 1], boxes[..., 3], boxes[..., 4], boxes[..., 5],
+                             boxes[..., 6]], dim=-1).contiguous()
+    keeps, nums = [], []
+    for n in range(N):
+        sel_n, num = SF.nms_gpu_device(bev_boxes[n], top[n], iou_thresh)
+        keeps.append(sel_n)
+        nums.append(num)
+    return boxes, top, torch.stack(keeps), torch.stack(nums)
+
+
 class HostPipeline:
     """Host-buffer front end of `GlobalHotPath`: batches come from / go back to PINNED host memory.
 

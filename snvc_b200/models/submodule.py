@@ -13,15 +13,14 @@ activations.  Tensor kinds at module boundaries:
   * bf16 `torch.channels_last_3d` input -> consumed zero-copy, output is bf16 channels_last_3d
     (chain modules this way to stay in the kernel layout).
 Inference only (BatchNorm must be in eval mode, as in tools/inference_agnostic.py:471).
-GroupNorm (`gn=True`) is supported for correctness: conv on the tensor cores, then the
-normalisation over the channels-last result.
+GroupNorm (`gn=True`): conv on the tensor cores with an fp32 result, then the native GroupNorm pass
+(snvc_group_norm_fwd: statistics, normalisation, skip add, ReLU, bf16 store).
 """
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from snvc_b200 import functional as SF
-from snvc_b200.conv import PackedConv3d
+from snvc_b200.conv import PackedConv2d, PackedConv3d
 
 
 # ----------------------------------------------------------------------------- tensor kinds
@@ -75,25 +74,11 @@ class _ConvNorm3d(nn.Sequential):
         plan = self._plan()
         norm = self[1]
         if isinstance(norm, nn.GroupNorm):
-            # conv on the tensor cores (fp32 out), GroupNorm + epilogue on the channels-last result
+            # conv on the tensor cores (fp32 out), then the native GroupNorm pass: statistics, normalisation, skip add, ReLU
+            # and the bf16 store in snvc_group_norm_fwd (no ATen kernels on the path)
             y = plan(x, out_dtype=torch.float32, in_coffset=in_coffset)
-            if residual is not None:
-                residual = residual[..., res_coffset:res_coffset + y.shape[-1]]
-            y = F.group_norm(y.permute(0, 4, 1, 2, 3), norm.num_groups, norm.weight, norm.bias, norm.eps)
-            y = y.permute(0, 2, 3, 4, 1)
-            if residual is not None and residual_mode in (0, 1):
-                y = y + residual.float()
-            if relu:
-                y = torch.relu(y)
-            if residual is not None and residual_mode == 2:
-                y = y + residual.float()
-            if sigmoid:
-                y = torch.sigmoid(y)
-            y = y.to(out_dtype).contiguous()
-            if out is not None:
-                out[..., out_coffset:out_coffset + y.shape[-1]] = y
-                return out
-            return y
+            return SF.group_norm_act(y, norm, relu=relu, residual=residual, residual_mode=residual_mode, sigmoid=sigmoid,
+                                     out_dtype=out_dtype, out=out, out_coffset=out_coffset, res_coffset=res_coffset)
         return plan(x, relu=relu, residual=residual, residual_mode=residual_mode, sigmoid=sigmoid,
                     out_dtype=out_dtype, out=out, out_coffset=out_coffset, in_coffset=in_coffset,
                     res_coffset=res_coffset)
@@ -225,3 +210,166 @@ class hourglass_downsample_16(nn.Module):
     def forward(self, x):
         xin, kind = _to_ndhwc(x)
         return _from_ndhwc(self.fused(xin), kind)
+
+
+# ============================================================================================ 2-D BEV blocks (N2)
+# Drop-ins for `convbn` (submodule.py:11-29), `get_hg_down_sample_2d` (:183-195), `get_hg_up_sample_2d` (:210-221),
+# `hourglass2d` (:317-361) and `hourglass2d_downsample_16` (:270-315) on the 2-D tensor-core kernel (snvc_conv2d_fwd).
+# Same names, constructor arguments, forward signatures and state_dict keys.  Tensor kinds as for the 3-D blocks:
+# fp32 NCHW in -> fp32 NCHW out; bf16 torch.channels_last in -> bf16 channels_last out (zero-copy).
+def _to_nhwc(x):
+    if x.dim() != 4:
+        raise RuntimeError(f"expected a 4-D feature map, got {tuple(x.shape)}")
+    if not x.is_cuda:
+        raise RuntimeError("Not implemented on the CPU")
+    if x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last):
+        return x.permute(0, 2, 3, 1), "cl"
+    return SF.to_ndhwc_bf16(x.float()[:, :, None])[:, 0], "f32"
+
+
+def _from_nhwc(y, kind):
+    if kind == "cl":
+        return y.permute(0, 3, 1, 2)
+    return SF.to_ncdhw_f32(y[:, None])[:, :, 0]
+
+
+def _opt_nhwc(t):
+    return None if t is None else _to_nhwc(t)[0]
+
+
+class _ConvNorm2d(nn.Sequential):
+    """nn.Sequential(Conv2d | ConvTranspose2d, BatchNorm2d | GroupNorm) with a fused forward."""
+
+    transposed = False
+
+    def _plan(self):
+        conv, norm = self[0], self[1]
+        gn = isinstance(norm, nn.GroupNorm)
+        if not gn and norm.training:
+            raise RuntimeError("snvc_b200 conv blocks are inference-only: call .eval() (BatchNorm uses running stats)")
+        vers = (conv.weight.data_ptr(), conv.weight._version, str(conv.weight.device))
+        if not gn:
+            vers += (norm.weight._version, norm.bias._version, norm.running_mean._version, norm.running_var._version)
+        plan = getattr(self, "_snvc_plan", None)
+        if plan is None or plan[0] != vers:
+            p = PackedConv2d(conv.weight, None if gn else norm, transposed=self.transposed, stride=conv.stride[0],
+                             pad=conv.padding[0], dilation=conv.dilation[0])
+            plan = (vers, p)
+            object.__setattr__(self, "_snvc_plan", plan)
+        return plan[1]
+
+    def fused(self, x, *, relu=False, residual=None, residual_mode=0, out_dtype=torch.bfloat16):
+        """x: NHWC bf16.  Returns NHWC."""
+        plan, norm = self._plan(), self[1]
+        if isinstance(norm, nn.GroupNorm):
+            y = plan(x, out_dtype=torch.float32)
+            return SF.group_norm_act(y, norm, relu=relu, residual=residual, residual_mode=residual_mode, out_dtype=out_dtype)
+        return plan(x, relu=relu, residual=residual, residual_mode=residual_mode, out_dtype=out_dtype)
+
+    def forward(self, x):
+        xin, kind = _to_nhwc(x)
+        return _from_nhwc(self.fused(xin), kind)
+
+
+class _DeconvNorm2d(_ConvNorm2d):
+    transposed = True
+
+
+def _norm2d(ch, gn, groups=32):
+    return nn.GroupNorm(groups, ch) if gn else nn.BatchNorm2d(ch)
+
+
+def convbn(in_planes, out_planes, kernel_size, stride, pad, dilation, gn=False, groups=32):
+    """submodule.py:11-29."""
+    return _ConvNorm2d(nn.Conv2d(in_planes, out_planes, kernel_size=kernel_size, stride=stride,
+                                 padding=dilation if dilation > 1 else pad, dilation=dilation, bias=False),
+                       _norm2d(out_planes, gn, groups))
+
+
+class _ConvNormReLU2d(nn.Sequential):
+    def fused(self, x, **kw):
+        kw.setdefault("relu", True)
+        return self[0].fused(x, **kw)
+
+    def forward(self, x):
+        xin, kind = _to_nhwc(x)
+        return _from_nhwc(self.fused(xin), kind)
+
+
+def _cbr2d(cin, cout, stride, gn=False):
+    return _ConvNormReLU2d(convbn(cin, cout, 3, stride, 1, 1, gn=gn), nn.ReLU(inplace=True))
+
+
+def get_hg_down_sample_2d(channel_in, channel_out, gn, downsample=True):
+    """submodule.py:183-195."""
+    return _cbr2d(channel_in, channel_out, 2 if downsample else 1, gn=gn)
+
+
+def get_hg_up_sample_2d(channel_in, channel_out, gn):
+    """submodule.py:210-221."""
+    return _DeconvNorm2d(nn.ConvTranspose2d(channel_in, channel_out, kernel_size=3, padding=1, output_padding=1, stride=2,
+                                            bias=False),
+                         _norm2d(channel_out, gn))
+
+
+class hourglass2d(nn.Module):
+    """submodule.py:317-361.  forward(x, presqu, postsqu) -> (out, pre, post)."""
+
+    def __init__(self, inplanes, gn=False):
+        super().__init__()
+        c2 = inplanes * 2
+        self.conv1 = _cbr2d(inplanes, c2, 2, gn)
+        self.conv2 = convbn(c2, c2, kernel_size=3, stride=1, pad=1, dilation=1, gn=gn)
+        self.conv3 = _cbr2d(c2, c2, 2, gn)
+        self.conv4 = _cbr2d(c2, c2, 1, gn)
+        self.conv5 = get_hg_up_sample_2d(c2, c2, gn)
+        self.conv6 = get_hg_up_sample_2d(c2, inplanes, gn)
+
+    def fused(self, x, presqu=None, postsqu=None, out_residual=None, out_dtype=torch.bfloat16):
+        out = self.conv1.fused(x)
+        pre = self.conv2.fused(out, relu=True, residual=postsqu, residual_mode=1 if postsqu is not None else 0)
+        out = self.conv4.fused(self.conv3.fused(pre))
+        post = self.conv5.fused(out, relu=True, residual=presqu if presqu is not None else pre, residual_mode=1)
+        out = self.conv6.fused(post, residual=out_residual, residual_mode=1 if out_residual is not None else 0,
+                               out_dtype=out_dtype)
+        return out, pre, post
+
+    def forward(self, x, presqu, postsqu):
+        xin, kind = _to_nhwc(x)
+        out, pre, post = self.fused(xin, _opt_nhwc(presqu), _opt_nhwc(postsqu))
+        return _from_nhwc(out, kind), _from_nhwc(pre, kind), _from_nhwc(post, kind)
+
+
+class hourglass2d_downsample_16(nn.Module):
+    """submodule.py:270-315."""
+
+    def __init__(self, inplanes, gn=False):
+        super().__init__()
+        c2 = inplanes * 2
+        self.conv1 = get_hg_down_sample_2d(inplanes, c2, gn)
+        self.conv2 = get_hg_down_sample_2d(c2, c2, gn, False)
+        self.conv3 = get_hg_down_sample_2d(c2, c2, gn)
+        self.conv4 = get_hg_down_sample_2d(c2, c2, gn, False)
+        self.conv5 = get_hg_down_sample_2d(c2, c2, gn)
+        self.conv6 = get_hg_down_sample_2d(c2, c2, gn, False)
+        self.conv7 = get_hg_down_sample_2d(c2, c2, gn)
+        self.conv8 = get_hg_down_sample_2d(c2, c2, gn, False)
+        self.conv9 = get_hg_up_sample_2d(c2, c2, gn)
+        self.conv10 = get_hg_up_sample_2d(c2, c2, gn)
+        self.conv11 = get_hg_up_sample_2d(c2, c2, gn)
+        self.conv12 = get_hg_up_sample_2d(c2, inplanes, gn)
+
+    def fused(self, x, out_residual=None, out_dtype=torch.bfloat16):
+        o2 = self.conv2.fused(self.conv1.fused(x))
+        o4 = self.conv4.fused(self.conv3.fused(o2))
+        o6 = self.conv6.fused(self.conv5.fused(o4))
+        o8 = self.conv8.fused(self.conv7.fused(o6))
+        i10 = self.conv9.fused(o8, residual=o6, residual_mode=1)
+        i11 = self.conv10.fused(i10, residual=o4, residual_mode=1)
+        i12 = self.conv11.fused(i11, residual=o2, residual_mode=1)
+        return self.conv12.fused(i12, residual=out_residual, residual_mode=1 if out_residual is not None else 0,
+                                 out_dtype=out_dtype)
+
+    def forward(self, x):
+        xin, kind = _to_nhwc(x)
+        return _from_nhwc(self.fused(xin), kind)

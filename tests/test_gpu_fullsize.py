@@ -122,9 +122,11 @@ def test_configs3_full_size_proposal_vs_oracle():
 
 
 def test_instance_confidence_ordering_and_argmax_vs_oracle():
-    """ordering of the per-proposal confidences max(ncf) (vernier.py:683-686) over 64 proposals and the
-    arg-max cell of each of the 9 part heatmaps.  The 2-D tail (conv5 / hm1 / hm2, vernier.py:440-455) is evaluated by
-    the SAME fp32 torch modules on both sides, so the comparison isolates the bf16 3-D path under test."""
+    """the ordering of the per-proposal confidences (mean over parts of max(ncf), vernier.py:683-686) over
+    64 proposals is IDENTICAL to the fp32 oracle's, and so is the arg-max cell of the part heatmaps.  The proposals differ
+    in feature amplitude (as real ROIs do), which spreads their confidences.  The 2-D tail (conv5 / hm1 / hm2,
+    vernier.py:440-455) is evaluated by the SAME fp32 torch modules on both sides, so the comparison isolates the bf16
+    3-D path under test."""
     from snvc_b200.models.vernier import VernierHotPath
     grid = (16, 64, 96)
     cfg = _vernier_cfg(grid)
@@ -137,10 +139,13 @@ def test_instance_confidence_ordering_and_argmax_vs_oracle():
     tail = oblocks.VernierBevTail(128, 9, n_sample_w=grid[1]).eval()
     tail.load_state_dict(synth.det_state_dict(tail, 33), strict=True)
     NP, chunk = 64, 8
+    amp = 0.3 + 1.4 * np.random.default_rng(4).permutation(NP).astype(np.float32) / (NP - 1)
     conf_ref, conf_got, arg_ref, arg_got, margin = [], [], [], [], []
     for c0 in range(0, NP, chunk):
         lf, rf, gl, gr = _instance_inputs(chunk, grid, 900 + 10 * c0, Hf=64)
-        bev, _ = m(*[torch.from_numpy(a).cuda() for a in (lf, rf, gl, gr)])
+        a = amp[c0:c0 + chunk, None, None, None]
+        lf, rf = synth.bf16_round(lf * a), synth.bf16_round(rf * a)
+        bev, _ = m(*[torch.from_numpy(x).cuda() for x in (lf, rf, gl, gr)])
         vox = ogs.roi_voxel_sample(lf, rf, gl, gr, *grid, (256, 256))
         want_bev, _ = ref(torch.from_numpy(vox))
         h_ref, h_got = tail(want_bev).numpy(), tail(bev.cpu()).numpy()          # [chunk,9,L,W]
@@ -151,21 +156,16 @@ def test_instance_confidence_ordering_and_argmax_vs_oracle():
             top2 = np.sort(fr, axis=1)[:, -2:]
             margin.append((top2[:, 1] - top2[:, 0], np.abs(fr - fg).max(1)))
     conf_ref, conf_got = np.array(conf_ref), np.array(conf_got)
-    noise = 2 * np.max(np.abs(conf_ref - conf_got))
+    err = np.max(np.abs(conf_ref - conf_got))
+    assert err <= TOL * np.max(np.abs(conf_ref)), err
     order_ref = np.argsort(-conf_ref, kind="stable")
     order_got = np.argsort(-conf_got, kind="stable")
     gaps = np.abs(np.diff(conf_ref[order_ref]))
-    # proposals whose oracle confidence is separated from both neighbours by more than the bf16 noise keep their rank
-    fixed = [r for r in range(NP) if (r == 0 or gaps[r - 1] > noise) and (r == NP - 1 or gaps[r] > noise)]
-    assert len(fixed) >= NP // 4, (len(fixed), noise)
-    for r in fixed:
-        assert order_ref[r] == order_got[r]
-    assert np.max(np.abs(conf_ref - conf_got)) <= TOL * np.max(np.abs(conf_ref))
-    checked = 0
+    assert np.array_equal(order_ref, order_got), (err, np.sort(gaps)[:5])      # identical confidence ordering, all 64
+    agree = sum(int(arg_ref[i][p] == arg_got[i][p]) for i in range(NP) for p in range(9))
+    assert agree >= 0.97 * NP * 9, agree
     for i in range(NP):
-        gap, err = margin[i]
+        gap, e = margin[i]
         for p in range(9):
-            if gap[p] > 2 * err[p]:                                            # the oracle's own arg-max is unambiguous
+            if gap[p] > 2 * e[p]:                                              # the oracle's own arg-max is unambiguous
                 assert arg_ref[i][p] == arg_got[i][p]
-                checked += 1
-    assert checked >= NP * 9 // 2, checked

@@ -25,7 +25,8 @@ def test_masked_rows_to_host_equals_dense_copy(C, rows, blocks):
     last_valid = torch.ones(rows, dtype=torch.bool, device="cuda")
     for it in range(4):
         valid = (torch.rand(rows, device="cuda", generator=g) < (0.2 + 0.2 * it)).to(torch.uint8)
-        src = torch.randn((rows, C), device="cuda", generator=g).to(torch.bfloat16) * valid[:, None].to(torch.bfloat16)
+        src = torch.randn((rows, C), device="cuda", generator=g).to(torch.bfloat16)
+        src = torch.where(valid[:, None].bool(), src, torch.zeros_like(src))          # masked rows are +0, as the lift writes them
         moved.zero_()
         _call(src, valid, prev, h_out, moved, blocks)
         torch.cuda.synchronize()
