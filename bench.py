@@ -126,7 +126,7 @@ def cpu_reference_pairs_per_s(steps, warmup, threads=None):
     import torch
     from oracle import blocks, torch_path
     import synth
-    threads = threads or os.cpu_count() or 1
+    threads = threads or len(os.sched_getaffinity(0)) or 1
     torch.set_num_threads(threads)
     geom = geometry()
     trunk = blocks.GlobalTrunk(2 * FEAT_C, 32).eval()
@@ -164,7 +164,8 @@ def run_reference(args, rank, world):
 
 # ----------------------------------------------------------------------------------------------
 def roofline_traffic():
-    """DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture."""
+    """DRAM bytes per launch per kernel, from the committed `ncu --set full` capture of this build
+    (profiles/roofline_traffic.json, regenerated by scripts/ncu_traffic.py on the GPU box)."""
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(p):
         with open(p) as f:
@@ -172,19 +173,160 @@ def roofline_traffic():
     return {}
 
 
+def gpu_baseline_leg(B):
+    """Same-box library baselines for the three stages: the reference's own cost-volume kernel
+    (oracle/_ref, if it was built), cuDNN bf16 channels_last_3d Conv3d trunk, ATen grid_sample lift.  Baseline code only."""
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import gpu_baselines
+    try:
+        g = gpu_baselines.global_baselines(B, iters=3, with_fp32=False)
+    except Exception as e:            # a baseline must never take the benchmark down
+        return {"error": str(e)[:200]}
+    keep = ("cost_volume_reference_kernel_f32_ms", "trunk_cudnn_bf16_channels_last_ms", "lift_aten_grid_sample_bf16_ms",
+            "lift_aten_grid_sample_f32_ms", "sum_library_best_ms", "pairs_per_s_library_best", "trunk_ours_vs_cudnn_bf16_relerr")
+    out = {k: g[k] for k in keep if k in g}
+    out["what"] = ("per batch of %d pairs on this GPU: reference BuildCostVolumeForward kernel compiled for sm_100 (fp32 NCDHW), "
+                   "oracle.blocks.GlobalTrunk through cuDNN (bf16, channels_last_3d, cudnn.benchmark), F.grid_sample (bf16)" % B)
+    return out
+
+
+def instance_leg(dev, rank, world, dist, peaks, frame_proposals=64, chunk=8, steps=2):
+    """BASELINE.json configs[3]: 64 proposals per frame sharded over the ranks (contiguous blocks, no collective), each
+    rank runs ROI voxel sampling + the BEV_type3 3-D CNN + the BEV tail on its block in chunks of <= 8 proposals."""
+    import torch
+    import synth
+    from snvc_b200.models.vernier import VernierHotPath
+    from snvc_b200.parallel import shard_range
+    ns = types.SimpleNamespace
+    grid = (32, 128, 192)
+    cfg = ns(vernier_type="BEV_type3", gn=False, hrfeat=ns(output_channel=32), num_parts=9, grid_resolution=list(grid),
+             n_sample_h=grid[0], n_sample_w=grid[1], n_sample_l=grid[2], resolution=[256, 256])
+    m = VernierHotPath(cfg, bev_tail=True).eval()
+    m.load_state_dict(synth.det_state_dict(m, 31), strict=True)
+    m = m.to(dev)
+    lo, hi = shard_range(frame_proposals, world, rank)
+    mine = hi - lo
+    P = min(chunk, max(mine, 1))
+    g = torch.Generator(device=dev).manual_seed(500 + rank)
+    lf = torch.randn((P, 32, 64, 64), device=dev, generator=g)
+    rf = torch.randn((P, 32, 64, 64), device=dev, generator=g)
+    nh, nw, nl = grid
+    hh, ww, ll = torch.meshgrid(torch.linspace(0, 1, nh), torch.linspace(0, 1, nw), torch.linspace(0, 1, nl), indexing="ij")
+
+    def coords(shift):       # coherent projections of the grid into the 256 x 256 ROI, partly outside it
+        u = (-12.0 + 280.0 * ll + 25.0 * ww + shift).reshape(-1)
+        v = (-8.0 + 270.0 * hh + 18.0 * ww).reshape(-1)
+        return torch.stack([u, v])[None].repeat(P, 1, 1).contiguous().to(dev)
+    gl, gr = coords(0.0), coords(-9.0)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    nchunks = (mine + P - 1) // P if mine else 0
+    with torch.no_grad():
+        vox = m.construct_voxel(lf, rf, gl, gr)
+        m.predict_heatmaps(vox)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0, t1, t2 = ev(), ev(), ev()
+        samp = cnn = 0.0
+        a, b = ev(), ev()
+        a.record()
+        for _ in range(steps):
+            for _ in range(nchunks):
+                t0.record()
+                vox = m.construct_voxel(lf, rf, gl, gr)
+                t1.record()
+                m.predict_heatmaps(vox)
+                t2.record()
+        b.record()
+        torch.cuda.synchronize()
+        # per-stage split from one more chunk (events inside the loop above would need a sync per chunk)
+        t0.record(); vox = m.construct_voxel(lf, rf, gl, gr); t1.record(); m.predict_heatmaps(vox); t2.record()
+        torch.cuda.synchronize()
+        samp, cnn = t0.elapsed_time(t1) / P, t1.elapsed_time(t2) / P
+    t = torch.tensor([a.elapsed_time(b) / steps, samp, cnn], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    frame_ms, samp, cnn = t.tolist()
+    gflop = 1708.36
+    return {"workload": "configs[3]: 64 proposals/frame, ROI voxel sampling (grid 32x128x192, 64 ch) + BEV_type3 3-D CNN + BEV tail, bf16",
+            "proposals_per_frame": frame_proposals, "parallelism": f"proposal-sharded x{world}, no collective",
+            "ms_per_frame": frame_ms, "proposals_per_s": frame_proposals / (frame_ms * 1e-3), "frames_per_s": 1e3 / frame_ms,
+            "roi_sampling": {"ms_per_proposal": samp, "achieved_gbs": 114_294_784 / (samp * 1e-3) / 1e9,
+                             "frac_hbm": 114_294_784 / (samp * 1e-3) / 1e9 / peaks["hbm"], "bytes_per_proposal": 114_294_784},
+            "cnn": {"ms_per_proposal": cnn, "achieved_tflops": gflop / cnn, "frac_tensor": gflop / cnn / peaks["tf_sustained"],
+                    "gflop_per_proposal": gflop}}
+
+
+def stress_leg(dev, rank, world, dist, steps=3):
+    """BASELINE.json configs[4]: ONE volume, 2x depth bins (D = 96) at full resolution (features 32 x 384 x 1248: cost
+    volume 5.9 GB bf16, trunk 15.7 TFLOP), split into depth slabs over the ranks with a conv3d halo exchange (NCCL P2P over
+    NVLink) after every layer and a z-partitioned lift.  Strong scaling: the work is fixed, ranks divide it."""
+    import torch
+    import synth
+    from snvc_b200 import parallel as par
+    from snvc_b200.models.stereonet import GlobalHotPath
+    from snvc_b200.utils.geometry import KITTI_P2, kitti_global_cfg, plane_sweep_shifts
+    D, H, W = 96, 384, 1248
+    if D % (4 * world) != 0:
+        return {"skipped": f"D={D} is not a multiple of 4*world"}
+    cfg = kitti_global_cfg(IH=H, IW=W, feat_stride=1, D=D)
+    m = GlobalHotPath(cfg).eval()
+    m.load_state_dict(synth.det_state_dict(m, 41), strict=True)
+    m = m.to(dev)
+    g = torch.Generator(device=dev).manual_seed(7)                    # same seed on every rank: replicated inputs
+    lf = torch.randn((1, 32, H, W), device=dev, generator=g)
+    rf = torch.randn((1, 32, H, W), device=dev, generator=g)
+    shift = torch.from_numpy(plane_sweep_shifts(cfg, 1)).to(dev)
+    proj = torch.from_numpy(KITTI_P2[None].copy()).to(dev)
+    slab = par.DepthSlab(D, world, rank)
+    comm = par.HaloComm(world, rank, dev) if world > 1 else None
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    with torch.no_grad():
+        for _ in range(2):
+            par.slab_global_forward(m, lf, rf, shift, proj, slab, out_dtype=torch.bfloat16, layout_out="NDHWC", comm=comm)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = ev(), ev()
+        e0.record()
+        for _ in range(steps):
+            par.slab_global_forward(m, lf, rf, shift, proj, slab, out_dtype=torch.bfloat16, layout_out="NDHWC", comm=comm)
+        e1.record()
+        torch.cuda.synchronize()
+    if comm is not None:
+        comm.close()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    gflop = 491.90 * 2 * 16
+    halo_mb = 384 * 1248 * 2 / 1e6 * (32 * 5 + 64 * (2 / 4 + 3 / 16))        # one plane per direction per layer, summed over the 10 layers
+    torch.cuda.empty_cache()
+    return {"workload": "configs[4] stress: 1 volume, D=96, features 32x384x1248 (cost volume 5.9 GB bf16, trunk 15.7 TFLOP)",
+            "parallelism": f"depth slabs x{world}" + (", conv3d halo exchange: snvc_halo_exchange (one ncclGroup of send/recv with ranks r-1 / r+1 over NVLink) after each of the 10 layers" if world > 1 else ""),
+            "scaling": "strong", "ms_per_volume": ms.item(), "volumes_per_s": 1e3 / ms.item(),
+            "aggregate_tflops": gflop / ms.item(), "slab_planes": slab.Dl,
+            "halo_mb_per_rank_per_direction": halo_mb if world > 1 else 0.0}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     import synth
     from snvc_b200 import _lib
-    from snvc_b200.models.stereonet import GlobalHotPath, GraphedHotPath, HostPipeline
+    from snvc_b200.models.stereonet import GlobalHotPath, GraphedHotPath, HostPipeline, RPN3DHead, decode_proposals
     from snvc_b200.extension.build_cost_volume import build_cost_volume_ndhwc_bf16
+    from snvc_b200.utils import numa
     from snvc_b200.utils.geometry import KITTI_P2, kitti_global_cfg, plane_sweep_shifts
 
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback in snvc_b200)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # host side of this rank next to its GPU: cores + (first-touch) pinned buffers on the GPU's NUMA node
+    all_cpus = os.sched_getaffinity(0)
+    numa_info = numa.bind_to_gpu_node(local_rank) if os.environ.get("SNVC_NUMA_BIND", "1") != "0" else {"bound": False}
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
@@ -237,13 +379,16 @@ def run_ours(args, rank, world, local_rank):
             e[4].record()
         return vox, e
 
-    with torch.no_grad():
-        for i in range(W):
-            step(i, False)
+    def sync_all():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for i in range(W):
+            step(i, False)
+        sync_all()
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
@@ -258,10 +403,7 @@ def run_ours(args, rank, world, local_rank):
         launches = L.snvc_launch_count() - launches0
         if graphed is not None:                             # replayed kernels do not pass the library's counter
             launches = K * graphed.launches_per_replay
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        sync_all()
         elapsed_ms = t_start.elapsed_time(t_stop)
         has_addend_stage = graphed is not None and "conv1_addend" in graphed.stage_names
         for e in evs:
@@ -270,24 +412,24 @@ def run_ours(args, rank, world, local_rank):
             stage_ms["trunk"] += e[1].elapsed_time(e[3])        # (split form: includes the 3-plane addend convolution)
             stage_ms["lift"] += e[3].elapsed_time(e[4])
 
-        # ---- end to end through the public host-buffer API: pinned host inputs -> H2D -> hot path -> D2H of
-        # the lifted voxels into pinned host memory, every step, copies overlapped with compute on separate
-        # streams (snvc_b200.models.stereonet.HostPipeline) -------------------------------------------------
+        # ---- end to end through the public host-buffer API: pinned host inputs -> H2D -> hot path -> the lifted voxels
+        # into pinned host memory, every step, transfers overlapped with compute on separate streams
+        # (snvc_b200.models.stereonet.HostPipeline).  The return moves only the in-frustum voxel rows (the dense tensor
+        # is what the host buffer holds afterwards; tests/test_gpu_host_return.py) -------------------------------------
         NH = 2
         h_in = [(torch.randn((B, FEAT_C, FEAT_H, FEAT_W)).pin_memory(), torch.randn((B, FEAT_C, FEAT_H, FEAT_W)).pin_memory(),
                  torch.from_numpy(plane_sweep_shifts(cfg, B)).pin_memory(),
                  torch.from_numpy(KITTI_P2[None].repeat(B, 0).copy()).pin_memory()) for _ in range(NH)]
         Z, Y, X = model.zs.numel(), model.ys.numel(), model.xs.numel()
         h_out = [torch.empty((B, Z, Y, X, 32), dtype=out_dtype).pin_memory() for _ in range(NH)]
-        pipe = HostPipeline(model, depth=2, out_dtype=out_dtype, layout_out=layout_out, graphed=not args.eager)
+        pipe = HostPipeline(model, depth=2, out_dtype=out_dtype, layout_out=layout_out, graphed=not args.eager,
+                            sparse_return=not args.dense_return, return_blocks=args.return_blocks)
         e2e_steps = max(4, min(K, 20))
         for i in range(3):
             pipe.submit(*h_in[i % NH], h_out[i % NH])
         pipe.drain()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        sync_all()
+        pipe.moved_bytes.zero_()
         e0, e1 = ev(), ev()
         cur = torch.cuda.current_stream()
         e0.record()
@@ -298,37 +440,80 @@ def run_ours(args, rank, world, local_rank):
         e1.record()
         torch.cuda.synchronize()
         e2e_ms = e0.elapsed_time(e1)
-        # same pipeline with the result left on the device (only a 64-value digest per pair returns to the host): what an
-        # on-device consumer of the voxels sees; reported next to the dense-result number, never instead of it
-        e2e_dev_ms = None
-        if not args.eager:
-            h_dig = [torch.empty((B, 64), dtype=out_dtype).pin_memory() for _ in range(NH)]
+        dense_bytes = int(B * LIFT_VOX * 32 * 2)
+        d2h_bytes = int(pipe.moved_bytes.item()) // e2e_steps if pipe.sparse_return else dense_bytes
+
+        # ---- second end-to-end record: the volume's real consumer is on the device.  hot path -> RPN3DHead (3-D convs on
+        # the lifted grid, Y-pool -> BEV, 2-D hourglass, heads) -> decode + rotated BEV NMS, all on the GPU; only the
+        # proposals (boxes, scores, keep lists) return to the host -----------------------------------------------------
+        e2e_prop = None
+        if not args.eager and not args.no_proposals:
+            rcfg = types.SimpleNamespace(**vars(cfg), RPN_CONVDIM=32, num_angles=4, num_classes=1, box_corner_parameters=False)
+            rpn = RPN3DHead(rcfg, channels=32, n_y=Y).eval()
+            rpn.load_state_dict(synth.det_state_dict(rpn, 71), strict=True)
+            rpn = rpn.to(dev)
+            PRE = 256
+            h_prop = [(torch.empty((B, PRE, 7)).pin_memory(), torch.empty((B, PRE)).pin_memory(),
+                       torch.empty((B, PRE), dtype=torch.int64).pin_memory(), torch.empty((B,), dtype=torch.int32).pin_memory())
+                      for _ in range(NH)]
+            g2 = [GraphedHotPath(model, B, FEAT_C, (FEAT_H, FEAT_W), DEPTH_BINS, out_dtype, layout_out) for _ in range(NH)]
+            s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+            done = [None] * NH
+
+            def submit_prop(i):
+                k = i % NH
+                with torch.cuda.stream(s_in):
+                    if done[k] is not None:
+                        s_in.wait_event(done[k][0])
+                    for d, h in zip(g2[k].inputs, h_in[k]):
+                        d.copy_(h, non_blocking=True)
+                    ready = torch.cuda.Event()
+                    ready.record(s_in)
+                cur.wait_event(ready)
+                vox = g2[k].replay()
+                res = decode_proposals(*rpn(vox), rcfg, pre_nms=PRE, iou_thresh=0.25)
+                computed = torch.cuda.Event()
+                computed.record(cur)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(computed)
+                    for h, d in zip(h_prop[k], res):
+                        h.copy_(d, non_blocking=True)
+                        d.record_stream(s_out)
+                done[k] = (computed,)
+
             for i in range(3):
-                pipe.submit(*h_in[i % NH], h_dig[i % NH])
-            pipe.drain()
-            torch.cuda.synchronize()
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
-            e2, e3 = ev(), ev()
-            e2.record()
+                submit_prop(i)
+            sync_all()
+            p0, p1 = ev(), ev()
+            p0.record()
             for i in range(e2e_steps):
-                pipe.submit(*h_in[i % NH], h_dig[i % NH])
-            cur.wait_stream(pipe.s_out)
-            cur.wait_stream(pipe.s_in)
-            e3.record()
+                submit_prop(i)
+            cur.wait_stream(s_out)
+            cur.wait_stream(s_in)
+            p1.record()
             torch.cuda.synchronize()
-            e2e_dev_ms = e2.elapsed_time(e3)
+            e2e_prop = p0.elapsed_time(p1)
+            del g2
         clocks = sampler.stop() if rank == 0 else None
+        del pipe, h_out
+        torch.cuda.empty_cache()
 
     t = torch.tensor([elapsed_ms, e2e_ms, stage_ms["cost_volume"], stage_ms["trunk"], stage_ms["lift"], stage_ms["conv1"],
-                      e2e_dev_ms if e2e_dev_ms is not None else 0.0], device=dev, dtype=torch.float64)
+                      e2e_prop if e2e_prop is not None else 0.0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms, e2e_ms, cv_ms, trunk_ms, lift_ms, conv1_ms, e2e_dev_ms = t.tolist()
+    elapsed_ms, e2e_ms, cv_ms, trunk_ms, lift_ms, conv1_ms, e2e_prop = t.tolist()
+
+    peaks = measured_peaks()
+    instance = None if args.no_instance else instance_leg(dev, rank, world, dist, peaks)
+    stress = None if args.no_stress else stress_leg(dev, rank, world, dist)
+    gpu_base = gpu_baseline_leg(B) if (rank == 0 and world == 1 and not args.no_gpu_baseline) else None
+    cpu_v = cpu_threads = None
+    if rank == 0 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)                   # the CPU arm gets every host core, not just the GPU-local node
+        cpu_v, _, cpu_threads = cpu_reference_pairs_per_s(2, 1)
 
     if rank == 0:
-        peaks = measured_peaks()
         pairs = world * B * K
         value = pairs / (elapsed_ms * 1e-3)
         split = graphed is not None and graphed.split
@@ -341,8 +526,33 @@ def run_ours(args, rank, world, local_rank):
         cv_gbs = cv_bytes * B * K / (cv_ms * 1e-3) / 1e9
         lift_gbs = lift_bytes_per_pair(2) * B * K / (lift_ms * 1e-3) / 1e9
         traffic = roofline_traffic()
-        cpu_v, cpu_spp, cpu_threads = cpu_reference_pairs_per_s(2, 1) if world == 1 and not args.no_cpu_baseline \
-            else (None, None, None)
+        # per-stage kernels against the roofline that bounds each; the dominant one (largest share of the step among the
+        # single-kernel stages) is the headline `roofline`, the others ride along in roofline.stages
+        conv1_name = ("conv3d_kdpair_kernel<2,64,addend> (dres0.conv1 3x3x3 on the split cost volume: right half 32->32 + "
+                      "depth-invariant addend, 1 launch / step)") if split else "conv3d_kdpair_kernel<4,128> (dres0.conv1 3x3x3 64->32, 1 launch / step)"
+        stages = {
+            "conv1": {"bound": "tensor", "kernel": conv1_name, "ms_per_step": conv1_ms / K, "achieved": conv1_tflops,
+                      "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": conv1_tflops / peaks["tf_sustained"],
+                      "frac_of_burst_peak": conv1_tflops / peaks["tf_burst"],
+                      "traffic": traffic.get("dres0.conv1_split_dram_bytes_per_launch" if split else "dres0.conv1_dram_bytes_per_launch"),
+                      "algorithmic_flop_per_launch": conv1_gflop * 1e9 * B, "share_of_step": conv1_ms / elapsed_ms},
+            "cost_volume": {"bound": "hbm", "kernel": "cv_split_bf16_kernel (2 launches / step: right-half volume, left planes)" if split
+                            else "cv_ndhwc_bf16_kernel", "ms_per_step": cv_ms / K, "achieved": cv_gbs, "peak": peaks["hbm"],
+                            "unit": "GB/s", "frac": cv_gbs / peaks["hbm"], "traffic": traffic.get("cost_volume_dram_bytes_per_step"),
+                            "algorithmic_bytes_per_launch": cv_bytes * B, "share_of_step": cv_ms / elapsed_ms},
+            "lift": {"bound": "hbm", "kernel": "lift_ndhwc_coop_kernel<bf16> (1 launch / step)", "ms_per_step": lift_ms / K,
+                     "achieved": lift_gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": lift_gbs / peaks["hbm"],
+                     "traffic": traffic.get("lift_dram_bytes_per_launch"), "algorithmic_bytes_per_launch": lift_bytes_per_pair(2) * B,
+                     "share_of_step": lift_ms / elapsed_ms},
+            "trunk": {"bound": "tensor", "kernel": "all 15 conv launches of dres0 / dres1 / hourglass", "ms_per_step": trunk_ms / K,
+                      "achieved": trunk_tflops, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                      "frac": trunk_tflops / peaks["tf_sustained"], "share_of_step": trunk_ms / elapsed_ms,
+                      "executed_gflop_per_pair": trunk_gflop, "reference_gflop_per_pair": TRUNK_GFLOP_PER_PAIR},
+        }
+        dom = max(("conv1", "cost_volume", "lift"), key=lambda k: stages[k]["ms_per_step"])
+        roof = dict(stages[dom])
+        roof["peak_source"] = peaks["source"] + (" (sustained bf16: kernel timed inside a long step)" if roof["bound"] == "tensor" else " (HBM copy bandwidth)")
+        roof["stages"] = {k: v for k, v in stages.items() if k != dom}
         line = {
             "metric": "stereo pairs/s (cost volume + 3D trunk + voxel lift)", "value": value, "unit": "pairs/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": elapsed_ms / K, "higher_is_better": True,
@@ -351,41 +561,39 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clocks,
             "e2e": {"value": world * B * e2e_steps / (e2e_ms * 1e-3), "unit": "pairs/s",
                     "h2d_bytes_per_step": int(2 * B * FEAT_C * FEAT_H * FEAT_W * 4 + B * DEPTH_BINS * 4 + B * 48),
-                    "d2h_bytes_per_step": int(B * LIFT_VOX * 32 * 2), "steps": e2e_steps,
-                    "result_on_device": ({"value": world * B * e2e_steps / (e2e_dev_ms * 1e-3), "unit": "pairs/s",
-                                          "d2h_bytes_per_step": int(B * 64 * 2),
-                                          "what": "same pipeline and H2D traffic; the voxels stay in HBM for an on-device "
-                                                  "consumer, a 64-value digest per pair is read back"} if e2e_dev_ms else None),
-                    "api": "snvc_b200.models.stereonet.HostPipeline.submit (pinned host buffers; H2D / compute / D2H "
-                           "on three streams, 2 slots" + ("" if args.eager else ", one CUDA-graph replay per batch") + ")"},
+                    "d2h_bytes_per_step": d2h_bytes, "dense_result_bytes_per_step": dense_bytes, "steps": e2e_steps,
+                    "return": ("in-frustum voxel rows only, written by snvc_masked_rows_to_host straight into the pinned host "
+                               "buffer at their dense positions (the buffer holds the dense tensor afterwards); "
+                               "d2h_bytes_per_step is counted by the kernel") if pipe_sparse(args) else "dense cudaMemcpyAsync",
+                    "numa": numa_info,
+                    "proposals_on_device": ({"value": world * B * e2e_steps / (e2e_prop * 1e-3), "unit": "pairs/s",
+                                             "d2h_bytes_per_step": int(B * 256 * (7 * 4 + 4 + 8) + B * 4),
+                                             "what": "same host inputs and H2D traffic; the lifted volume feeds RPN3DHead + decode + rotated "
+                                                     "BEV NMS on the device and only the proposals return (random-init heads)"}
+                                            if e2e_prop else None),
+                    "api": "snvc_b200.models.stereonet.HostPipeline.submit (pinned host buffers; H2D / compute / return on three "
+                           "streams, 2 slots" + ("" if args.eager else ", one CUDA-graph replay per batch") + ")"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor",
-                         "kernel": ("conv3d_kdpair_kernel<2,64,addend> (dres0.conv1 3x3x3 on the split cost volume: right half "
-                                    "32->32 + depth-invariant addend, 1 launch / step)") if split else
-                                   "conv3d_kdpair_kernel<4,128> (dres0.conv1 3x3x3 64->32, 1 launch / step)",
-                         "achieved": conv1_tflops, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                         "frac": conv1_tflops / peaks["tf_sustained"],
-                         "traffic": traffic.get("dres0.conv1_split_dram_bytes_per_launch" if split else
-                                                "dres0.conv1_dram_bytes_per_launch"),
-                         "algorithmic_flop_per_launch": conv1_gflop * 1e9 * B,
-                         "peak_source": peaks["source"] + " (sustained bf16, kernel timed inside a long step)",
-                         "share_of_step": conv1_ms / elapsed_ms},
-            "stages": {"cost_volume": {"ms_per_step": cv_ms / K, "achieved_gbs": cv_gbs, "frac_hbm": cv_gbs / peaks["hbm"],
-                                       "bytes_per_pair": cv_bytes,
-                                       "form": "split: right-half volume + 3 left planes (the 3-plane addend convolution is timed "
-                                               "with the trunk)" if split else "full 64-channel volume"},
-                       "trunk": {"ms_per_step": trunk_ms / K, "achieved_tflops": trunk_tflops,
-                                 "frac_tensor": trunk_tflops / peaks["tf_sustained"], "share_of_step": trunk_ms / elapsed_ms,
-                                 "executed_gflop_per_pair": trunk_gflop, "reference_gflop_per_pair": TRUNK_GFLOP_PER_PAIR},
-                       "lift": {"ms_per_step": lift_ms / K, "achieved_gbs": lift_gbs, "frac_hbm": lift_gbs / peaks["hbm"]}},
+            "roofline": roof,
         }
+        if instance is not None:
+            line["instance"] = instance
+        if stress is not None:
+            line["stress"] = stress
+        if gpu_base is not None:
+            line["gpu_baseline"] = gpu_base
         if cpu_v is not None:
             line["cpu_baseline"] = {"value": cpu_v, "unit": "pairs/s", "cores": cpu_threads, "kind": "port",
                                     "sample": "2 timed + 1 warm-up passes of 1 synthetic pair, same stages, fp32 torch "
-                                              "CPU ops (oracle/torch_path.py)"}
+                                              "CPU ops (oracle/torch_path.py), rank 0's host cores"}
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+
+
+def pipe_sparse(args):
+    return not args.dense_return
 
 
 def main():
@@ -396,6 +604,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="launch kernel by kernel from Python instead of CUDA-graph replay")
+    ap.add_argument("--dense-return", action="store_true", help="e2e: plain dense cudaMemcpyAsync of the voxels instead of the in-frustum-only return")
+    ap.add_argument("--return-blocks", type=int, default=32, help="e2e: grid size of the host-return kernel")
+    ap.add_argument("--no-instance", action="store_true", help="skip the configs[3] (instance branch) sub-record")
+    ap.add_argument("--no-stress", action="store_true", help="skip the configs[4] (depth-slab stress volume) sub-record")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the same-box library baselines (N = 1 only)")
+    ap.add_argument("--no-proposals", action="store_true", help="skip the proposals-on-device end-to-end record")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

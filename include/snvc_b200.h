@@ -51,6 +51,13 @@ const char* snvc_last_error(void);
  * only process-wide state besides cached device attributes).  bench.py reports the difference over
  * its timed region as `gpu_launches`. */
 int64_t snvc_launch_count(void);
+/* Debug / A-B switches (kernel-generation selection, grid clamps for the ring wrap-around tests): SNVC_CONV_MODE,
+ * SNVC_CONV_STORE, SNVC_CONV_OCC, SNVC_CONV_MAXGRID, SNVC_CV_SPLIT_OLD, SNVC_ROI_MODE, SNVC_LIFT_MODE.  Each is read from
+ * the environment once, when the library is loaded; snvc_set_option changes one afterwards (value NULL or "" = unset;
+ * name NULL = unset all).  Not synchronised with concurrent launches: set options before starting work.  Launches never
+ * call getenv. */
+int snvc_set_option(const char* name, const char* value);
+const char* snvc_get_option(const char* name);
 
 /* ---------------------------------------------------------------------------------------------
  * A1  plane-sweep cost volume, forward.
@@ -320,6 +327,22 @@ int snvc_avgpool_to_bev(const void* x, float* bev, int64_t N, int64_t Dh, int64_
  * grid [N,Z,Y,X,C] pooled over Y (restated RPN side). */
 int snvc_avgpool_to_bev_nhwc(const void* x, void* bev, int64_t N, int64_t S0, int64_t S1, int64_t S2, int32_t C,
                              int32_t pool, int32_t axis, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Depth-slab halo exchange of the single-volume stress configuration.  No reference
+ * counterpart (the reference only has nn.DataParallel over the batch, tools/inference_agnostic.py:472).
+ * One volume is split along depth over `world` ranks; an extended slab holds `halo` planes below and above its real
+ * planes.  snvc_halo_exchange sends the slab's first / last REAL plane to rank-1 / rank+1 and receives their last /
+ * first real plane into the INNER halo planes (index halo-1 and planes_ext-halo) -- one ncclGroup of point-to-point
+ * transfers over NVLink on `stream`, no host synchronisation; at the global boundary the inner halo plane is zero-filled
+ * (the convolution's zero padding).  x: device pointer to planes_ext planes of plane_bytes bytes each.
+ * The communicator is an ncclComm_t (passed as void*): snvc_halo_unique_id on one rank, distribute the 128 bytes out of
+ * band (torch.distributed broadcast), snvc_halo_comm_create on every rank.  NCCL is resolved with dlopen at first use. */
+int snvc_halo_unique_id(void* id128);
+int snvc_halo_comm_create(const void* id128, int32_t world, int32_t rank, void** comm);
+int snvc_halo_comm_destroy(void* comm);
+int snvc_halo_exchange(void* comm, void* x, int64_t planes_ext, int64_t plane_bytes, int32_t halo, int32_t rank,
+                       int32_t world, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Host return of a row-masked volume (end-to-end path of the global branch).

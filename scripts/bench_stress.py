@@ -32,10 +32,11 @@ lf = torch.randn((1, 32, H, W), device=dev, generator=g); rf = torch.randn((1, 3
 shift = torch.from_numpy(plane_sweep_shifts(cfg, 1)).to(dev)
 proj = torch.from_numpy(KITTI_P2[None].copy()).to(dev)
 slab = par.DepthSlab(D, world, rank)
+comm = par.HaloComm(world, rank, dev) if world > 1 else None
 ev = lambda: torch.cuda.Event(enable_timing=True)
 with torch.no_grad():
     for _ in range(2):
-        par.slab_global_forward(m, lf, rf, shift, proj, slab, out_dtype=torch.bfloat16, layout_out="NDHWC")
+        par.slab_global_forward(m, lf, rf, shift, proj, slab, out_dtype=torch.bfloat16, layout_out="NDHWC", comm=comm)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -43,7 +44,7 @@ with torch.no_grad():
     e0, e1 = ev(), ev()
     e0.record()
     for _ in range(steps):
-        vox, (zlo, zhi) = par.slab_global_forward(m, lf, rf, shift, proj, slab, out_dtype=torch.bfloat16, layout_out="NDHWC")
+        vox, (zlo, zhi) = par.slab_global_forward(m, lf, rf, shift, proj, slab, out_dtype=torch.bfloat16, layout_out="NDHWC", comm=comm)
     e1.record()
     torch.cuda.synchronize()
 ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)

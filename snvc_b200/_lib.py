@@ -32,6 +32,8 @@ _SIGS = {
     "snvc_version": ([], _i32),
     "snvc_last_error": ([], ctypes.c_char_p),
     "snvc_launch_count": ([], _i64),
+    "snvc_set_option": ([ctypes.c_char_p, ctypes.c_char_p], _i32),
+    "snvc_get_option": ([ctypes.c_char_p], ctypes.c_char_p),
     "snvc_cost_volume_fwd": ([_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _p], _i32),
     "snvc_cost_volume_split_fwd": ([_p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i32, _p], _i32),
     "snvc_cost_volume_bwd": ([_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _p], _i32),
@@ -63,6 +65,10 @@ _SIGS = {
     "snvc_scale_by_occupancy": ([_p, _p, _p, _i64, _i32, _i32, _i32, _p], _i32),
     "snvc_avgpool_to_bev": ([_p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _p], _i32),
     "snvc_avgpool_to_bev_nhwc": ([_p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _p], _i32),
+    "snvc_halo_unique_id": ([_p], _i32),
+    "snvc_halo_comm_create": ([_p, _i32, _i32, ctypes.POINTER(ctypes.c_void_p)], _i32),
+    "snvc_halo_comm_destroy": ([_p], _i32),
+    "snvc_halo_exchange": ([_p, _p, _i64, _i64, _i32, _i32, _i32, _p], _i32),
     "snvc_masked_rows_to_host": ([_p, _p, _p, _p, _i64, _i32, _i32, _p, _p], _i32),
 }
 
@@ -84,6 +90,17 @@ def lib():
             f.argtypes, f.restype = args, res
         _lib = l
     return _lib
+
+
+def set_option(name, value=None):
+    """Debug / A-B switch of the library (see include/snvc_b200.h); value None = unset, name None = unset all."""
+    st = lib().snvc_set_option(name.encode() if name is not None else None, str(value).encode() if value is not None else None)
+    check(st, "snvc_set_option")
+
+
+def get_option(name):
+    v = lib().snvc_get_option(name.encode())
+    return v.decode() if v else None
 
 
 def check(status, what):

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsnvc_b200.so")
-SOURCES = ["common.cu", "cost_volume.cu", "voxel_sample.cu", "elementwise.cu", "grid_proj.cu", "depth_head.cu", "nms_bev.cu", "host_return.cu", "group_norm.cu", "conv2d_tcgen05.cu", "conv3d_tcgen05.cu"]
+SOURCES = ["common.cu", "cost_volume.cu", "voxel_sample.cu", "elementwise.cu", "grid_proj.cu", "depth_head.cu", "nms_bev.cu", "host_return.cu", "halo_exchange.cu", "group_norm.cu", "conv2d_tcgen05.cu", "conv3d_tcgen05.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 
@@ -57,7 +57,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    link = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-cudart", "static"]
+    link = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-cudart", "static", "-ldl"]
     subprocess.check_call(link)
     return LIB
 

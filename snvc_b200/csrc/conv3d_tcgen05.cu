@@ -2670,7 +2670,7 @@ int launch_halo(const void* x, const void* w_packed, const float* scale, const f
   const int K3 = d.kernel * d.kernel * d.kernel;
   p.w_tap_bytes = cp.CoutPad * d.Cin * 2;
   const int w_total = round_up(K3 * p.w_tap_bytes, 1024);
-  const char* mode = getenv("SNVC_CONV_MODE");
+  const char* mode = opt(OPT_CONV_MODE);
   const bool kdfuse = d.dilation == 1 && !(mode && mode[0] == 'h');     // SNVC_CONV_MODE=halo: v2 (A/B runs)
   if (!kdfuse && ncout > 0) return 1;                                   // Cout slicing is implemented by the kd-fused kernel only
   // staged epilogue (bulk tensor store of a swizzled smem tile), opt-in with SNVC_CONV_STORE=staged.  Measured
@@ -2678,7 +2678,7 @@ int launch_halo(const void* x, const void* w_packed, const float* scale, const f
   // max(71.6, N/2) cycles, so at N = 96 this kernel is bound by MMA issue (18 x 71.6 = 1289 of the 1319 cycles
   // per plane tile), not by the L1 data pipe: removing the store wavefronts changed nothing (615 vs 614 us) and
   // the smaller plane ring made the residual layer slower (773 vs 684 us).  Direct stores stay the default.
-  const char* smode = getenv("SNVC_CONV_STORE");
+  const char* smode = opt(OPT_CONV_STORE);
   const bool staged = kdfuse && cp.Cout == cp.CoutPad && !cp.sigmoid && !cp.out_f32 &&
                       ((cp.out_cstride | cp.out_coffset) & 7) == 0 &&
                       (cp.CoutPad == 16 || cp.CoutPad == 32 || cp.CoutPad == 64) && (smode && smode[0] == 's');
@@ -2704,7 +2704,7 @@ int launch_halo(const void* x, const void* w_packed, const float* scale, const f
     // two CTAs per SM when weights + staging + a 3-slot plane ring fit in half the shared memory (Cin = Cout = 32
     // does): while one CTA's MMA warp does its per-plane bookkeeping the other CTA's MMAs keep the tensor pipe busy
     const int half_budget = (233472 - 2 * 1024) / 2 - 2048 /* static */ - 1024 /* alignment */;
-    const char* occ = getenv("SNVC_CONV_OCC");
+    const char* occ = opt(OPT_CONV_OCC);
     HaloParams keep = p;
     if (!(occ && occ[0] == '1') && pick(half_budget - w_total, staged ? 3 : 4)) ctas_per_sm = 2;
     else p = keep;
@@ -2787,7 +2787,7 @@ int launch_halo(const void* x, const void* w_packed, const float* scale, const f
   if (!kern) return 1;                                  // CoutPad 48: per-tap kernel
   SNVC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = std::min(p.num_cols, ctas_per_sm * sm_count());
-  if (const char* mg = getenv("SNVC_CONV_MAXGRID")) grid = std::max(1, std::min(grid, atoi(mg)));   // tests: force ring wrap-around
+  if (const char* mg = opt(OPT_CONV_MAXGRID)) grid = std::max(1, std::min(grid, atoi(mg)));   // tests: force ring wrap-around
   kern<<<grid, kThreads, smem, stream>>>(map_x, map_w, map_y, p);
   return launch_status("conv3d_kdfuse_kernel");
 }
@@ -2797,7 +2797,7 @@ int launch_halo(const void* x, const void* w_packed, const float* scale, const f
 int launch_kdpair(const void* x, const void* w_packed, const float* scale, const float* bias, const void* residual,
                   void* y, const snvc_conv3d_desc& d, const ConvParams& cp_full, cudaStream_t stream, int cout0 = 0,
                   int ncout = 0, const float* addend = nullptr) {
-  const char* mode = getenv("SNVC_CONV_MODE");
+  const char* mode = opt(OPT_CONV_MODE);
   if (!addend && mode && (mode[0] == 'h' || mode[0] == 'k')) return 1;  // SNVC_CONV_MODE=kw / kd / halo: v7 / v3 / v2 (A/B runs)
   if (addend && (d.Cin != 32 || cp_full.residual_mode || ncout > 0 || d.Di < 2)) return 1;
   ConvParams cp = cp_full;
@@ -2926,7 +2926,7 @@ int launch_kdpair(const void* x, const void* w_packed, const float* scale, const
   }
   if (max_clusters < 1) return 1;
   int pairs = std::min((p.num_cols + 1) / 2, max_clusters);
-  if (const char* mg = getenv("SNVC_CONV_MAXGRID")) pairs = std::max(1, std::min(pairs, atoi(mg)));   // tests: force ring wrap-around
+  if (const char* mg = opt(OPT_CONV_MAXGRID)) pairs = std::max(1, std::min(pairs, atoi(mg)));   // tests: force ring wrap-around
   kern<<<2 * pairs, kPairThreads, smem, stream>>>(map_x, map_w, map_r, p);
   return launch_status("conv3d_kdpair_kernel");
 }
@@ -2936,7 +2936,7 @@ int launch_kdpair(const void* x, const void* w_packed, const float* scale, const
 int launch_kwfuse(const void* x, const void* w_packed, const float* scale, const float* bias, const void* residual,
                   void* y, const snvc_conv3d_desc& d, const ConvParams& cp_full, cudaStream_t stream, int cout0 = 0,
                   int ncout = 0) {
-  const char* mode = getenv("SNVC_CONV_MODE");
+  const char* mode = opt(OPT_CONV_MODE);
   if (mode && (mode[0] == 'h' || (mode[0] == 'k' && mode[1] == 'd'))) return 1;   // SNVC_CONV_MODE=kd / halo: v3 / v2 (A/B runs)
   ConvParams cp = cp_full;
   if (ncout > 0) {
@@ -3012,7 +3012,7 @@ int launch_kwfuse(const void* x, const void* w_packed, const float* scale, const
                   : (cp.residual_mode ? conv3d_kwfuse_kernel<4, 128, true> : conv3d_kwfuse_kernel<4, 128, false>);
   SNVC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = std::min(p.num_cols, sm_count());
-  if (const char* mg = getenv("SNVC_CONV_MAXGRID")) grid = std::max(1, std::min(grid, atoi(mg)));   // tests: force ring wrap-around
+  if (const char* mg = opt(OPT_CONV_MAXGRID)) grid = std::max(1, std::min(grid, atoi(mg)));   // tests: force ring wrap-around
   kern<<<grid, kKwThreads, smem, stream>>>(map_x, map_w, p);
   return launch_status("conv3d_kwfuse_kernel");
 }
@@ -3114,7 +3114,7 @@ int launch_deconv(const void* x, const void* w_packed, const float* scale, const
   }
   SNVC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = std::min(p.num_units, sm_count());
-  if (const char* mg = getenv("SNVC_CONV_MAXGRID")) grid = std::max(1, std::min(grid, atoi(mg)));   // tests: force ring wrap-around
+  if (const char* mg = opt(OPT_CONV_MAXGRID)) grid = std::max(1, std::min(grid, atoi(mg)));   // tests: force ring wrap-around
   kern<<<grid, kDeconvThreads, smem, stream>>>(map_x, map_w, map_y, map_r, p);
   return launch_status("conv3d_deconv_kernel");
 }
@@ -3194,7 +3194,7 @@ int launch_s2(const void* x, const void* w_packed, const float* scale, const flo
       cp.Cout == 64 ? conv3d_s2_kernel<64> : conv3d_s2_kernel<32>;
   SNVC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = std::min(p.num_units, sm_count());
-  if (const char* mg = getenv("SNVC_CONV_MAXGRID")) grid = std::max(1, std::min(grid, atoi(mg)));   // tests: force ring wrap-around
+  if (const char* mg = opt(OPT_CONV_MAXGRID)) grid = std::max(1, std::min(grid, atoi(mg)));   // tests: force ring wrap-around
   kern<<<grid, kThreads, smem, stream>>>(map_xe, map_xo, map_w, p);
   return launch_status("conv3d_s2_kernel");
 }
@@ -3208,7 +3208,7 @@ int launch_bigk(const void* x, const void* w_packed, const float* scale, const f
   if (d.Do != d.Di || d.Ho != d.Hi || d.Wo != d.Wi) return 1;
   if (cp.CoutPad != 32 || !(d.Cin == 32 || d.Cin == 64)) return 1;
   if (d.dilation == 2 && (d.Di & 1)) return 1;            // the parity-split accumulator ring needs an even depth
-  const char* mode = getenv("SNVC_CONV_MODE");
+  const char* mode = opt(OPT_CONV_MODE);
   if (mode && mode[0] == 't') return 1;
   EncodeTiledFn enc = encode_fn();
   if (!enc) return fail(SNVC_E_DRIVER, "cuTensorMapEncodeTiled is not available from the CUDA driver");
@@ -3272,7 +3272,7 @@ int launch_bigk(const void* x, const void* w_packed, const float* scale, const f
   else kern = conv3d_bigk_kernel<5, 2, 64>;
   SNVC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = std::min(p.num_cols, sm_count());
-  if (const char* mg = getenv("SNVC_CONV_MAXGRID")) grid = std::max(1, std::min(grid, atoi(mg)));   // tests: force ring wrap-around
+  if (const char* mg = opt(OPT_CONV_MAXGRID)) grid = std::max(1, std::min(grid, atoi(mg)));   // tests: force ring wrap-around
   kern<<<grid, kBigThreads, smem, stream>>>(map_x, map_w, p);
   return launch_status("conv3d_bigk_kernel");
 }
@@ -3367,7 +3367,7 @@ static int conv3d_fwd_impl(const void* x, const void* w_packed, const float* sca
     // SNVC_CONV_MODE=tap forces the per-tap kernel (A/B measurements).  Descriptor base offset stays 0:
     // measured on B200, UMMA swizzles on absolute smem address bits, so row-shifted windows of a
     // TMA-written tile need no base-offset correction (base offset = (addr>>7)&7 gives wrong results).
-    const char* mode = getenv("SNVC_CONV_MODE");
+    const char* mode = opt(OPT_CONV_MODE);
     if (addend) {
       // depth-invariant addend: implemented by the CTA-pair kernel only (3x3x3 s1, Cin = Cout = 32, D >= 2, no residual)
       const int r = launch_kdpair(x, w_packed, scale, bias, nullptr, y, d, p, stream, 0, 0, addend);
@@ -3411,7 +3411,7 @@ static int conv3d_fwd_impl(const void* x, const void* w_packed, const float* sca
                  "transposed conv supports k=3, s=2, p=1, output_padding=1 only");
   SNVC_CHECK_ARG(d.Do == 2 * d.Di && d.Ho == 2 * d.Hi && d.Wo == 2 * d.Wi, "transposed conv output must be 2x input");
   {
-    const char* mode = getenv("SNVC_CONV_MODE");
+    const char* mode = opt(OPT_CONV_MODE);
     if (!(mode && mode[0] == 't')) {                     // SNVC_CONV_MODE=tap: per-class launches (A/B runs)
       int r = 1;
       for (int c0 = 0; c0 < d.Cout; c0 += kDeconvCP) {

@@ -557,7 +557,7 @@ namespace {
 int launch_cv_ndhwc(const void* left, const void* right, const void* shift, void* cost, void* left_planes, int64_t N,
                     int64_t C, int64_t IH, int64_t IW, int64_t D, int ds, int64_t H, int64_t W, cudaStream_t stream) {
   SNVC_CHECK_ARG(C % 8 == 0, "NDHWC cost volume needs C %% 8 == 0 (got %lld)", (long long)C);
-  if (left_planes && H <= 2147483647ll && N <= 65535 && !getenv("SNVC_CV_SPLIT_OLD")) {
+  if (left_planes && H <= 2147483647ll && N <= 65535 && !opt(OPT_CV_SPLIT_OLD)) {
     // split form, whole rows staged: the right row [img_w][C] fp32 + the sample table of one depth split (the left planes
     // are a second, small launch of the same kernel)
     const size_t rows = (size_t)IW * C * 4;

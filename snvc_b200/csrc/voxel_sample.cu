@@ -782,7 +782,7 @@ extern "C" int snvc_roi_voxel_sample_fwd(const float* feat_l, const float* feat_
     const int64_t total = N * P * (2 * C / 8);
     // cooperative kernel (set-up once per point, C/8 lanes per (point, view)); SNVC_ROI_MODE=thread keeps v1 (A/B runs)
     const int lpv = (int)(C / 8);
-    const char* rmode = getenv("SNVC_ROI_MODE");
+    const char* rmode = opt(OPT_ROI_MODE);
     // v3 (both views per round, 256-bit corner loads); SNVC_ROI_MODE=coop1 keeps v2 (A/B runs)
     if (lpv <= 16 && (lpv & (lpv - 1)) == 0 && N * P < (1ll << 30) && N * Hf * Wf < (1ll << 31) &&
         (reinterpret_cast<uintptr_t>(workspace) & 31) == 0 && (reinterpret_cast<uintptr_t>(out) & 31) == 0 &&
@@ -879,7 +879,7 @@ static int lift_fwd_impl(const void* vol, const float* proj, const float* zs, co
     // cooperative gather (C/8 lanes per voxel) whenever the row splits into a power-of-two number of 16-byte
     // pieces; SNVC_LIFT_MODE=thread keeps the one-thread-per-voxel kernel (A/B runs)
     const int lpv = (int)(C / 8);
-    const char* lmode = getenv("SNVC_LIFT_MODE");
+    const char* lmode = opt(OPT_LIFT_MODE);
     if (out_layout == SNVC_NDHWC && C % 8 == 0 && lpv <= 32 && (lpv & (lpv - 1)) == 0 && N * D * H * W < (1ll << 31) &&
         nvox < (1ll << 31) && N * D * H * W * lpv < (1ll << 32) && !(lmode && lmode[0] == 't')) {
       int log_lpv = 0;

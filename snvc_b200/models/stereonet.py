@@ -82,7 +82,8 @@ class GlobalHotPath(nn.Module):
     def split_supported(self, depth_bins):
         """The split first layer needs the CTA-pair conv kernel (default conv mode), >= 2 depth bins, 32 + 32 channels."""
         import os
-        return depth_bins >= 2 and not os.environ.get("SNVC_CONV_MODE") and os.environ.get("SNVC_SPLIT_CV", "1") != "0" \
+        from snvc_b200 import _lib
+        return depth_bins >= 2 and not _lib.get_option("SNVC_CONV_MODE") and os.environ.get("SNVC_SPLIT_CV", "1") != "0" \
             and self._split_plans() is not None
 
     def trunk_head_split(self, right_vol, left_planes):

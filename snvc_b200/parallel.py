@@ -8,8 +8,9 @@ The reference's only parallelism is single-process `nn.DataParallel` over the ba
   `gather_outputs` reproduces DataParallel's gather for callers that want it;
 * the single-volume stress case splits the DEPTH axis into slabs (`DepthSlab`): cost-volume bins are
   independent (BuildCostVolume_cuda.cu:84), every 3x3x3 conv needs neighbour planes, exchanged with
-  point-to-point sends between ranks r-1 / r+1 (`exchange_depth_halo`; NCCL over NVLink on GPUs,
-  gloo in the CPU tests), the lift is partitioned by the world-z range each slab covers.
+  point-to-point sends between ranks r-1 / r+1 (`exchange_depth_halo`; on GPUs the C-ABI `snvc_halo_exchange` over the
+  library's own NCCL communicator, `HaloComm`; torch.distributed / gloo in the CPU tests), the lift is partitioned by
+  the world-z range each slab covers.
 
 `SlabTrunk` drives any module tree with the layer interface of snvc_b200.models.submodule
 (`.fused(x, relu=, residual=, residual_mode=, out=)` on NDHWC tensors), so the slab algebra is
@@ -79,43 +80,95 @@ class DepthSlab:
         return list(range(self.d0 - HALO, self.d0 + self.Dl + HALO))
 
 
-def exchange_depth_halo(x, slab, group=None):
+class HaloComm:
+    """An NCCL communicator of the library's own (snvc_halo_comm_create) for the depth-slab halo exchange: the 128-byte
+    ncclUniqueId is created on rank 0 and broadcast through torch.distributed; afterwards an exchange is ONE C call
+    (ncclGroup of <= 2 sends + 2 receives on the caller's stream) instead of four P2POp objects and a
+    batch_isend_irecv per layer -- at 8 ranks the 10 exchanges of a volume otherwise cost more host time than the
+    3 ms of kernels they separate."""
+
+    def __init__(self, world, rank, device, group=None):
+        import ctypes
+        from snvc_b200 import _lib
+        self.world, self.rank, self.device = world, rank, device
+        self.comm = ctypes.c_void_p()
+        if world == 1:
+            return
+        L = _lib.lib()
+        buf = (ctypes.c_ubyte * 128)()
+        if rank == 0:
+            _lib.check(L.snvc_halo_unique_id(buf), "snvc_halo_unique_id")
+        t = torch.tensor(list(buf), dtype=torch.uint8, device=device)
+        dist.broadcast(t, src=_peer(0, group), group=group)
+        host = t.cpu().tolist()
+        for i, v in enumerate(host):
+            buf[i] = v
+        with torch.cuda.device(device):
+            _lib.check(L.snvc_halo_comm_create(buf, world, rank, ctypes.byref(self.comm)), "snvc_halo_comm_create")
+
+    def exchange(self, x):
+        from snvc_b200 import _lib
+        planes = x.shape[1]
+        plane_bytes = x[0, 0].numel() * x.element_size()
+        with torch.cuda.device(x.device):
+            st = _lib.lib().snvc_halo_exchange(self.comm, x.data_ptr(), planes, plane_bytes, HALO, self.rank, self.world,
+                                               _lib.stream_ptr())
+        _lib.check(st, "snvc_halo_exchange")
+        return x
+
+    def close(self):
+        from snvc_b200 import _lib
+        if self.comm:
+            _lib.lib().snvc_halo_comm_destroy(self.comm)
+            self.comm = None
+
+
+def exchange_depth_halo(x, slab, group=None, comm=None):
     """x: [1, Dl_level + 2*HALO, H, W, C] extended slab at any pyramid level (in place).
 
-    Sends the first / last HALO real planes to the previous / next rank, receives their halos; at the
-    global boundary the halo planes are zeroed (they stand for the convolution's zero padding)."""
+    Every consumer of a slab reads at most ONE plane beyond the real ones -- a 3^3 stride-1 conv one on each side, a
+    stride-2 conv (pad 1) only the lower one, a transposed conv (k3,s2,p1,op1) only the upper one -- so the exchange
+    moves one plane per direction: the first / last real plane goes to rank r-1 / r+1 and lands in their INNER halo
+    plane (index HALO-1 / -HALO); at the global boundary the inner halo plane is zeroed (the convolution's zero
+    padding).  The outer halo planes only keep stride-2 levels aligned and are never read for a real output.
+    `comm` (HaloComm): the C-ABI NCCL path (GPU); otherwise torch.distributed point-to-point ops (gloo in the CPU tests)."""
     h = HALO
-    if x.shape[1] < 3 * h:
-        raise ValueError("slab too thin for the halo exchange")
-    ops, recv_lo, recv_hi = [], None, None
+    if x.shape[0] != 1 or x.shape[1] < 2 * h + 1:
+        raise ValueError("slab too thin for the halo exchange (or batch != 1: depth slices must be contiguous)")
+    if comm is not None and x.is_cuda:
+        return comm.exchange(x)
+    lo_halo, hi_halo = x[:, h - 1:h], x[:, -h:x.shape[1] - h + 1]            # contiguous views (batch 1)
+    ops, stage_lo, stage_hi = [], None, None
     # gloo moves host memory only: stage through the CPU there (tests); NCCL sends device buffers over NVLink
     stage = slab.world > 1 and x.is_cuda and dist.get_backend(group) == "gloo"
     if slab.world > 1:
         if not slab.first:
-            send_lo = x[:, h:2 * h].contiguous()
+            send_lo = x[:, h:h + 1]
+            recv_lo = lo_halo
             if stage:
-                send_lo = send_lo.cpu()
-            recv_lo = torch.empty_like(send_lo)
+                send_lo, stage_lo = send_lo.cpu(), torch.empty(lo_halo.shape, dtype=x.dtype)
+                recv_lo = stage_lo
             ops += [dist.P2POp(dist.isend, send_lo, _peer(slab.rank - 1, group), group),
                     dist.P2POp(dist.irecv, recv_lo, _peer(slab.rank - 1, group), group)]
         if not slab.last:
-            send_hi = x[:, -2 * h:-h].contiguous()
+            send_hi = x[:, -h - 1:x.shape[1] - h]
+            recv_hi = hi_halo
             if stage:
-                send_hi = send_hi.cpu()
-            recv_hi = torch.empty_like(send_hi)
+                send_hi, stage_hi = send_hi.cpu(), torch.empty(hi_halo.shape, dtype=x.dtype)
+                recv_hi = stage_hi
             ops += [dist.P2POp(dist.isend, send_hi, _peer(slab.rank + 1, group), group),
                     dist.P2POp(dist.irecv, recv_hi, _peer(slab.rank + 1, group), group)]
     if ops:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
-    if recv_lo is not None:
-        x[:, :h] = recv_lo.to(x.device)
-    else:
-        x[:, :h] = 0
-    if recv_hi is not None:
-        x[:, -h:] = recv_hi.to(x.device)
-    else:
-        x[:, -h:] = 0
+    if slab.first or slab.world == 1:
+        lo_halo.zero_()
+    elif stage_lo is not None:
+        lo_halo.copy_(stage_lo)
+    if slab.last or slab.world == 1:
+        hi_halo.zero_()
+    elif stage_hi is not None:
+        hi_halo.copy_(stage_hi)
     return x
 
 
@@ -128,14 +181,34 @@ class SlabTrunk:
     exchange after every layer.  `model` needs attributes dres0, dres1, hg with the fused-layer
     interface; tensors are NDHWC with N == 1 (depth slices of an N=1 volume are contiguous views)."""
 
-    def __init__(self, model, slab, group=None):
-        self.m, self.slab, self.group = model, slab, group
+    def __init__(self, model, slab, group=None, comm=None):
+        self.m, self.slab, self.group, self.comm = model, slab, group, comm
 
     def _xchg(self, x):
-        return exchange_depth_halo(x, self.slab, self.group)
+        return exchange_depth_halo(x, self.slab, self.group, self.comm)
 
-    def _s1(self, layer, x, **kw):
-        return self._xchg(layer.fused(x, **kw))
+    @staticmethod
+    def _cout(layer):
+        """Output channels of a fused layer: test executors carry `.cout`; the product's modules are
+        Sequential(conv, norm) or Sequential(Sequential(conv, norm), ReLU)."""
+        c = getattr(layer, "cout", None)
+        if c:
+            return c
+        first = layer[0]
+        return first.out_channels if hasattr(first, "out_channels") else first[0].out_channels
+
+    def _s1(self, layer, x, residual=None, **kw):
+        """stride-1 conv on an ext slab [1, Dl+2*HALO, ...]: only the real planes and the two inner halo planes are
+        convolved (input view x[:, 1:-1], zero padding beyond it), so the slab costs (Dl + 2) planes of work instead of
+        (Dl + 4); the two inner halo outputs lack a depth tap and are overwritten by the exchange."""
+        cout = self._cout(layer)
+        out = torch.empty(tuple(x.shape[:-1]) + (cout,), dtype=x.dtype, device=x.device)
+        out[:, 0].zero_()
+        out[:, -1].zero_()
+        if residual is not None:
+            kw["residual"] = residual[:, 1:-1]
+        layer.fused(x[:, 1:-1], out=out[:, 1:-1], **kw)
+        return self._xchg(out)
 
     def _s2(self, layer, x, **kw):
         """stride-2 conv: ext [1, Dl+4, ...] -> ext [1, Dl/2+4, ...]; the conv output (Dl/2+2 planes, plane o
@@ -143,17 +216,21 @@ class SlabTrunk:
         N, De, H, W, _ = x.shape
         assert N == 1 and (De - 2 * HALO) % 2 == 0
         Do = (De - 2 * HALO) // 2 + 2 * HALO
-        cout = getattr(layer, "cout", None) or layer[0][0].out_channels
-        out = torch.zeros((1, Do, (H + 1) // 2, (W + 1) // 2, cout), dtype=x.dtype, device=x.device)
+        cout = self._cout(layer)
+        out = torch.empty((1, Do, (H + 1) // 2, (W + 1) // 2, cout), dtype=x.dtype, device=x.device)
+        out[:, 0].zero_()
+        out[:, -1].zero_()
         layer.fused(x, out=out[:, 1:-1], **kw)
         return self._xchg(out)
 
-    def _up(self, layer, x, **kw):
+    def _up(self, layer, x, residual=None, **kw):
         """transposed conv (k3,s2,p1,op1): input planes [1, -1) of the ext slab -> ext slab at 2x resolution."""
+        if residual is not None:
+            kw["residual"] = residual
         return self._xchg(layer.fused(x[:, 1:-1], **kw))
 
     def __call__(self, cost):
-        """cost: extended cost-volume slab [1, Dl+2*HALO, H, W, 2F] (halo planes already valid or zero)."""
+        """cost: extended cost-volume slab [1, Dl+2*HALO, H, W, 2F] (inner halo planes valid, or zero at the boundary)."""
         m = self.m
         x = self._s1(m.dres0[0], cost)
         x = self._s1(m.dres0[1], x)
@@ -186,7 +263,7 @@ def slab_z_range(zs, cv_z_min, cv_z_max, D, slab, align_corners=True):
 
 
 def slab_global_forward(model, left_feat, right_feat, shift, proj, slab, group=None, out_dtype=torch.float32,
-                        layout_out="NCDHW"):
+                        layout_out="NCDHW", comm=None):
     """Depth-slab-parallel GlobalHotPath.forward for ONE pair (N == 1).
 
     Every rank passes the same (replicated) inputs and returns (voxels[:, zlo:zhi] slice, (zlo, zhi)):
@@ -207,7 +284,7 @@ def slab_global_forward(model, left_feat, right_feat, shift, proj, slab, group=N
         cost[:, lo_pad:lo_pad + len(keep)] = cost_in
     else:
         cost = cost_in
-    feat = SlabTrunk(model, slab, group)(cost)                        # [1, Dl+2*HALO, H, W, ch]
+    feat = SlabTrunk(model, slab, group, comm)(cost)                  # [1, Dl+2*HALO, H, W, ch]
     zlo, zhi = slab_z_range(model.zs.cpu().numpy(), model.cv_range[4], model.cv_range[5], D, slab,
                             model.align_corners)
     vox = SF.frustum_lift(feat, proj, model.zs[zlo:zhi].contiguous(), model.ys, model.xs, model.cv_range,

@@ -40,3 +40,22 @@ def golden():
     def load(name):
         return dict(np.load(os.path.join(GOLDEN, name + ".npz")))
     return load
+
+
+def set_opt(monkeypatch, name, value):
+    """Set a debug switch of libsnvc_b200 for the rest of the test: the library reads its switches from the environment
+    only when it is loaded, so a test sets them through snvc_set_option (and the environment, for spawned ranks)."""
+    from snvc_b200 import _lib
+    monkeypatch.setenv(name, str(value))
+    _lib.set_option(name, value)
+
+
+@pytest.fixture(autouse=True)
+def _reset_library_options():
+    yield
+    try:
+        from snvc_b200 import _lib
+        if _lib._lib is not None:
+            _lib.set_option(None)
+    except Exception:
+        pass

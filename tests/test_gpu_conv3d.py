@@ -6,6 +6,7 @@ output the only difference is fp32 summation order (tolerance 1e-4 of max|ref|);
 the additional error is one bf16 rounding (<= 2^-8 relative; north_star bar: 1e-2)."""
 import numpy as np
 import pytest
+from conftest import set_opt
 import torch
 import torch.nn.functional as TF
 
@@ -90,7 +91,7 @@ def test_conv_s2_plane_march_variants(monkeypatch):
     _case(32, 32, 3, 2, 1, 1, False, (8, 16, 24), N=2, relu=True)
     _case(32, 64, 3, 2, 1, 1, False, (6, 20, 64), N=2, relu=True, residual_mode=1)
     _case(32, 64, 3, 2, 1, 1, False, (4, 96, 312), relu=True)
-    monkeypatch.setenv("SNVC_CONV_MAXGRID", "2")
+    set_opt(monkeypatch, "SNVC_CONV_MAXGRID", "2")
     _case(32, 64, 3, 2, 1, 1, False, (40, 16, 62), relu=True)
     _case(32, 32, 3, 2, 1, 1, False, (72, 16, 30), relu=True, residual_mode=2)
 
@@ -104,7 +105,7 @@ def test_deconv_staged_tiles_many_units_per_cta(monkeypatch):
     """Fused transposed conv with its staged (TMA load residual -> in-place update -> TMA store) epilogue: tiles
     clipped at the H / W edges, several work units per CTA (grid clamped) so that both tile buffers, the plane ring
     and the TMEM double buffer wrap, every residual mode."""
-    monkeypatch.setenv("SNVC_CONV_MAXGRID", "3")
+    set_opt(monkeypatch, "SNVC_CONV_MAXGRID", "3")
     _case(64, 32, 3, 2, 1, 1, True, (10, 20, 40), N=2, residual_mode=1)                 # hourglass conv6 (+ out residual)
     _case(64, 64, 3, 2, 1, 1, True, (6, 12, 39), relu=True, residual_mode=1)            # hourglass conv5: relu(bn + pre)
     _case(64, 32, 3, 2, 1, 1, True, (5, 9, 17), N=3)                                    # no residual
@@ -113,7 +114,7 @@ def test_deconv_staged_tiles_many_units_per_cta(monkeypatch):
 
 def test_conv_staged_tma_store_epilogue(monkeypatch):
     """Opt-in epilogue of the kd-fused kernel: rows staged in a swizzled shared-memory tile, one bulk tensor store."""
-    monkeypatch.setenv("SNVC_CONV_STORE", "staged")
+    set_opt(monkeypatch, "SNVC_CONV_STORE", "staged")
     _case(32, 32, 3, 1, 1, 1, False, (6, 10, 40), N=2, relu=True, residual_mode=1)
     _case(64, 32, 3, 1, 1, 1, False, (4, 96, 312), relu=True)
     _case(64, 64, 3, 1, 1, 1, False, (5, 12, 70), relu=True)
@@ -137,7 +138,7 @@ def test_conv_large_kernel_plane_march(monkeypatch):
     """5^3 / 7^3 plane march with streamed weights (instance conv1-conv3): more than 16 planes (the TMEM accumulator
     ring wraps), depths that are not multiples of the 4-plane group, several tile columns per CTA (grid clamped), both
     dilations (dilation 2 uses the parity-split ring; an odd depth falls back to the per-tap kernel)."""
-    monkeypatch.setenv("SNVC_CONV_MAXGRID", "2")
+    set_opt(monkeypatch, "SNVC_CONV_MAXGRID", "2")
     _case(64, 32, 7, 1, 3, 1, False, (18, 9, 40), relu=True)                               # conv1
     _case(32, 32, 5, 1, 2, 1, False, (21, 12, 60), N=2, relu=True, residual_mode=2)        # conv2
     _case(32, 32, 5, 1, 4, 2, False, (22, 10, 50), relu=True, residual_mode=2)             # conv3 (dilation 2)
@@ -151,8 +152,8 @@ def test_conv_kw_kd_fused_plane_march(monkeypatch):
     W = 40 / 14 -> 16), Cin 32 / 64, the 64 -> 64 output slices, every residual mode, ragged H / W edges, depths 1 and 2,
     and -- grid clamped -- several tile columns per CTA with depths that are not multiples of 5, so the accumulator
     ring wraps at every phase."""
-    monkeypatch.setenv("SNVC_CONV_MODE", "kw")
-    monkeypatch.setenv("SNVC_CONV_MAXGRID", "2")
+    set_opt(monkeypatch, "SNVC_CONV_MODE", "kw")
+    set_opt(monkeypatch, "SNVC_CONV_MAXGRID", "2")
     _case(32, 32, 3, 1, 1, 1, False, (13, 10, 60), N=2, relu=True, residual_mode=1)
     _case(64, 32, 3, 1, 1, 1, False, (7, 16, 40), relu=True)
     _case(64, 64, 3, 1, 1, 1, False, (6, 12, 44), relu=True, residual_mode=1)
@@ -180,7 +181,7 @@ def test_conv_cta_pair_plane_march(monkeypatch):
     for c in cases[:3]:
         _case(*c["a"], **c["k"])
     for clamp in ("1", "2"):
-        monkeypatch.setenv("SNVC_CONV_MAXGRID", clamp)
+        set_opt(monkeypatch, "SNVC_CONV_MAXGRID", clamp)
         for c in cases:
             _case(*c["a"], **c["k"])
     # pitch-42 tiles (3 rows x 42 columns = 126 of the 128 MMA rows; chosen when they waste fewer rows): W = 40 / 78 with
@@ -189,11 +190,11 @@ def test_conv_cta_pair_plane_march(monkeypatch):
     _case(64, 32, 3, 1, 1, 1, False, (5, 10, 78), relu=True)
     _case(64, 64, 3, 1, 1, 1, False, (6, 7, 118), N=2, relu=True, residual_mode=2)
     # depth-split tail units: the pair-columns left over after the whole rounds are cut into 2 / 3 / 4 depth ranges
-    monkeypatch.setenv("SNVC_CONV_MAXGRID", "2")                                            # 3 pairs on 2 clusters -> 2 ranges
+    set_opt(monkeypatch, "SNVC_CONV_MAXGRID", "2")                                            # 3 pairs on 2 clusters -> 2 ranges
     _case(64, 32, 3, 1, 1, 1, False, (15, 16, 40), relu=True, residual_mode=1)
-    monkeypatch.setenv("SNVC_CONV_MAXGRID", "3")                                            # 4 pairs on 3 clusters -> 3 ranges
+    set_opt(monkeypatch, "SNVC_CONV_MAXGRID", "3")                                            # 4 pairs on 3 clusters -> 3 ranges
     _case(32, 32, 3, 1, 1, 1, False, (13, 8, 60), N=2, relu=True, residual_mode=2)
-    monkeypatch.setenv("SNVC_CONV_MAXGRID", "4")                                            # 5 pairs on 4 clusters -> 4 ranges
+    set_opt(monkeypatch, "SNVC_CONV_MAXGRID", "4")                                            # 5 pairs on 4 clusters -> 4 ranges
     _case(32, 32, 3, 1, 1, 1, False, (16, 4, 300), relu=True, residual_mode=1)
     _case(64, 64, 3, 1, 1, 1, False, (18, 4, 270), relu=True)                               # 9 columns: ghost follower + ranges
 
@@ -236,11 +237,11 @@ def test_conv_depth_invariant_addend(monkeypatch):
     _split_case((3, 5, 33), N=2)
     _split_case((17, 10, 60), N=2)
     _split_case((6, 9, 40), N=2)                                                            # pitch-42 tiles
-    monkeypatch.setenv("SNVC_CONV_MAXGRID", "3")                                            # 4 pairs on 3 clusters -> 3 depth ranges
+    set_opt(monkeypatch, "SNVC_CONV_MAXGRID", "3")                                            # 4 pairs on 3 clusters -> 3 depth ranges
     _split_case((13, 8, 60), N=2)
-    monkeypatch.setenv("SNVC_CONV_MAXGRID", "4")                                            # 5 pairs on 4 clusters -> 4 depth ranges
+    set_opt(monkeypatch, "SNVC_CONV_MAXGRID", "4")                                            # 5 pairs on 4 clusters -> 4 depth ranges
     _split_case((16, 4, 300))
-    monkeypatch.setenv("SNVC_CONV_MAXGRID", "1")
+    set_opt(monkeypatch, "SNVC_CONV_MAXGRID", "1")
     _split_case((20, 4, 30), N=3)
     _split_case((9, 16, 40))
     _split_case((6, 3, 124))
@@ -253,8 +254,8 @@ def test_conv_depth_invariant_addend(monkeypatch):
 
 def test_conv_kd_fused_kernel_still_green(monkeypatch):
     """SNVC_CONV_MODE=kd keeps the v3 kernel (kd taps only) reachable for A/B runs; it also serves Cout = 16 / 64."""
-    monkeypatch.setenv("SNVC_CONV_MODE", "kd")
-    monkeypatch.setenv("SNVC_CONV_MAXGRID", "2")
+    set_opt(monkeypatch, "SNVC_CONV_MODE", "kd")
+    set_opt(monkeypatch, "SNVC_CONV_MAXGRID", "2")
     _case(32, 32, 3, 1, 1, 1, False, (13, 10, 60), N=2, relu=True, residual_mode=1)
     _case(64, 32, 3, 1, 1, 1, False, (7, 16, 40), relu=True)
 

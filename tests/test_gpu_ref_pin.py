@@ -81,7 +81,7 @@ def test_forward_kitti_shape_bit_exact_vs_reference_op(ref_cv):
 
 @pytest.mark.parametrize("shape,ds,dtype", [((2, 3, 6, 10), 1, np.float32), ((2, 3, 6, 10), 2, np.float32),
                                             ((2, 8, 12, 40), 1, np.float64), ((1, 32, 24, 78), 1, np.float32)])
-def test_backward_vs_reference_op(ref_cv, shape, ds, dtype):
+def test_backward_vs_reference_op(ref_cv, shape, ds, dtype, monkeypatch):
     """The reference scatters with atomicAdd (sum order varies run to run); ours is a deterministic gather."""
     N, C, IH, IW = shape
     D = len(EDGE_SHIFTS)
@@ -91,7 +91,7 @@ def test_backward_vs_reference_op(ref_cv, shape, ds, dtype):
     wl, wr = ref_cv.build_cost_volume_backward(tg, ts, ds)
     l = torch.zeros(shape, dtype=tg.dtype, device="cuda", requires_grad=True)
     r = torch.zeros(shape, dtype=tg.dtype, device="cuda", requires_grad=True)
-    os.environ["SNVC_B200_SKIP_SHIFT_CHECK"] = "1"
+    monkeypatch.setenv("SNVC_B200_SKIP_SHIFT_CHECK", "1")
     _bcv().build_cost_volume(l, r, ts, ds).backward(tg)
     tol = 1e-5 if dtype == np.float32 else 1e-13
     for got, want in ((l.grad, wl), (r.grad, wr)):

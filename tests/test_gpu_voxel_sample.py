@@ -1,6 +1,7 @@
 """GPU parity: ROI voxel sampling (A3) and frustum-to-voxel lift (A4) vs the CPU oracle."""
 import numpy as np
 import pytest
+from conftest import set_opt
 import torch
 
 import synth
@@ -145,7 +146,7 @@ def test_roi_sample_kernel_generations_agree(C, monkeypatch):
     for od in (torch.bfloat16, torch.float32):
         outs = []
         for mode in ("thread", "coop1", "v3"):
-            monkeypatch.setenv("SNVC_ROI_MODE", mode)
+            set_opt(monkeypatch, "SNVC_ROI_MODE", mode)
             outs.append(_F().roi_voxel_sample(*t, res, out_dtype=od, layout="NDHWC"))
         view = torch.int16 if od == torch.bfloat16 else torch.int32
         assert torch.equal(outs[0].view(view), outs[1].view(view))
@@ -168,10 +169,10 @@ def test_lift_cooperative_kernel_matches_thread_per_voxel_kernel(C, monkeypatch)
     assert (N * zs.numel() * ys.numel() * xs.numel()) % 32 != 0
     Ps = torch.from_numpy(np.stack([geom.P] * N)).cuda()
     for od in (torch.bfloat16, torch.float32):
-        monkeypatch.setenv("SNVC_LIFT_MODE", "thread")
+        set_opt(monkeypatch, "SNVC_LIFT_MODE", "thread")
         want, wv = F.frustum_lift(vol, Ps, zs, ys, xs, geom.cv_ranges(), True, layout_in="NDHWC", out_dtype=od,
                                   return_valid=True)
-        monkeypatch.setenv("SNVC_LIFT_MODE", "coop")
+        set_opt(monkeypatch, "SNVC_LIFT_MODE", "coop")
         got, gv = F.frustum_lift(vol, Ps, zs, ys, xs, geom.cv_ranges(), True, layout_in="NDHWC", out_dtype=od,
                                  return_valid=True)
         assert torch.equal(gv, wv) and 0.05 < wv.float().mean().item() < 0.95
