@@ -36,6 +36,7 @@ def timeit(fn, n=5, pre=None):
     b.record(); torch.cuda.synchronize(); return a.elapsed_time(b) / n
 with torch.no_grad():
     g = GraphedHotPath(m, B, 32, (96, 312), 48, torch.bfloat16, "NDHWC")
+    g_other = GraphedHotPath(m, B, 32, (96, 312), 48, torch.bfloat16, "NDHWC")   # the "next batch" (own memory pool, as in HostPipeline)
     gen = torch.Generator(device=dev).manual_seed(1)
     g(torch.randn((B, 32, 96, 312), device=dev, generator=gen), torch.randn((B, 32, 96, 312), device=dev, generator=gen),
       torch.from_numpy(plane_sweep_shifts(cfg, B)).to(dev), torch.from_numpy(KITTI_P2[None].repeat(B, 0).copy()).to(dev))
@@ -49,7 +50,7 @@ with torch.no_grad():
     moved = torch.zeros((), dtype=torch.int64, device=dev)
     ones = torch.ones(valid.numel(), dtype=torch.uint8, device=dev)
     s2 = torch.cuda.Stream()
-    for blocks in (8, 16, 32, 64, 148, 296):
+    for blocks in ((8, 16, 32, 64, 148) if world == 1 else (32,)):
         def run(v=valid):
             prev = v.reshape(-1).clone()
             L.snvc_masked_rows_to_host(vox.data_ptr(), v.data_ptr(), prev.data_ptr(), ho.data_ptr(), v.numel(), 64, blocks, moved.data_ptr(), _lib.stream_ptr())
@@ -58,9 +59,14 @@ with torch.no_grad():
         def with_compute():
             with torch.cuda.stream(s2):
                 s2.wait_stream(torch.cuda.current_stream()); run()
-            g.replay(); torch.cuda.current_stream().wait_stream(s2)
+            g_other.replay(); torch.cuda.current_stream().wait_stream(s2)
         t2 = timeit(with_compute)
         print(f"[rank {rank}] masked return, {blocks:3d} blocks: valid {frac:.3f} -> {mb*frac:.0f} MB in {t:.2f} ms = {mb*frac/t:.1f} GB/s | all rows {mb:.0f} MB in {t1:.2f} ms = {mb/t1:.1f} GB/s | with a concurrent step: {t2:.2f} ms", flush=True)
-    tc = timeit(lambda: g.replay()); print(f"[rank {rank}] compute only: {tc:.2f} ms", flush=True)
+    tc = timeit(lambda: g_other.replay()); print(f"[rank {rank}] compute only: {tc:.2f} ms", flush=True)
     assert torch.equal(ho.view(torch.int16), vox.cpu().view(torch.int16))
+    def dense_with_compute():
+        with torch.cuda.stream(s2):
+            s2.wait_stream(torch.cuda.current_stream()); ho.copy_(vox, non_blocking=True)
+        g_other.replay(); torch.cuda.current_stream().wait_stream(s2)
+    t3 = timeit(dense_with_compute); print(f"[rank {rank}] dense cudaMemcpyAsync with a concurrent step: {t3:.2f} ms", flush=True)
 if world > 1: dist.destroy_process_group()

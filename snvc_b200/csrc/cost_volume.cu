@@ -254,7 +254,7 @@ cv_ndhwc_bf16_kernel(const float* __restrict__ left, const float* __restrict__ r
       const float lx = __int_as_float(te.y);
       uint4 v = make_uint4(0u, 0u, 0u, 0u);
       if (te.x >= 0) {                                         // right half: 1-D interpolation along the row
-        if (xl >= rlo) {
+        if (xl >= rlo && xh < rhi) {
           if (xl != cur_xl || xh != cur_xh) {
             if (xl == cur_xh) {
 #pragma unroll
@@ -275,7 +275,8 @@ cv_ndhwc_bf16_kernel(const float* __restrict__ left, const float* __restrict__ r
             cur_xl = xl; cur_xh = xh;
           }
         } else {
-          // sample left of the staged window (very large shift on a w-tiled row): read HBM directly
+          // sample outside the staged window (very large shift on a w-tiled row -> left of it; a NEGATIVE shift, which the
+          // reference's Python layer rejects but this entry point cannot see, -> right of it): read HBM directly
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             r0[j] = rrow[(int64_t)(cg * 8 + j) * cstride + xl];

@@ -90,6 +90,19 @@ disparity_regression_kernel(const float* __restrict__ prob, const float* __restr
   }
 }
 
+// any H*W, any alignment: one pixel per thread (the reference's torch.sum accepts every shape, submodule.py:82-83)
+__global__ void __launch_bounds__(256)
+disparity_regression_scalar_kernel(const float* __restrict__ prob, const float* __restrict__ depth, float* __restrict__ out,
+                                   int K, int64_t HW, int64_t total /* N*HW */) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = i / HW, q = i - n * HW;
+    const float* p = prob + n * K * HW + q;
+    float a = 0.f;
+    for (int k = 0; k < K; ++k) a += __ldcs(p + (int64_t)k * HW) * __ldg(depth + k);
+    out[i] = a;
+  }
+}
+
 }  // namespace
 }  // namespace snvc
 
@@ -124,8 +137,12 @@ extern "C" int snvc_disparity_regression(const float* prob, const float* depth_v
   SNVC_CHECK_ARG(N >= 0 && K > 0 && HW > 0, "bad dimensions");
   if (N == 0) return 0;
   SNVC_CHECK_ARG(prob && depth_values && out, "null pointer");
-  SNVC_CHECK_ARG(HW % 4 == 0 && (reinterpret_cast<uintptr_t>(prob) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
-                 "H*W must be a multiple of 4 and the buffers 16-byte aligned");
+  if (HW % 4 != 0 || (reinterpret_cast<uintptr_t>(prob) & 15) != 0 || (reinterpret_cast<uintptr_t>(out) & 15) != 0) {
+    const int64_t total = N * HW;
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total, 256), (int64_t)sm_count() * 8));
+    disparity_regression_scalar_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(prob, depth_values, out, (int)K, HW, total);
+    return launch_status("disparity_regression_scalar_kernel");
+  }
   const int64_t total4 = N * HW / 4;
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total4, 256), (int64_t)sm_count() * 8));
   disparity_regression_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(prob, depth_values, out, (int)K, HW, total4);

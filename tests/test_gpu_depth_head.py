@@ -23,6 +23,20 @@ def test_disparity_regression_matches_reference_module_semantics():
     assert got.shape == want.shape and _relerr(got, want) <= 1e-6
 
 
+def test_disparity_regression_any_shape_and_alignment():
+    """The reference's torch.sum accepts every shape (submodule.py:82-83): odd H*W and a non-16-byte-aligned view."""
+    from snvc_b200.models.submodule import disparityregression
+    m = disparityregression(7, None).cuda()
+    depth = torch.linspace(1.0, 9.0, 7)
+    x = torch.softmax(torch.from_numpy(synth.det_uniform((3, 7, 5, 9), 4, -3, 3, bf16=False)), dim=1)     # H*W = 45
+    want = torch.sum(x * depth[None, :, None, None], 1).numpy()
+    assert _relerr(m(x.cuda(), depth.cuda()).cpu().numpy(), want) <= 1e-6
+    big = torch.zeros(3 * 7 * 5 * 9 + 1, device="cuda")
+    view = big[1:].view(3, 7, 5, 9)                                           # 4-byte aligned only
+    view.copy_(x)
+    assert _relerr(m(view, depth.cuda()).cpu().numpy(), want) <= 1e-6
+
+
 @pytest.mark.parametrize("ac", [True, False])
 @pytest.mark.parametrize("shape", [((12, 6, 10), (48, 24, 40)), ((48, 24, 78), (192, 96, 312)), ((5, 7, 9), (11, 13, 30))])
 def test_fused_depth_regression_vs_torch_ops(ac, shape):
