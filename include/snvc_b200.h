@@ -79,7 +79,9 @@ int snvc_cost_volume_fwd(const void* left, const void* right, const void* shift,
  * right_vol   : [N, D, IH/ds, IW/ds, C]  = channels [C, 2C) of the NDHWC volume above (the shifted right features)
  * left_planes : [N, 3, IH/ds, IW/ds, C]  = the left features, channels-last bf16, on three identical planes -- the
  *               input of the 3-plane convolution that yields the depth-invariant addend of snvc_conv3d_fwd_addend.
- * Together they carry exactly the information of the [N,D,H,W,2C] volume; half the bytes are written. */
+ * Together they carry exactly the information of the [N,D,H,W,2C] volume; half the bytes are written.
+ * Either output pointer may be NULL: the halves are independent launches, so a caller can enqueue them on different
+ * streams (GlobalHotPath overlaps left planes -> addend convolution with the right-half build). */
 int snvc_cost_volume_split_fwd(const void* left, const void* right, const void* shift, void* right_vol,
                                void* left_planes, int64_t N, int64_t C, int64_t IH, int64_t IW, int64_t D,
                                int32_t downsample, void* stream);

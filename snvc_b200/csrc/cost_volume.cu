@@ -490,7 +490,8 @@ __global__ void cv_xlow_kernel(const float* __restrict__ shift, int32_t* __restr
 }
 
 int launch_cv_ndhwc(const void* left, const void* right, const void* shift, void* cost, void* left_planes, int64_t N,
-                    int64_t C, int64_t IH, int64_t IW, int64_t D, int ds, int64_t H, int64_t W, cudaStream_t stream);
+                    int64_t C, int64_t IH, int64_t IW, int64_t D, int ds, int64_t H, int64_t W, cudaStream_t stream,
+                    int parts = 3);
 
 }  // namespace
 }  // namespace snvc
@@ -555,10 +556,13 @@ extern "C" int snvc_cost_volume_fwd(const void* left, const void* right, const v
 
 namespace snvc {
 namespace {
+// parts (split form only): bit 0 = right-half volume, bit 1 = left planes (two independent launches)
 int launch_cv_ndhwc(const void* left, const void* right, const void* shift, void* cost, void* left_planes, int64_t N,
-                    int64_t C, int64_t IH, int64_t IW, int64_t D, int ds, int64_t H, int64_t W, cudaStream_t stream) {
+                    int64_t C, int64_t IH, int64_t IW, int64_t D, int ds, int64_t H, int64_t W, cudaStream_t stream,
+                    int parts) {
   SNVC_CHECK_ARG(C % 8 == 0, "NDHWC cost volume needs C %% 8 == 0 (got %lld)", (long long)C);
-  if (left_planes && H <= 2147483647ll && N <= 65535 && !opt(OPT_CV_SPLIT_OLD)) {
+  const bool split_form = left_planes != nullptr || parts != 3;
+  if (split_form && H <= 2147483647ll && N <= 65535 && (!opt(OPT_CV_SPLIT_OLD) || parts != 3)) {
     // split form, whole rows staged: the right row [img_w][C] fp32 + the sample table of one depth split (the left planes
     // are a second, small launch of the same kernel)
     const size_t rows = (size_t)IW * C * 4;
@@ -590,10 +594,13 @@ int launch_cv_ndhwc(const void* left, const void* right, const void* shift, void
         if (std::max(smem, smem_left) > 48 * 1024)
           SNVC_CUDA_OK(cudaFuncSetAttribute(cv_split_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)std::max(smem, smem_left)));
-        cv_split_bf16_kernel<<<dim3((unsigned)H, (unsigned)N, 1), 512, smem_left, stream>>>(
-            (const float*)left, (const float*)right, (const float*)shift, (__nv_bfloat16*)cost, (__nv_bfloat16*)left_planes,
-            (int)C, (int)IH, (int)IW, (int)D, (int)H, (int)W, ds, d_per, mask, 2);
-        if (int e = launch_status("cv_split_bf16_kernel")) return e;
+        if (parts & 2) {
+          cv_split_bf16_kernel<<<dim3((unsigned)H, (unsigned)N, 1), 512, smem_left, stream>>>(
+              (const float*)left, (const float*)right, (const float*)shift, (__nv_bfloat16*)cost, (__nv_bfloat16*)left_planes,
+              (int)C, (int)IH, (int)IW, (int)D, (int)H, (int)W, ds, d_per, mask, 2);
+          if (int e = launch_status("cv_split_bf16_kernel")) return e;
+        }
+        if (!(parts & 1)) return 0;
         dim3 grid((unsigned)H, (unsigned)N, (unsigned)dsplit);
         cv_split_bf16_kernel<<<grid, 512, smem, stream>>>((const float*)left, (const float*)right, (const float*)shift,
                                                            (__nv_bfloat16*)cost, (__nv_bfloat16*)left_planes, (int)C, (int)IH,
@@ -602,6 +609,7 @@ int launch_cv_ndhwc(const void* left, const void* right, const void* shift, void
       }
     }
   }
+  if (parts != 3) return fail(SNVC_E_UNSUPPORTED, "split cost volume: a single part needs rows that fit shared memory");
   {
     SNVC_CHECK_ARG((reinterpret_cast<uintptr_t>(cost) & 15) == 0, "cost must be 16-byte aligned");
     SNVC_CHECK_ARG(H <= 2147483647ll && N <= 65535, "H/N too large");
@@ -661,9 +669,13 @@ extern "C" int snvc_cost_volume_split_fwd(const void* left, const void* right, c
   SNVC_CHECK_ARG(IH % ds == 0 && IW % ds == 0, "IH and IW must be multiples of downsample");
   const int64_t H = IH / ds, W = IW / ds;
   if (N * C * D * H * W == 0) return 0;
-  SNVC_CHECK_ARG(left && right && shift && right_vol && left_planes, "null pointer");
-  SNVC_CHECK_ARG((reinterpret_cast<uintptr_t>(left_planes) & 15) == 0, "left_planes must be 16-byte aligned");
-  return launch_cv_ndhwc(left, right, shift, right_vol, left_planes, N, C, IH, IW, D, ds, H, W, (cudaStream_t)stream_);
+  SNVC_CHECK_ARG(left && right && shift && (right_vol || left_planes), "null pointer");
+  SNVC_CHECK_ARG(((reinterpret_cast<uintptr_t>(left_planes) | reinterpret_cast<uintptr_t>(right_vol)) & 15) == 0,
+                 "right_vol and left_planes must be 16-byte aligned");
+  // either output may be NULL: the two halves are independent launches, so a caller can enqueue them on different
+  // streams (the left planes feed the small addend convolution, which then overlaps the right-half build)
+  const int parts = (right_vol ? 1 : 0) | (left_planes ? 2 : 0);
+  return launch_cv_ndhwc(left, right, shift, right_vol, left_planes, N, C, IH, IW, D, ds, H, W, (cudaStream_t)stream_, parts);
 }
 
 extern "C" int snvc_cost_volume_bwd(const void* grad, const void* shift, void* grad_left, void* grad_right, int64_t N,

@@ -87,11 +87,12 @@ def build_cost_volume_ndhwc_bf16(left, right, shift, downsample=1):
     return _forward(left, right, shift, downsample, _lib.BF16, _lib.NDHWC)
 
 
-def build_cost_volume_split_bf16(left, right, shift, downsample=1):
+def build_cost_volume_split_bf16(left, right, shift, downsample=1, parts="both"):
     """Split form of the NDHWC bf16 cost volume (snvc_cost_volume_split_fwd): the left half is a pure broadcast over
     depth (BuildCostVolume_cuda.cu:84-86), so it is written once.  Returns
     (right_vol [N,D,H,W,C] = channels [C,2C) of the full volume, left_planes [N,3,H,W,C] = the left features on three
-    identical planes, the input of the depth-invariant part of the first trunk convolution)."""
+    identical planes, the input of the depth-invariant part of the first trunk convolution).
+    `parts` = "right" / "left" builds (and returns) only that half: the two are independent launches."""
     _check_inputs(left, right, shift)
     if left.dtype != torch.float32:
         raise RuntimeError("build_cost_volume_split_bf16: fp32 features only")
@@ -100,13 +101,21 @@ def build_cost_volume_split_bf16(left, right, shift, downsample=1):
     N, C, IH, IW = left.shape
     D = shift.size(1)
     H, W = IH // ds, IW // ds
-    right_vol = torch.empty((N, D, H, W, C), dtype=torch.bfloat16, device=left.device)
-    left_planes = torch.empty((N, 3, H, W, C), dtype=torch.bfloat16, device=left.device)
+    right_vol = left_planes = None
+    if parts in ("both", "right"):
+        right_vol = torch.empty((N, D, H, W, C), dtype=torch.bfloat16, device=left.device)
+    if parts in ("both", "left"):
+        left_planes = torch.empty((N, 3, H, W, C), dtype=torch.bfloat16, device=left.device)
     with torch.cuda.device(left.device):
         st = _lib.lib().snvc_cost_volume_split_fwd(left.data_ptr(), right.data_ptr(), shift.data_ptr(),
-                                                   right_vol.data_ptr(), left_planes.data_ptr(), N, C, IH, IW, D, ds,
-                                                   _lib.stream_ptr())
+                                                   right_vol.data_ptr() if right_vol is not None else None,
+                                                   left_planes.data_ptr() if left_planes is not None else None,
+                                                   N, C, IH, IW, D, ds, _lib.stream_ptr())
     _lib.check(st, "snvc_cost_volume_split_fwd")
+    if parts == "right":
+        return right_vol
+    if parts == "left":
+        return left_planes
     return right_vol, left_planes
 
 

@@ -138,13 +138,15 @@ class GraphedHotPath:
     batch are captured once -- the C ABI launches on the caller's stream, keeps no host state and never synchronises,
     so it is capturable as is -- and replayed with one `cudaGraphLaunch` per stage.
 
-    `stages=True` captures one graph per stage (`stage_names`: cost volume | [3-plane addend convolution of the split
-    first layer] | dres0.conv1 | rest of the trunk | lift) sharing one memory pool, so a caller can record events between them (bench.py); `stages=False` captures one graph.
+    `stages=True` captures one graph per stage (`stage_names`: cost volume (split form: with the 3-plane addend convolution
+    of the first layer on a forked stream) | dres0.conv1 | rest of the trunk | lift) sharing one memory pool, so a caller can record events between them (bench.py); `stages=False` captures one graph.
     Inputs are copied into the graph's static buffers (`self.inputs`); the result is the static tensor `self.vox`
     (valid until the next replay).  `launches_per_replay` = kernels captured, from the library's launch counter."""
 
     def __init__(self, model, batch, feat_channels, feat_hw, depth_bins, out_dtype=torch.bfloat16, layout_out="NDHWC",
-                 stages=False):
+                 stages=False, consumer=None):
+        """`consumer(vox)`: an on-device consumer of the lifted volume (e.g. RPN3DHead + decode_proposals) captured as one
+        more stage behind the lift; its return value is kept in `self.consumed` (static tensors, valid until the next replay)."""
         from snvc_b200 import _lib
         self.model = model
         dev = next(model.parameters()).device
@@ -158,16 +160,30 @@ class GraphedHotPath:
         tail = [lambda: setattr(self, "_feat", model.trunk_tail(self._x1)),
                 lambda: self._set_lift(model.lift(self._feat, pr, out_dtype, layout_out, return_valid=True))]
         if self.split:
-            # five stages: the 3-plane addend convolution is part of the first layer but gets its own graph, so that the
-            # "conv1" stage is the single large launch a caller may want to time on its own
-            fns = [lambda: setattr(self, "_cost", build_cost_volume_split_bf16(l, r, sh, 1)),
-                   lambda: setattr(self, "_addend", model.trunk_head_addend(self._cost[1])),
-                   lambda: setattr(self, "_x1", model.trunk_head_right(self._cost[0], self._addend))] + tail
-            self.stage_names = ["cost_volume", "conv1_addend", "conv1", "trunk_rest", "lift"]
+            # The left planes and the 3-plane addend convolution they feed do not depend on the right-half volume: they are
+            # captured on a forked stream, so the latency-bound addend convolution (14 tile columns per CTA pair, ~50 us)
+            # runs under the HBM-bound right-half build instead of after it.
+            self._side = torch.cuda.Stream(dev)
+
+            def cost_volume_stage():
+                cur = torch.cuda.current_stream(dev)
+                self._side.wait_stream(cur)
+                with torch.cuda.stream(self._side):
+                    self._lp = build_cost_volume_split_bf16(l, r, sh, 1, parts="left")
+                    self._addend = model.trunk_head_addend(self._lp)
+                self._rv = build_cost_volume_split_bf16(l, r, sh, 1, parts="right")
+                cur.wait_stream(self._side)
+
+            fns = [cost_volume_stage, lambda: setattr(self, "_x1", model.trunk_head_right(self._rv, self._addend))] + tail
+            self.stage_names = ["cost_volume", "conv1", "trunk_rest", "lift"]
         else:
             fns = [lambda: setattr(self, "_cost", build_cost_volume_ndhwc_bf16(l, r, sh, 1)),
                    lambda: setattr(self, "_x1", model.trunk_head(self._cost))] + tail
             self.stage_names = ["cost_volume", "conv1", "trunk_rest", "lift"]
+        self.consumed = None
+        if consumer is not None:
+            fns.append(lambda: setattr(self, "consumed", consumer(self.vox)))
+            self.stage_names.append("consumer")
         if not stages:
             parts = list(fns)
             fns = [lambda: [f() for f in parts]]
@@ -311,44 +327,54 @@ class RPN3DHead(nn.Module):
         return cls.permute(0, 3, 1, 2), reg.permute(0, 3, 1, 2), ctr.permute(0, 3, 1, 2)
 
 
+class ProposalDecoder:
+    """BEV head outputs -> rotated-NMS'd proposals per pair, entirely on the device (no host synchronisation, CUDA-graph
+    capturable): scores sigmoid(cls) * sigmoid(centerness) per (cell, angle anchor), the `pre_nms` best are decoded as
+    [x + dx, y_a + dy, z + dz, l * e^dl, w * e^dw, h * e^dh, angle_a + dtheta] around compute_locations_bev
+    (torch_utils.py:77-98; 7-parameter regression, loss3d.py:101) and passed to the rotated BEV NMS (snvc_nms_bev, N4).
+    Restated decoder: the reference ships the heads' loss, not a decoder."""
+
+    def __init__(self, cfg, device, anchor_size=(1.56, 1.6, 3.9), anchor_y=1.0, pre_nms=512, iou_thresh=0.25):
+        self.zs = voxel_centres(cfg.Z_MIN, cfg.Z_MAX, cfg.VOXEL_Z_SIZE).to(device)
+        self.xs = voxel_centres(cfg.X_MIN, cfg.X_MAX, cfg.VOXEL_X_SIZE).to(device)
+        self.anchor_size, self.anchor_y, self.pre_nms, self.iou_thresh = anchor_size, anchor_y, pre_nms, iou_thresh
+
+    def __call__(self, bbox_cls, bbox_reg, bbox_centerness):
+        """-> (boxes [N, k, 7] in score order, scores [N, k], keep [N, k] int64 kept positions padded with -1,
+        num_keep [N] int32), k = min(pre_nms, cells * anchors)."""
+        N, A, Z, X = bbox_cls.shape
+        dev = bbox_cls.device
+        zs, xs = self.zs, self.xs
+        angles = torch.arange(A, device=dev, dtype=torch.float32) * (np.pi / A)
+        score = (torch.sigmoid(bbox_cls) * torch.sigmoid(bbox_centerness)).reshape(N, -1)          # [N, A*Z*X]
+        k = min(self.pre_nms, score.shape[1])
+        top, idx = score.topk(k, dim=1)
+        a = idx // (Z * X)
+        cell = idx % (Z * X)
+        zi, xi = cell // X, cell % X
+        reg = bbox_reg.reshape(N, A, -1, Z * X)                                                      # [N, A, R, Z*X]
+        if reg.shape[2] != 7:
+            raise RuntimeError("ProposalDecoder: 7-parameter regression expected (cfg.box_corner_parameters = False)")
+        sel = reg[torch.arange(N, device=dev)[:, None], a, :, cell]                                  # [N, k, 7]
+        h0, w0, l0 = self.anchor_size
+        boxes = torch.stack([xs[xi] + sel[..., 0], self.anchor_y + sel[..., 1], zs[zi] + sel[..., 2],
+                             l0 * torch.exp(sel[..., 5].clamp(-2, 2)), w0 * torch.exp(sel[..., 4].clamp(-2, 2)),
+                             h0 * torch.exp(sel[..., 3].clamp(-2, 2)), angles[a] + sel[..., 6]], dim=-1)
+        # BEV NMS works on [x, y(bev) = z, z, dx, dy, dz, heading]: put the ground-plane axes first
+        bev_boxes = torch.stack([boxes[..., 0], boxes[..., 2], boxes[..., 1], boxes[..., 3], boxes[..., 4], boxes[..., 5],
+                                 boxes[..., 6]], dim=-1).contiguous()
+        keeps, nums = [], []
+        for n in range(N):
+            sel_n, num = SF.nms_gpu_device(bev_boxes[n], top[n], self.iou_thresh)
+            keeps.append(sel_n)
+            nums.append(num)
+        return boxes, top, torch.stack(keeps), torch.stack(nums)
+
+
 def decode_proposals(bbox_cls, bbox_reg, bbox_centerness, cfg, anchor_size=(1.56, 1.6, 3.9), anchor_y=1.0, pre_nms=512,
                      iou_thresh=0.25):
-    """BEV head outputs -> rotated-NMS'd proposals per pair, entirely on the device (no host synchronisation): scores
-    sigmoid(cls) * sigmoid(centerness) per (cell, angle anchor), the `pre_nms` best are decoded as
-    [x + dx, y_a + dy, z + dz, h * e^dh, w * e^dw, l * e^dl, angle_a + dtheta] around compute_locations_bev
-    (torch_utils.py:77-98; 7-parameter regression, loss3d.py:101) and passed to the rotated BEV NMS (snvc_nms_bev, N4).
-    Returns (boxes [N, pre_nms, 7] in score order, scores [N, pre_nms], keep [N, pre_nms] int64 kept positions padded
-    with -1, num_keep [N] int32).  Restated decoder: the reference ships the heads' loss, not a decoder."""
-    N, AK, Z, X = bbox_cls.shape
-    A = AK
-    dev = bbox_cls.device
-    zs = voxel_centres(cfg.Z_MIN, cfg.Z_MAX, cfg.VOXEL_Z_SIZE).to(dev)
-    xs = voxel_centres(cfg.X_MIN, cfg.X_MAX, cfg.VOXEL_X_SIZE).to(dev)
-    angles = torch.arange(A, device=dev, dtype=torch.float32) * (np.pi / A)
-    score = (torch.sigmoid(bbox_cls) * torch.sigmoid(bbox_centerness)).reshape(N, -1)          # [N, A*Z*X]
-    k = min(pre_nms, score.shape[1])
-    top, idx = score.topk(k, dim=1)
-    a = idx // (Z * X)
-    cell = idx % (Z * X)
-    zi, xi = cell // X, cell % X
-    reg = bbox_reg.reshape(N, A, -1, Z * X)                                                      # [N, A, R, Z*X]
-    R = reg.shape[2]
-    sel = reg[torch.arange(N, device=dev)[:, None], a, :, cell]                                  # [N, k, R]
-    if R != 7:
-        raise RuntimeError("decode_proposals: 7-parameter regression expected (cfg.box_corner_parameters = False)")
-    h0, w0, l0 = anchor_size
-    boxes = torch.stack([xs[xi] + sel[..., 0], anchor_y + sel[..., 1], zs[zi] + sel[..., 2],
-                         l0 * torch.exp(sel[..., 5].clamp(-2, 2)), w0 * torch.exp(sel[..., 4].clamp(-2, 2)),
-                         h0 * torch.exp(sel[..., 3].clamp(-2, 2)), angles[a] + sel[..., 6]], dim=-1)
-    # BEV NMS works on [x, y(bev) = z, z, dx, dy, dz, heading]: put the ground-plane axes first
-    bev_boxes = torch.stack([boxes[..., 0], boxes[..., 2], boxes[..., 1], boxes[..., 3], boxes[..., 4], boxes[..., 5],
-                             boxes[..., 6]], dim=-1).contiguous()
-    keeps, nums = [], []
-    for n in range(N):
-        sel_n, num = SF.nms_gpu_device(bev_boxes[n], top[n], iou_thresh)
-        keeps.append(sel_n)
-        nums.append(num)
-    return boxes, top, torch.stack(keeps), torch.stack(nums)
+    """One-shot form of `ProposalDecoder` (builds the cell-centre vectors on every call; not graph-capturable)."""
+    return ProposalDecoder(cfg, bbox_cls.device, anchor_size, anchor_y, pre_nms, iou_thresh)(bbox_cls, bbox_reg, bbox_centerness)
 
 
 class HostPipeline:
