@@ -25,8 +25,14 @@ for r in data:
         try:
             f = float(v)
             if U[i] == 'byte': f /= 1e9
+            if U[i] == 'Kbyte': f /= 1e6
+            if U[i] == 'Mbyte': f /= 1e3
+            if U[i] == 'Tbyte': f *= 1e3
             if U[i] in ('ns', 'nsecond'): f /= 1e6
-            if U[i] == 'us' or U[i] == 'usecond': f /= 1e3
+            if U[i] in ('us', 'usecond'): f /= 1e3
+            if U[i] in ('s', 'second'): f *= 1e3
+            if 'per_second' in b and U[i] in ('Ghz', 'GHz'): f *= 1e3
+            if 'per_second' in b and U[i] in ('hz', 'Hz'): f /= 1e6
             vals.append(f'{f:9.3f}')
         except ValueError:
             vals.append(v[:9].rjust(9))

@@ -4,7 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 import torch, synth
 from snvc_b200 import conv as C
-from snvc_b200.models.stereonet import RPN3DHead, decode_proposals
+from snvc_b200.models.stereonet import RPN3DHead, decode_proposals, ProposalDecoder
 from snvc_b200.utils.geometry import kitti_global_cfg
 dev = torch.device("cuda", 0)
 cfg = kitti_global_cfg()
@@ -31,13 +31,22 @@ with torch.no_grad():
     rpn(vox); torch.cuda.synchronize()
     for n, x, y in recs: print(f"{x.elapsed_time(y)*1e3:9.1f} us  {n}")
     C.PackedConv3d.__call__, C.PackedConv2d.__call__ = o3, o2
-    g = torch.cuda.CUDAGraph()
-    s = torch.cuda.Stream()
-    with torch.cuda.stream(s):
-        with torch.cuda.graph(g):
-            res = decode_proposals(*rpn(vox), rcfg, pre_nms=256)
-    torch.cuda.synchronize()
-    a.record()
-    for _ in range(5): g.replay()
-    b.record(); torch.cuda.synchronize()
-    print(f"graph replay rpn + decode + nms: {a.elapsed_time(b)/5:.3f} ms; kept {res[3].tolist()}")
+    dec = ProposalDecoder(rcfg, dev, pre_nms=256)
+    out = rpn(vox)
+    for name, fn in (("rpn", lambda: rpn(vox)), ("decode+nms", lambda: dec(*out)), ("rpn+decode+nms", lambda: dec(*rpn(vox)))):
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            fn()
+            with torch.cuda.graph(g):
+                res = fn()
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(5): g.replay()
+        b.record(); torch.cuda.synchronize()
+        print(f"graph replay {name}: {a.elapsed_time(b)/5:.3f} ms")
+    print("kept", res[3].tolist())
+    import torch.profiler as tp
+    with tp.profile(activities=[tp.ProfilerActivity.CUDA]) as prof:
+        g.replay(); torch.cuda.synchronize()
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=14, max_name_column_width=60))

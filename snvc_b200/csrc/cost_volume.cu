@@ -328,13 +328,23 @@ cv_split_bf16_kernel(const float* __restrict__ left, const float* __restrict__ r
   const int64_t cstride = (int64_t)img_h * img_w;
   const float* rrow = right + ((int64_t)n * C * img_h + ih) * img_w;
   const float* lrow = left + ((int64_t)n * C * img_h + ih) * img_w;
-  // staging: a warp takes one channel at a time and runs along the row (coalesced 4-byte cp.async, no divisions)
+  // staging with 4-byte cp.async: a warp instruction covers 8 consecutive columns x the 4 channels of one 16-byte chunk.
+  // With the XOR swizzle the 8 columns land in 8 different chunk positions, so the 32 lanes hit 32 different banks (the
+  // earlier one-channel-per-warp mapping was a 4-way conflict: ncu showed 4 wavefronts per LDGSTS, a fifth of the kernel's
+  // shared-memory wavefronts), while every lane quartet still reads whole 32-byte sectors of a channel row.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-  for (int c = warp; c < C; c += nwarp) {
-    if (do_right)
-      for (int col = lane; col < img_w; col += 32) cp_async_4(&sR[swz(col, c, C, mask)], rrow + c * cstride + col);
-    if (do_left)
-      for (int col = lane; col < lw; col += 32) cp_async_4(&sL[swz(col, c, C, mask)], lrow + c * cstride + col);
+  {
+    const int c4 = lane & 3, col8 = lane >> 2;
+    const int nchunk = C >> 2;
+    const int srcw = do_right ? img_w : lw;
+    const float* srow = do_right ? rrow : lrow;
+    float* sdst = do_right ? sR : sL;
+    const int ncb = (srcw + 7) >> 3;
+    for (int t = warp; t < nchunk * ncb; t += nwarp) {
+      const int ch = t % nchunk, cb = t / nchunk;
+      const int c = ch * 4 + c4, col = cb * 8 + col8;
+      if (col < srcw) cp_async_4(&sdst[swz(col, c, C, mask)], srow + c * cstride + col);
+    }
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
   for (int dd = warp; dd < dn; dd += nwarp) {
@@ -390,7 +400,8 @@ cv_split_bf16_kernel(const float* __restrict__ left, const float* __restrict__ r
     // one step: `lo` must end up holding column xl, `hi` column xh; on entry `lo` holds column `held` (the previous
     // step's high column), `hi` is free
     auto step = [&](float2 (&lo)[4], float2 (&hi)[4], int pw, __nv_bfloat16* op) {
-      const int2 te = tab[pw];
+      int2 te;                                           // one LDS.64 (the table is 8-byte aligned; the compiler cannot see it)
+      asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(te.x), "=r"(te.y) : "r"((uint32_t)__cvta_generic_to_shared(tab + pw)));
       uint4 v = make_uint4(0u, 0u, 0u, 0u);
       if (te.x >= 0) {
         const int xl = te.x & 0x3fffffff, xh = xl + ((te.x >> 30) & 1);
@@ -602,7 +613,22 @@ int launch_cv_ndhwc(const void* left, const void* right, const void* shift, void
         }
         if (!(parts & 1)) return 0;
         dim3 grid((unsigned)H, (unsigned)N, (unsigned)dsplit);
-        cv_split_bf16_kernel<<<grid, 512, smem, stream>>>((const float*)left, (const float*)right, (const float*)shift,
+        // threads: a lane owns (bin, strip of columns, 8 channels); pick the block size (a multiple of 32, <= 512) whose
+        // strips -- odd length, see the kernel -- cover the row with the least padding (KITTI: 12 bins x 4 groups x 8
+        // strips of 39 columns = 384 threads, no padding; 512 threads = 10 strips of 33 = 5.8 % padded + an idle warp)
+        int threads = 512;
+        {
+            const int per_strip = std::min(d_per, (int)D) * (int)(C / 8);
+            double best_w = 1e30;
+            for (int t = 512; t >= 256; t -= 32) {
+              const int ns = std::max(1, t / per_strip);
+              const int L = (int)(((W + ns - 1) / ns) | 1);
+              const double waste = (double)ns * L / (double)W * ((double)t / (double)(ns * per_strip > t ? t : ns * per_strip));
+              if (waste < best_w - 1e-9) { best_w = waste; threads = t; }
+            }
+            if (const char* o = opt(OPT_CV_THREADS)) threads = std::max(32, std::min(512, atoi(o) / 32 * 32));
+        }
+        cv_split_bf16_kernel<<<grid, threads, smem, stream>>>((const float*)left, (const float*)right, (const float*)shift,
                                                            (__nv_bfloat16*)cost, (__nv_bfloat16*)left_planes, (int)C, (int)IH,
                                                            (int)IW, (int)D, (int)H, (int)W, ds, d_per, mask, 1);
         return launch_status("cv_split_bf16_kernel");

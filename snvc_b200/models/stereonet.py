@@ -138,8 +138,8 @@ class GraphedHotPath:
     batch are captured once -- the C ABI launches on the caller's stream, keeps no host state and never synchronises,
     so it is capturable as is -- and replayed with one `cudaGraphLaunch` per stage.
 
-    `stages=True` captures one graph per stage (`stage_names`: cost volume (split form: with the 3-plane addend convolution
-    of the first layer on a forked stream) | dres0.conv1 | rest of the trunk | lift) sharing one memory pool, so a caller can record events between them (bench.py); `stages=False` captures one graph.
+    `stages=True` captures one graph per stage (`stage_names`: cost volume | [3-plane addend convolution of the split
+    first layer] | dres0.conv1 | rest of the trunk | lift) sharing one memory pool, so a caller can record events between them (bench.py); `stages=False` captures one graph.
     Inputs are copied into the graph's static buffers (`self.inputs`); the result is the static tensor `self.vox`
     (valid until the next replay).  `launches_per_replay` = kernels captured, from the library's launch counter."""
 
@@ -160,22 +160,15 @@ class GraphedHotPath:
         tail = [lambda: setattr(self, "_feat", model.trunk_tail(self._x1)),
                 lambda: self._set_lift(model.lift(self._feat, pr, out_dtype, layout_out, return_valid=True))]
         if self.split:
-            # The left planes and the 3-plane addend convolution they feed do not depend on the right-half volume: they are
-            # captured on a forked stream, so the latency-bound addend convolution (14 tile columns per CTA pair, ~50 us)
-            # runs under the HBM-bound right-half build instead of after it.
-            self._side = torch.cuda.Stream(dev)
-
-            def cost_volume_stage():
-                cur = torch.cuda.current_stream(dev)
-                self._side.wait_stream(cur)
-                with torch.cuda.stream(self._side):
-                    self._lp = build_cost_volume_split_bf16(l, r, sh, 1, parts="left")
-                    self._addend = model.trunk_head_addend(self._lp)
-                self._rv = build_cost_volume_split_bf16(l, r, sh, 1, parts="right")
-                cur.wait_stream(self._side)
-
-            fns = [cost_volume_stage, lambda: setattr(self, "_x1", model.trunk_head_right(self._rv, self._addend))] + tail
-            self.stage_names = ["cost_volume", "conv1", "trunk_rest", "lift"]
+            # five stages: the 3-plane addend convolution is part of the first layer but gets its own graph, so that the
+            # "conv1" stage is the single large launch a caller may want to time on its own.  (Forking left planes ->
+            # addend convolution onto a second stream to hide its ~50 us under the right-half build was measured and
+            # dropped: either kernel fills every SM's shared memory, so the two branches serialise anyway --
+            # profiles/r02_notes.txt.)
+            fns = [lambda: setattr(self, "_cost", build_cost_volume_split_bf16(l, r, sh, 1)),
+                   lambda: setattr(self, "_addend", model.trunk_head_addend(self._cost[1])),
+                   lambda: setattr(self, "_x1", model.trunk_head_right(self._cost[0], self._addend))] + tail
+            self.stage_names = ["cost_volume", "conv1_addend", "conv1", "trunk_rest", "lift"]
         else:
             fns = [lambda: setattr(self, "_cost", build_cost_volume_ndhwc_bf16(l, r, sh, 1)),
                    lambda: setattr(self, "_x1", model.trunk_head(self._cost))] + tail
