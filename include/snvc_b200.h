@@ -52,7 +52,7 @@ const char* snvc_last_error(void);
  * its timed region as `gpu_launches`. */
 int64_t snvc_launch_count(void);
 /* Debug / A-B switches (kernel-generation selection, grid clamps for the ring wrap-around tests): SNVC_CONV_MODE,
- * SNVC_CONV_STORE, SNVC_CONV_OCC, SNVC_CONV_MAXGRID, SNVC_CV_SPLIT_OLD, SNVC_CV_THREADS, SNVC_ROI_MODE, SNVC_LIFT_MODE.  Each is read from
+ * SNVC_CONV_STORE, SNVC_CONV_OCC, SNVC_CONV_MAXGRID, SNVC_CV_SPLIT_OLD, SNVC_CV_THREADS, SNVC_CV_TUNE, SNVC_ROI_MODE, SNVC_LIFT_MODE.  Each is read from
  * the environment once, when the library is loaded; snvc_set_option changes one afterwards (value NULL or "" = unset;
  * name NULL = unset all).  Not synchronised with concurrent launches: set options before starting work.  Launches never
  * call getenv. */
@@ -308,6 +308,10 @@ int snvc_boxes_iou_bev(const float* boxes_a, const float* boxes_b, float* iou, i
 int64_t snvc_nms_bev_workspace_bytes(int64_t N);
 int snvc_nms_bev(const float* boxes_sorted, void* workspace, int64_t* keep, int32_t* num_keep, int64_t N,
                  float thresh, void* stream);
+/* B independent box sets of N boxes each in two launches (the pairs of a batch): boxes_sorted [B,N,7], workspace
+ * B * snvc_nms_bev_workspace_bytes(N) bytes, keep [B,N], num_keep [B]. */
+int snvc_nms_bev_batched(const float* boxes_sorted, void* workspace, int64_t* keep, int32_t* num_keep, int64_t B,
+                         int64_t N, float thresh, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Layout / elementwise helpers on the path.

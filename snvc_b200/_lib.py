@@ -51,6 +51,7 @@ _SIGS = {
     "snvc_boxes_iou_bev": ([_p, _p, _p, _i64, _i64, _p], _i32),
     "snvc_nms_bev_workspace_bytes": ([_i64], _i64),
     "snvc_nms_bev": ([_p, _p, _p, _p, _i64, _f, _p], _i32),
+    "snvc_nms_bev_batched": ([_p, _p, _p, _p, _i64, _i64, _f, _p], _i32),
     "snvc_conv3d_packed_weight_bytes": ([_i32, _i32, _i32], _i64),
     "snvc_conv3d_pack_weights": ([_p, _p, _i32, _i32, _i32, _i32, _p], _i32),
     "snvc_conv3d_fwd": ([_p, _p, _p, _p, _p, _p, ctypes.POINTER(ConvDesc), _p], _i32),

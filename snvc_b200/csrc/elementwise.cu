@@ -86,13 +86,11 @@ avgpool_bev_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ bev,
 // channel index c*Q + q (the reference's reshape of the pooled NCDHW tensor: vernier.py:436-438).
 // One thread per (n, r0, r2, 8-channel group): `pool` 16-byte loads per q, Q results per channel kept in registers and
 // written as one run of Q consecutive bf16 per channel.
-template <int AXIS>
+template <int AXIS, int Q>
 __global__ void __launch_bounds__(256)
 avgpool_bev_nhwc_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ bev, int64_t total, int S0, int S1,
                         int S2, int C, int pool) {
   const int CG = C >> 3;
-  const int Sax = AXIS == 0 ? S0 : S1;
-  const int Q = Sax / pool;
   const int R0 = AXIS == 0 ? S1 : S0;
   const float inv = 1.f / (float)pool;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -101,10 +99,9 @@ avgpool_bev_nhwc_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __re
     const int r2 = (int)(t % S2); t /= S2;
     const int r0 = (int)(t % R0);
     const int64_t n = t / R0;
-    float acc[8][8];
+    float acc[Q][8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      if (q >= Q) break;
+    for (int q = 0; q < Q; ++q) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[q][j] = 0.f;
       for (int k = 0; k < pool; ++k) {
@@ -116,13 +113,30 @@ avgpool_bev_nhwc_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __re
         for (int j = 0; j < 4; ++j) { acc[q][2 * j] += bf16_lo(w[j]); acc[q][2 * j + 1] += bf16_hi(w[j]); }
       }
     }
-    __nv_bfloat16* o = bev + ((n * R0 + r0) * S2 + r2) * ((int64_t)C * Q) + (int64_t)cg * 8 * Q;
+    // this thread's 8 channels x Q windows are 8*Q consecutive output channels (index j*Q + q): Q 16-byte stores
+    uint32_t words[4 * Q];
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
+    for (int e = 0; e < 4 * Q; ++e) {
+      const int e0 = 2 * e, e1 = 2 * e + 1;
+      words[e] = pack_bf16x2(acc[e0 % Q][e0 / Q] * inv, acc[e1 % Q][e1 / Q] * inv);
+    }
+    uint4* o = reinterpret_cast<uint4*>(bev + ((n * R0 + r0) * S2 + r2) * ((int64_t)C * Q) + (int64_t)cg * 8 * Q);
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
-        if (q < Q) o[j * Q + q] = __float2bfloat16_rn(acc[q][j] * inv);
+    for (int e = 0; e < Q; ++e) o[e] = make_uint4(words[4 * e], words[4 * e + 1], words[4 * e + 2], words[4 * e + 3]);
   }
+}
+
+template <int AXIS>
+int launch_avgpool_nhwc(int Q, int blocks, cudaStream_t st, const __nv_bfloat16* x, __nv_bfloat16* bev, int64_t total, int S0,
+                        int S1, int S2, int C, int pool) {
+  switch (Q) {
+#define SNVC_POOL_CASE(q) case q: avgpool_bev_nhwc_kernel<AXIS, q><<<blocks, 256, 0, st>>>(x, bev, total, S0, S1, S2, C, pool); break;
+    SNVC_POOL_CASE(1) SNVC_POOL_CASE(2) SNVC_POOL_CASE(3) SNVC_POOL_CASE(4) SNVC_POOL_CASE(5) SNVC_POOL_CASE(6) SNVC_POOL_CASE(7)
+    SNVC_POOL_CASE(8)
+#undef SNVC_POOL_CASE
+    default: return fail(SNVC_E_UNSUPPORTED, "at most 8 pooling windows");
+  }
+  return launch_status("avgpool_bev_nhwc_kernel<>");
 }
 
 }  // namespace
@@ -140,13 +154,13 @@ extern "C" int snvc_avgpool_to_bev_nhwc(const void* x, void* bev, int64_t N, int
   SNVC_CHECK_ARG(C % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "C must be a multiple of 8 and x 16-byte aligned");
   const int64_t total = N * (axis == 0 ? S1 : S0) * S2 * (C / 8);
   const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), (int64_t)sm_count() * 16);
+  SNVC_CHECK_ARG((reinterpret_cast<uintptr_t>(bev) & 15) == 0, "bev must be 16-byte aligned");
+  const int Q = (int)(Sax / pool);
   if (axis == 0)
-    avgpool_bev_nhwc_kernel<0><<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)bev, total, (int)S0,
-                                                                        (int)S1, (int)S2, C, pool);
-  else
-    avgpool_bev_nhwc_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)bev, total, (int)S0,
-                                                                        (int)S1, (int)S2, C, pool);
-  return launch_status("avgpool_bev_nhwc_kernel");
+    return launch_avgpool_nhwc<0>(Q, blocks, (cudaStream_t)stream, (const __nv_bfloat16*)x, (__nv_bfloat16*)bev, total, (int)S0, (int)S1,
+                                  (int)S2, C, pool);
+  return launch_avgpool_nhwc<1>(Q, blocks, (cudaStream_t)stream, (const __nv_bfloat16*)x, (__nv_bfloat16*)bev, total, (int)S0, (int)S1,
+                                (int)S2, C, pool);
 }
 
 extern "C" int snvc_ncdhw_f32_to_ndhwc_bf16(const float* src, void* dst, int64_t N, int64_t C, int64_t S, void* stream) {

@@ -193,6 +193,26 @@ def nms_gpu_device(boxes, scores, thresh, pre_maxsize=None):
     return sel, num
 
 
+def nms_gpu_device_batched(boxes, scores, thresh):
+    """Sync-free rotated NMS of B independent box sets in two launches: boxes [B,N,7], scores [B,N] -> (selected [B,N] int64
+    indices into each set in score order, padded with -1; num_kept [B] int32)."""
+    _lib.require_cuda(boxes, scores)
+    if boxes.dim() != 3 or boxes.shape[-1] != 7 or tuple(scores.shape) != tuple(boxes.shape[:2]):
+        raise RuntimeError("nms: boxes must be [B, N, 7] and scores [B, N]")
+    B, n = scores.shape
+    order = scores.sort(1, descending=True)[1]
+    b = torch.gather(boxes.float(), 1, order[..., None].expand(B, n, 7)).contiguous()
+    L = _lib.lib()
+    ws = torch.empty(max(8, B * L.snvc_nms_bev_workspace_bytes(n)), dtype=torch.uint8, device=b.device)
+    keep = torch.full((B, n), -1, dtype=torch.int64, device=b.device)
+    num = torch.zeros((B,), dtype=torch.int32, device=b.device)
+    with torch.cuda.device(b.device):
+        st = L.snvc_nms_bev_batched(b.data_ptr(), ws.data_ptr(), keep.data_ptr(), num.data_ptr(), B, n, float(thresh), _lib.stream_ptr())
+    _lib.check(st, "snvc_nms_bev_batched")
+    sel = torch.where(keep >= 0, torch.gather(order, 1, keep.clamp(min=0)), keep)
+    return sel, num
+
+
 def nms_gpu(boxes, scores, thresh, pre_maxsize=None, **kwargs):
     """Drop-in for iou3d_nms_utils.nms_gpu (iou3d_nms_utils.py:86-102): -> (indices of the kept boxes, None)."""
     sel, num = nms_gpu_device(boxes, scores, thresh, pre_maxsize)

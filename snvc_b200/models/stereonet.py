@@ -356,12 +356,8 @@ class ProposalDecoder:
         # BEV NMS works on [x, y(bev) = z, z, dx, dy, dz, heading]: put the ground-plane axes first
         bev_boxes = torch.stack([boxes[..., 0], boxes[..., 2], boxes[..., 1], boxes[..., 3], boxes[..., 4], boxes[..., 5],
                                  boxes[..., 6]], dim=-1).contiguous()
-        keeps, nums = [], []
-        for n in range(N):
-            sel_n, num = SF.nms_gpu_device(bev_boxes[n], top[n], self.iou_thresh)
-            keeps.append(sel_n)
-            nums.append(num)
-        return boxes, top, torch.stack(keeps), torch.stack(nums)
+        keep, num = SF.nms_gpu_device_batched(bev_boxes, top, self.iou_thresh)       # all pairs in two launches
+        return boxes, top, keep, num
 
 
 def decode_proposals(bbox_cls, bbox_reg, bbox_centerness, cfg, anchor_size=(1.56, 1.6, 3.9), anchor_y=1.0, pre_nms=512,

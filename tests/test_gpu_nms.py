@@ -43,3 +43,17 @@ def test_nms_empty_and_bad_input():
     assert got.numel() == 0
     with pytest.raises(RuntimeError):
         F.nms_gpu(torch.zeros((4, 5), device="cuda"), torch.zeros((4,), device="cuda"), 0.1)
+
+
+def test_batched_nms_equals_per_set_nms():
+    """snvc_nms_bev_batched (all box sets of a batch in two launches; 512-thread mask blocks) == the single-set entry point."""
+    from snvc_b200 import functional as F
+    sets = [o.synthetic_boxes(200, seed=40 + i) for i in range(5)]
+    boxes = torch.from_numpy(np.stack([b for b, _ in sets])).cuda()
+    scores = torch.from_numpy(np.stack([s for _, s in sets])).cuda()
+    sel, num = F.nms_gpu_device_batched(boxes, scores, 0.2)
+    for i in range(5):
+        s1, n1 = F.nms_gpu_device(boxes[i], scores[i], 0.2)
+        assert int(num[i].item()) == int(n1.item()) and torch.equal(sel[i], s1)
+        want = o.nms(sets[i][0], sets[i][1], 0.2)
+        assert np.array_equal(sel[i, :len(want)].cpu().numpy(), want)
