@@ -310,7 +310,7 @@ cv_ndhwc_bf16_kernel(const float* __restrict__ left, const float* __restrict__ r
 __global__ void __launch_bounds__(512)
 cv_split_bf16_kernel(const float* __restrict__ left, const float* __restrict__ right, const float* __restrict__ shift,
                      __nv_bfloat16* __restrict__ right_vol, __nv_bfloat16* __restrict__ left_planes, int C, int img_h,
-                     int img_w, int D, int H, int W, int ds, int d_per_cta, int mask, int mode, int tune) {
+                     int img_w, int D, int H, int W, int ds, int d_per_cta, int mask, int mode) {
   // mode 1: right half only (grid.z = depth splits; shared memory = one right row + the sample table -> 3 CTAs per SM);
   // mode 2: left planes only (grid.z = 1; shared memory = one left row).  Two launches, so that the 40 KB left row does
   // not sit in the shared memory of every depth split.
@@ -328,30 +328,16 @@ cv_split_bf16_kernel(const float* __restrict__ left, const float* __restrict__ r
   const int64_t cstride = (int64_t)img_h * img_w;
   const float* rrow = right + ((int64_t)n * C * img_h + ih) * img_w;
   const float* lrow = left + ((int64_t)n * C * img_h + ih) * img_w;
-  // staging with 4-byte cp.async: a warp instruction covers 8 consecutive columns x the 4 channels of one 16-byte chunk.
-  // With the XOR swizzle the 8 columns land in 8 different chunk positions, so the 32 lanes hit 32 different banks (the
-  // earlier one-channel-per-warp mapping was a 4-way conflict: ncu showed 4 wavefronts per LDGSTS, a fifth of the kernel's
-  // shared-memory wavefronts), while every lane quartet still reads whole 32-byte sectors of a channel row.
+  // staging: a warp takes one channel at a time and runs along the row (coalesced 4-byte cp.async, no divisions).  The
+  // transposing scatter is a 4-way bank conflict (a fifth of the kernel's shared-memory wavefronts, ncu r02); the
+  // conflict-free mapping -- 8 columns x the 4 channels of a chunk per warp instruction -- was measured SLOWER (180 vs
+  // 156 us: every lane quartet then pulls a different 32-byte sector, four times the L2 requests) and dropped.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-  if (tune & 1) {
-    const int c4 = lane & 3, col8 = lane >> 2;
-    const int nchunk = C >> 2;
-    const int srcw = do_right ? img_w : lw;
-    const float* srow = do_right ? rrow : lrow;
-    float* sdst = do_right ? sR : sL;
-    const int ncb = (srcw + 7) >> 3;
-    for (int t = warp; t < nchunk * ncb; t += nwarp) {
-      const int ch = t % nchunk, cb = t / nchunk;
-      const int c = ch * 4 + c4, col = cb * 8 + col8;
-      if (col < srcw) cp_async_4(&sdst[swz(col, c, C, mask)], srow + c * cstride + col);
-    }
-  } else {
-    for (int c = warp; c < C; c += nwarp) {
-      if (do_right)
-        for (int col = lane; col < img_w; col += 32) cp_async_4(&sR[swz(col, c, C, mask)], rrow + c * cstride + col);
-      if (do_left)
-        for (int col = lane; col < lw; col += 32) cp_async_4(&sL[swz(col, c, C, mask)], lrow + c * cstride + col);
-    }
+  for (int c = warp; c < C; c += nwarp) {
+    if (do_right)
+      for (int col = lane; col < img_w; col += 32) cp_async_4(&sR[swz(col, c, C, mask)], rrow + c * cstride + col);
+    if (do_left)
+      for (int col = lane; col < lw; col += 32) cp_async_4(&sL[swz(col, c, C, mask)], lrow + c * cstride + col);
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
   for (int dd = warp; dd < dn; dd += nwarp) {
@@ -407,12 +393,7 @@ cv_split_bf16_kernel(const float* __restrict__ left, const float* __restrict__ r
     // one step: `lo` must end up holding column xl, `hi` column xh; on entry `lo` holds column `held` (the previous
     // step's high column), `hi` is free
     auto step = [&](float2 (&lo)[4], float2 (&hi)[4], int pw, __nv_bfloat16* op) {
-      int2 te;
-      if (tune & 2) {                                    // one LDS.64 (the compiler emits two LDS.32)
-        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(te.x), "=r"(te.y) : "r"((uint32_t)__cvta_generic_to_shared(tab + pw)));
-      } else {
-        te = tab[pw];
-      }
+      const int2 te = tab[pw];
       uint4 v = make_uint4(0u, 0u, 0u, 0u);
       if (te.x >= 0) {
         const int xl = te.x & 0x3fffffff, xh = xl + ((te.x >> 30) & 1);
@@ -616,11 +597,10 @@ int launch_cv_ndhwc(const void* left, const void* right, const void* shift, void
         if (std::max(smem, smem_left) > 48 * 1024)
           SNVC_CUDA_OK(cudaFuncSetAttribute(cv_split_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)std::max(smem, smem_left)));
-        const int tune = opt(OPT_CV_TUNE) ? atoi(opt(OPT_CV_TUNE)) : 0;
         if (parts & 2) {
           cv_split_bf16_kernel<<<dim3((unsigned)H, (unsigned)N, 1), 512, smem_left, stream>>>(
               (const float*)left, (const float*)right, (const float*)shift, (__nv_bfloat16*)cost, (__nv_bfloat16*)left_planes,
-              (int)C, (int)IH, (int)IW, (int)D, (int)H, (int)W, ds, d_per, mask, 2, tune);
+              (int)C, (int)IH, (int)IW, (int)D, (int)H, (int)W, ds, d_per, mask, 2);
           if (int e = launch_status("cv_split_bf16_kernel")) return e;
         }
         if (!(parts & 1)) return 0;
@@ -642,7 +622,7 @@ int launch_cv_ndhwc(const void* left, const void* right, const void* shift, void
         }
         cv_split_bf16_kernel<<<grid, threads, smem, stream>>>((const float*)left, (const float*)right, (const float*)shift,
                                                            (__nv_bfloat16*)cost, (__nv_bfloat16*)left_planes, (int)C, (int)IH,
-                                                           (int)IW, (int)D, (int)H, (int)W, ds, d_per, mask, 1, tune);
+                                                           (int)IW, (int)D, (int)H, (int)W, ds, d_per, mask, 1);
         return launch_status("cv_split_bf16_kernel");
       }
     }
