@@ -373,3 +373,27 @@ class hourglass2d_downsample_16(nn.Module):
     def forward(self, x):
         xin, kind = _to_nhwc(x)
         return _from_nhwc(self.fused(xin), kind)
+
+
+class BasicBlock(nn.Module):
+    """submodule.py:52-74 (2-D residual block of the global backbone): conv1 = convbn + ReLU, conv2 = convbn,
+    out = conv2(conv1(x)) + (downsample(x) if downsample else x).  The skip add is fused into conv2's epilogue.
+    Supports the kernel's geometry (3x3, stride 1 / 2, dilation 1 with pad 1 or dilation == pad); channel counts
+    must be multiples of 8 and >= 16, which holds from the backbone's second stage on."""
+    expansion = 1
+
+    def __init__(self, inplanes, planes, stride, downsample, pad, dilation, gn=False):
+        super().__init__()
+        self.conv1 = _ConvNormReLU2d(convbn(inplanes, planes, 3, stride, pad, dilation, gn=gn), nn.ReLU(inplace=True))
+        self.conv2 = convbn(planes, planes, 3, 1, pad, dilation, gn=gn)
+        self.downsample = downsample
+        self.stride = stride
+
+    def forward(self, x):
+        xin, kind = _to_nhwc(x)
+        skip = xin
+        if self.downsample is not None:
+            ds = self.downsample
+            skip = ds.fused(xin) if hasattr(ds, "fused") else _to_nhwc(ds(x))[0]
+        out = self.conv2.fused(self.conv1.fused(xin), residual=skip, residual_mode=1)
+        return _from_nhwc(out, kind)

@@ -260,3 +260,21 @@ def test_rpn3d_head_vs_oracle_and_device_nms(n_y):
         want_keep = onms.nms(bev, scores[n].cpu().numpy(), 0.1)
         k = int(num[n].item())
         assert k == len(want_keep) and np.array_equal(keep[n, :k].cpu().numpy(), want_keep) and bool((keep[n, k:] == -1).all())
+
+
+@pytest.mark.parametrize("stride,dil", [(1, 1), (2, 1), (1, 2)])
+def test_basic_block_vs_torch(stride, dil):
+    """submodule.py:52-74 with the kernel-backed convbn: same keys, same numbers as the plain-torch block."""
+    from snvc_b200.models.submodule import BasicBlock, convbn
+    cin, planes = 32, 64
+    ds = convbn(cin, planes, 1, stride, 0, 1)                                 # the 1x1 projection the reference passes in (:391-397)
+    m = BasicBlock(cin, planes, stride, ds, 1, dil).eval()
+    m.load_state_dict(synth.det_state_dict(m, 81), strict=True)
+    ref_ds = oblocks.convbn(cin, planes, 1, stride, 0, 1)
+    ref = torch.nn.ModuleDict(dict(conv1=torch.nn.Sequential(oblocks.convbn(cin, planes, 3, stride, 1, dil), torch.nn.ReLU()),
+                                   conv2=oblocks.convbn(planes, planes, 3, 1, 1, dil), downsample=ref_ds)).eval()
+    ref.load_state_dict(m.state_dict(), strict=True)
+    x = synth.det_uniform((2, cin, 20, 28), 82)
+    want = ref["conv2"](ref["conv1"](torch.from_numpy(x))) + ref["downsample"](torch.from_numpy(x))
+    got = m.cuda()(torch.from_numpy(x).cuda())
+    assert _relerr(got.cpu().numpy(), want.numpy()) <= TOL
