@@ -9,6 +9,7 @@
 // element is written exactly once, in the layout its consumer reads (NDHWC bf16 for the tcgen05
 // conv3d, or the reference's NCDHW fp32), with 128-bit accesses.
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -33,10 +34,11 @@ struct Bilinear {
   unsigned mask;       // bit k set <=> corner k inside the feature map
 };
 
-__device__ __forceinline__ Bilinear bilinear_setup(float px, float py, float res_x, float res_y, int Wf, int Hf) {
+// qx, qy = p / resolution (the first of the three rounded operations of vernier.py:335-338)
+__device__ __forceinline__ Bilinear bilinear_setup_norm(float qx, float qy, int Wf, int Hf) {
   Bilinear b;
-  float ix = unnormalize(roi_normalize(px, res_x), Wf, false);
-  float iy = unnormalize(roi_normalize(py, res_y), Hf, false);
+  float ix = unnormalize(__fsub_rn(__fmul_rn(qx, 2.f), 1.f), Wf, false);
+  float iy = unnormalize(__fsub_rn(__fmul_rn(qy, 2.f), 1.f), Hf, false);
   float fx0 = floorf(ix), fy0 = floorf(iy);
   // non-finite coordinates: no corner is in bounds (torch compares the float->int cast; here the
   // range test on the float itself rejects NaN/inf before the cast)
@@ -54,6 +56,9 @@ __device__ __forceinline__ Bilinear bilinear_setup(float px, float py, float res
   bool yin0 = b.y0 >= 0 && b.y0 < Hf, yin1 = b.y0 + 1 >= 0 && b.y0 + 1 < Hf;
   b.mask = (xin0 && yin0 ? 1u : 0u) | (xin1 && yin0 ? 2u : 0u) | (xin0 && yin1 ? 4u : 0u) | (xin1 && yin1 ? 8u : 0u);
   return b;
+}
+__device__ __forceinline__ Bilinear bilinear_setup(float px, float py, float res_x, float res_y, int Wf, int Hf) {
+  return bilinear_setup_norm(__fdiv_rn(px, res_x), __fdiv_rn(py, res_y), Wf, Hf);
 }
 
 // out = (((0 + v_nw*w_nw) + v_ne*w_ne) + v_sw*w_sw) + v_se*w_se, out-of-bounds corners skipped
@@ -78,6 +83,25 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ a, const float* __
     int64_t src = (n * C + c) * HW + p;
     oa[i] = a[src];
     ob[i] = b[src];
+  }
+}
+
+// NCHW fp32 -> NHWC bf16 (both views at once): the feature copy of the bf16 product path (v4 kernel below).  A thread
+// writes 8 channels of one pixel (16 bytes); reads are strided but the maps are L2 resident.
+__global__ void nchw_to_nhwc_bf16_kernel(const float* __restrict__ a, const float* __restrict__ b, uint4* __restrict__ oa,
+                                         uint4* __restrict__ ob, int C, int HW, int64_t total /* N*HW*C/8 */) {
+  const int CG = C >> 3;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % CG);
+    const int64_t t = i / CG;
+    const int p = (int)(t % HW);
+    const int64_t n = t / HW;
+    const int64_t src = (n * C + cg * 8) * HW + p;
+    float va[8], vb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { va[j] = a[src + (int64_t)j * HW]; vb[j] = b[src + (int64_t)j * HW]; }
+    oa[i] = make_uint4(pack_bf16x2(va[0], va[1]), pack_bf16x2(va[2], va[3]), pack_bf16x2(va[4], va[5]), pack_bf16x2(va[6], va[7]));
+    ob[i] = make_uint4(pack_bf16x2(vb[0], vb[1]), pack_bf16x2(vb[2], vb[3]), pack_bf16x2(vb[4], vb[5]), pack_bf16x2(vb[6], vb[7]));
   }
 }
 
@@ -359,6 +383,137 @@ roi_sample_coop2_kernel(const float* __restrict__ fl, const float* __restrict__ 
                     make_float4(acc2[2].x, acc2[2].y, acc2[3].x, acc2[3].y));
         }
       }
+    }
+  }
+}
+
+// ---- A3, NDHWC bf16 output, v4 (the product path of the instance branch).  ncu on v3 (profiles/r02_hbm_kernels_summary.txt):
+// nothing saturated -- DRAM 30 %, L1 63 %, issue 65 % -- but 38.8 warp instructions per point, of which only 18 % are the
+// interpolation arithmetic (FFMA2 / FADD2): the rest is 64-bit address arithmetic, zeroing of masked corner registers
+// (CS2R 10 %), constant-bank reloads, predicates and the branches of the corner-block reuse, and the six shuffles per
+// round cost as many L1 data-pipe wavefronts as all the feature loads.  The bf16 output is compared at the 1e-2 bar (the
+// fp32 outputs stay on the exact kernels above; corner indices and masks are the same bit-exact set-up), which allows:
+//   * one fused FFMA2 per (corner, channel pair) instead of the separately rounded FMUL2 + FADD2 (<= 1 fp32 ulp before the
+//     bf16 rounding);
+//   * masked corners as ZERO WEIGHTS on a clamped, always valid address: no per-corner predicate, no register zeroing
+//     (the accumulator starts from +0, so fully masked points give +0 like the oracle);
+//   * the per-(point, view) set-up handed over through shared memory (one STS.128 + one STS.32 per lane and chunk, one
+//     LDS.128 + one LDS.32 per round, both broadcast reads) instead of six shuffles per round;
+//   * the lane groups of a round take CONSECUTIVE points (voxel spacing is a fraction of a feature pixel, so the 2*PPR
+//     corner rows of a request fall into one or two 128-byte lines and the L1 serves them in as many wavefronts): the reuse
+//     that v3 got from registers and branches comes from request coalescing, branch-free.
+// base + 4 * off in ONE instruction (IMAD.WIDE.U32); plain pointer arithmetic compiles to a 4-instruction carry chain
+__device__ __forceinline__ const float* ptr_plus_u32x4(const float* base, uint32_t off) {
+  uint64_t r;
+  asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(r) : "r"(off), "l"(reinterpret_cast<uint64_t>(base)));
+  return reinterpret_cast<const float*>(r);
+}
+
+template <int LOG_LPV, bool FEAT16>   // lanes per (point, view): C / 8 == 1 << LOG_LPV; features NHWC bf16 | fp32
+__global__ void __launch_bounds__(256, 4)
+roi_sample_fast_bf16_kernel(const void* __restrict__ fl_, const void* __restrict__ fr_, const float* __restrict__ pl,
+                            const float* __restrict__ pr, __nv_bfloat16* __restrict__ out, int Hf, int Wf, FastDiv divP,
+                            float res_x, float res_y, float inv_res_x, float inv_res_y,
+                            uint32_t total /* N*P < 2^30, N*Hf*Wf*C < 2^31 */) {
+  constexpr int LPV = 1 << LOG_LPV, PPR = 16 >> LOG_LPV, ROUNDS = 16 / PPR, C = 8 * LPV;
+  __shared__ float4 s_w[8][2][32];      // corner weights (0 for a corner outside the map)
+  __shared__ uint4 s_o[8][2][32];       // corner offsets in floats from the view's feature base (clamped into the map)
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  // Lane roles.  Set-up: lane i owns (point i & 15, view i >> 4) of the chunk.  Gather: the half-warp is the VIEW, inside it
+  // PPR consecutive points x LPV channel groups -- a quarter-warp (the unit the L1 serves per wavefront) then reads the
+  // rows of 8 / LPV consecutive points of one view, i.e. one or two 128-byte lines.  [With the two views of a point in the
+  // same quarter every 16-byte load cost 8 wavefronts (2 lines x 4 quarters) and the kernel sat at 97 % of the L1 data pipe.]
+  const int cg = lane & (LPV - 1);
+  const int view = lane >> 4;
+  const int psel = (lane >> LOG_LPV) & (PPR - 1);
+  // lane's channel group inside a feature row: 8 channels = 16 B (bf16 copy of the features) or 32 B (fp32)
+  const float* const feat = reinterpret_cast<const float*>(view ? fr_ : fl_) + cg * (FEAT16 ? 4 : 8);
+  const float* const my_pts = view ? pr : pl;
+  const uint32_t P = divP.d;
+  const uint32_t nchunks = (total + 15u) >> 4;
+  const uint32_t c_begin = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t wstep = (gridDim.x * blockDim.x) >> 5;
+  auto load_pts = [&](uint32_t chunk, float& u, float& v, uint32_t& n_out) {
+    const uint32_t np = chunk * 16u + (uint32_t)(lane & 15);
+    u = v = 0.f; n_out = 0u;
+    if (np < total) {                                      // (chunk >= nchunks implies np >= total)
+      const uint32_t n = fdiv(np, divP), i = np + n * P;   // n * 2P + (np - n * P)
+      u = __ldg(ptr_plus_u32x4(my_pts, i)); v = __ldg(ptr_plus_u32x4(my_pts, i + P)); n_out = n;
+    }
+  };
+  float nu, nv;
+  uint32_t nn;
+  load_pts(c_begin, nu, nv, nn);
+  int buf = 0;
+  // this lane's output position inside a chunk's 16 rows of 2C bf16: point psel (+ r * PPR), view, channel group
+  __nv_bfloat16* const out_lane = out + (size_t)psel * (2 * C) + view * C + cg * 8;
+  const float4* const sw = &s_w[wib][0][view * 16 + psel];
+  const uint4* const so = &s_o[wib][0][view * 16 + psel];
+  for (uint32_t chunk = c_begin; chunk < nchunks; chunk += wstep, buf ^= 1) {
+    // ---- phase A: lane i sets up (point chunk*16 + (i & 15), view i >> 4): the arithmetic of bilinear_setup() (bit-exact corner
+    // indices and weights), with the in-bounds tests folded into per-axis weights (w = 0 for a corner outside the map)
+    // and corner addresses clamped into the map.  Lanes past the end compute a harmless dummy.
+    const float pu = nu, pv = nv;
+    const uint32_t n = nn;
+    load_pts(chunk + wstep, nu, nv, nn);
+    // p / res == p * (1 / res) bit for bit when res is a power of two (the host passes inv_res != 0 only then)
+    const float qx = inv_res_x != 0.f ? __fmul_rn(pu, inv_res_x) : __fdiv_rn(pu, res_x);
+    const float qy = inv_res_x != 0.f ? __fmul_rn(pv, inv_res_y) : __fdiv_rn(pv, res_y);
+    const float ix = unnormalize(__fsub_rn(__fmul_rn(qx, 2.f), 1.f), Wf, false);
+    const float iy = unnormalize(__fsub_rn(__fmul_rn(qy, 2.f), 1.f), Hf, false);
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    const bool finite = (fabsf(ix) < 1e9f) && (fabsf(iy) < 1e9f);
+    const int x0 = finite ? (int)fx0 : -2, y0 = finite ? (int)fy0 : -2;
+    const float dx1 = (unsigned)x0 < (unsigned)Wf ? __fsub_rn(__fadd_rn(fx0, 1.f), ix) : 0.f;
+    const float dx0 = (unsigned)(x0 + 1) < (unsigned)Wf ? __fsub_rn(ix, fx0) : 0.f;
+    const float dy1 = (unsigned)y0 < (unsigned)Hf ? __fsub_rn(__fadd_rn(fy0, 1.f), iy) : 0.f;
+    const float dy0 = (unsigned)(y0 + 1) < (unsigned)Hf ? __fsub_rn(iy, fy0) : 0.f;
+    const float4 w = make_float4(__fmul_rn(dx1, dy1), __fmul_rn(dx0, dy1), __fmul_rn(dx1, dy0), __fmul_rn(dx0, dy0));
+    constexpr uint32_t RW = FEAT16 ? C / 2 : C;            // 32-bit words per feature row
+    const uint32_t x0c = (uint32_t)min(max(x0, 0), Wf - 1) * RW, x1c = (uint32_t)min(max(x0 + 1, 0), Wf - 1) * RW;
+    const uint32_t r0 = ((n * Hf + (uint32_t)min(max(y0, 0), Hf - 1)) * Wf) * RW;
+    const uint32_t r1 = ((n * Hf + (uint32_t)min(max(y0 + 1, 0), Hf - 1)) * Wf) * RW;
+    const uint4 off = make_uint4(r0 + x0c, r0 + x1c, r1 + x0c, r1 + x1c);
+    s_w[wib][buf][lane] = w;
+    s_o[wib][buf][lane] = off;
+    __syncwarp();
+    // ---- phase B: ROUNDS rounds of PPR consecutive points, both views of a point in the same round
+    __nv_bfloat16* const o = out_lane + (size_t)chunk * 16u * (2 * C);
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+      const float4 wk = sw[buf * 32 + r * PPR];
+      const uint4 ok = so[buf * 32 + r * PPR];
+      float2 acc[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+      const float wv[4] = {wk.x, wk.y, wk.z, wk.w};
+      const uint32_t ov[4] = {ok.x, ok.y, ok.z, ok.w};
+      if (FEAT16) {
+        uint4 q[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) q[k] = __ldg(reinterpret_cast<const uint4*>(ptr_plus_u32x4(feat, ov[k])));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 w2 = make_float2(wv[k], wv[k]);
+          const uint32_t u[4] = {q[k].x, q[k].y, q[k].z, q[k].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[j] = __ffma2_rn(make_float2(bf16_lo(u[j]), bf16_hi(u[j])), w2, acc[j]);
+        }
+      } else {
+        float4 q[4][2];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ldg256_f4(ptr_plus_u32x4(feat, ov[k]), q[k][0], q[k][1]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 w2 = make_float2(wv[k], wv[k]);
+          acc[0] = __ffma2_rn(make_float2(q[k][0].x, q[k][0].y), w2, acc[0]);
+          acc[1] = __ffma2_rn(make_float2(q[k][0].z, q[k][0].w), w2, acc[1]);
+          acc[2] = __ffma2_rn(make_float2(q[k][1].x, q[k][1].y), w2, acc[2]);
+          acc[3] = __ffma2_rn(make_float2(q[k][1].z, q[k][1].w), w2, acc[3]);
+        }
+      }
+      if (chunk * 16u + (uint32_t)(r * PPR + psel) < total)
+        *reinterpret_cast<uint4*>(o + (size_t)r * PPR * (2 * C)) =
+            make_uint4(pack_bf16x2(acc[0].x, acc[0].y), pack_bf16x2(acc[1].x, acc[1].y), pack_bf16x2(acc[2].x, acc[2].y),
+                       pack_bf16x2(acc[3].x, acc[3].y));
     }
   }
 }
@@ -775,15 +930,60 @@ extern "C" int snvc_roi_voxel_sample_fwd(const float* feat_l, const float* feat_
   float* wl = (float*)workspace;
   float* wr = wl + N * C * Hf * Wf;
   const int64_t nfeat = N * C * Hf * Wf;
+  const char* rmode = opt(OPT_ROI_MODE);
+  const int lpv = (int)(C / 8);
+  // bf16 NDHWC output (the instance branch's product path): v4 kernel on a bf16 channels-last copy of the features (fused
+  // FMA, zero-weight masking, set-up through shared memory).  SNVC_ROI_MODE=fast32 keeps fp32 features in the same kernel,
+  // =v3 / coop1 / thread select the bit-exact kernels (A/B runs, tests).
+  const bool fast32 = rmode && rmode[0] == 'f';
+  if (out_layout == SNVC_NDHWC && out_dtype == SNVC_BF16 && C % 8 == 0 && lpv <= 16 && (lpv & (lpv - 1)) == 0 &&
+      N * P < (1ll << 30) && N * Hf * Wf * C < (1ll << 31) && (reinterpret_cast<uintptr_t>(workspace) & 31) == 0 &&
+      (!rmode || fast32)) {
+    const void *fa, *fb;
+    if (fast32) {
+      nchw_to_nhwc_kernel<<<grid_for(nfeat), 256, 0, stream>>>(feat_l, feat_r, wl, wr, (int)C, (int)(Hf * Wf), nfeat);
+      fa = wl; fb = wr;
+    } else {
+      uint4* ha = (uint4*)workspace;
+      uint4* hb = ha + nfeat / 8;
+      nchw_to_nhwc_bf16_kernel<<<grid_for(nfeat / 8), 256, 0, stream>>>(feat_l, feat_r, ha, hb, (int)C, (int)(Hf * Wf), nfeat / 8);
+      fa = ha; fb = hb;
+    }
+    if (int e = launch_status("nchw_to_nhwc_kernel")) return e;
+    // division by a power-of-two resolution (256 in the shipped configuration) is an exact multiplication
+    int ex, ey;
+    const bool pow2 = res_x > 0.f && res_y > 0.f && std::frexp(res_x, &ex) == 0.5f && std::frexp(res_y, &ey) == 0.5f &&
+                      ex > -100 && ex < 100 && ey > -100 && ey < 100;
+    const float inv_x = pow2 ? 1.f / res_x : 0.f, inv_y = pow2 ? 1.f / res_y : 0.f;
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(N * P, 128), (int64_t)sm_count() * 4));
+#define SNVC_ROI_FAST(L)                                                                                                      \
+  do {                                                                                                                        \
+    if (fast32)                                                                                                               \
+      roi_sample_fast_bf16_kernel<L, false><<<blocks, 256, 0, stream>>>(fa, fb, pts_l, pts_r, (__nv_bfloat16*)out, (int)Hf,   \
+                                                                        (int)Wf, make_fastdiv(P), res_x, res_y, inv_x, inv_y, \
+                                                                        (uint32_t)(N * P));                                   \
+    else                                                                                                                      \
+      roi_sample_fast_bf16_kernel<L, true><<<blocks, 256, 0, stream>>>(fa, fb, pts_l, pts_r, (__nv_bfloat16*)out, (int)Hf,    \
+                                                                       (int)Wf, make_fastdiv(P), res_x, res_y, inv_x, inv_y,  \
+                                                                       (uint32_t)(N * P));                                    \
+  } while (0)
+    switch (lpv) {
+      case 1: SNVC_ROI_FAST(0); break;
+      case 2: SNVC_ROI_FAST(1); break;
+      case 4: SNVC_ROI_FAST(2); break;
+      case 8: SNVC_ROI_FAST(3); break;
+      default: SNVC_ROI_FAST(4); break;
+    }
+#undef SNVC_ROI_FAST
+    return launch_status("roi_sample_fast_bf16_kernel");
+  }
   nchw_to_nhwc_kernel<<<grid_for(nfeat), 256, 0, stream>>>(feat_l, feat_r, wl, wr, (int)C, (int)(Hf * Wf), nfeat);
   if (int e = launch_status("nchw_to_nhwc_kernel")) return e;
   if (out_layout == SNVC_NDHWC) {
     SNVC_CHECK_ARG(C % 8 == 0, "NDHWC output needs C %% 8 == 0");
     const int64_t total = N * P * (2 * C / 8);
-    // cooperative kernel (set-up once per point, C/8 lanes per (point, view)); SNVC_ROI_MODE=thread keeps v1 (A/B runs)
-    const int lpv = (int)(C / 8);
-    const char* rmode = opt(OPT_ROI_MODE);
-    // v3 (both views per round, 256-bit corner loads); SNVC_ROI_MODE=coop1 keeps v2 (A/B runs)
+    // cooperative kernels (set-up once per point, C/8 lanes per (point, view)); SNVC_ROI_MODE=thread keeps v1 (A/B runs)
+    // v3 (both views per round, 256-bit corner loads; bit-exact); SNVC_ROI_MODE=coop1 keeps v2 (A/B runs)
     if (lpv <= 16 && (lpv & (lpv - 1)) == 0 && N * P < (1ll << 30) && N * Hf * Wf < (1ll << 31) &&
         (reinterpret_cast<uintptr_t>(workspace) & 31) == 0 && (reinterpret_cast<uintptr_t>(out) & 31) == 0 &&
         (out_dtype == SNVC_BF16 || out_dtype == SNVC_F32) && !(rmode && (rmode[0] == 't' || rmode[0] == 'c'))) {

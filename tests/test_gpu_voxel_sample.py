@@ -45,9 +45,35 @@ def test_roi_sample_vs_oracle(kw):
     got16 = _F().roi_voxel_sample(*t, res, out_dtype=torch.bfloat16, layout="NDHWC")
     N = lf.shape[0]
     got16 = got16.float().reshape(N, nh, nw, nl, -1).permute(0, 4, 1, 2, 3).cpu().numpy()
-    assert np.array_equal(got16, synth.bf16_round(want))
+    # bf16 product path (v4 kernel): one fused FMA per corner instead of separately rounded mul + add -> within one bf16
+    # ulp of the rounded oracle, identical zero support (masked corners are zero weights, fully masked points give +0)
+    r16 = synth.bf16_round(want)
+    assert np.max(np.abs(got16 - r16)) <= 2.0 ** -7 * np.max(np.abs(want))
+    assert np.mean(got16 == r16) > 0.99 and np.array_equal(got16 == 0, r16 == 0)
     got32 = _F().roi_voxel_sample(*t, res, out_dtype=torch.float32, layout="NDHWC")
     assert np.array_equal(got32.reshape(N, nh, nw, nl, -1).permute(0, 4, 1, 2, 3).cpu().numpy(), want)
+
+
+def test_roi_bf16_product_path_rounds_features_once():
+    """The bf16-output product kernel samples a bf16 channels-last COPY of the features (half the L1 traffic): with
+    features that are not bf16-representable the result is the sampling of the rounded features (within one bf16 ulp of
+    that oracle) and stays far inside the 1e-2 bar against the unrounded fp32 oracle; fp32 outputs are untouched by this."""
+    N, C, Hf, Wf, (nh, nw, nl), res = 2, 32, 16, 16, (4, 6, 10), (64, 64)
+    P = nh * nw * nl
+    lf, rf = synth.det_uniform((N, C, Hf, Wf), 61, bf16=False), synth.det_uniform((N, C, Hf, Wf), 62, bf16=False)
+    gl = synth.det_uniform((N, 2, P), 63, -6.4, 70.4, bf16=False)
+    gr = synth.det_uniform((N, 2, P), 64, -6.4, 70.4, bf16=False)
+    assert not np.array_equal(lf, synth.bf16_round(lf))
+    want = ogs.roi_voxel_sample(lf, rf, gl, gr, nh, nw, nl, res)
+    want_r = ogs.roi_voxel_sample(synth.bf16_round(lf), synth.bf16_round(rf), gl, gr, nh, nw, nl, res)
+    t = [torch.from_numpy(a).cuda() for a in (lf, rf, gl, gr)]
+    got = _F().roi_voxel_sample(*t, res, out_dtype=torch.bfloat16, layout="NDHWC")
+    got = got.float().reshape(N, nh, nw, nl, -1).permute(0, 4, 1, 2, 3).cpu().numpy()
+    r16 = synth.bf16_round(want_r)
+    assert np.max(np.abs(got - r16)) <= 2.0 ** -7 * np.max(np.abs(want_r)) and np.mean(got == r16) > 0.99
+    assert _relerr(got, want) <= 1e-2 and np.array_equal(got == 0, want == 0)
+    exact = _F().roi_voxel_sample(*t, res).reshape(want.shape).cpu().numpy()
+    assert np.array_equal(exact, want)
 
 
 def test_roi_indices_bit_exact():
@@ -137,12 +163,13 @@ def test_lift_indices_bit_exact_kitti_geometry(ac):
 
 @pytest.mark.parametrize("C", [8, 16, 32, 64, 128])
 def test_roi_sample_kernel_generations_agree(C, monkeypatch):
-    """The product ROI sampler (v3: both views per round, 256-bit corner loads) must be bit-identical to v2
+    """The exact ROI sampler (v3: both views per round, 256-bit corner loads) must be bit-identical to v2
     (SNVC_ROI_MODE=coop1) and to the one-thread-per-(point, view, 8 channels) kernel (SNVC_ROI_MODE=thread), with a
     point count that is not a multiple of 16."""
     lf, rf, gl, gr, (nh, nw, nl), res = _roi_case(N=2, C=C, Hf=12, Wf=20, grid=(3, 7, 11), res=(48, 80), seed=C)
     assert (2 * nh * nw * nl) % 16 != 0
     t = [torch.from_numpy(a).cuda() for a in (lf, rf, gl, gr)]
+    fast = _F().roi_voxel_sample(*t, res, out_dtype=torch.bfloat16, layout="NDHWC")      # default: the v4 product kernel
     for od in (torch.bfloat16, torch.float32):
         outs = []
         for mode in ("thread", "coop1", "v3"):
@@ -152,6 +179,10 @@ def test_roi_sample_kernel_generations_agree(C, monkeypatch):
         assert torch.equal(outs[0].view(view), outs[1].view(view))
         assert torch.equal(outs[0].view(view), outs[2].view(view))
         assert outs[2].float().abs().max().item() > 0
+        if od == torch.bfloat16:        # v4 (fused FMA) vs the exact kernels: <= 1 bf16 ulp, same zero support
+            a, b = fast.float(), outs[2].float()
+            assert (a - b).abs().max().item() <= 2.0 ** -7 * b.abs().max().item()
+            assert (a == b).float().mean().item() > 0.99 and torch.equal(a == 0, b == 0)
 
 
 @pytest.mark.parametrize("C", [16, 32, 64])
