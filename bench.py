@@ -258,7 +258,7 @@ def instance_leg(dev, rank, world, dist, peaks, frame_proposals=64, chunk=8, ste
                     "gflop_per_proposal": gflop}}
 
 
-def stress_leg(dev, rank, world, dist, steps=3):
+def stress_leg(dev, rank, world, dist, steps=5):
     """BASELINE.json configs[4]: ONE volume, 2x depth bins (D = 96) at full resolution (features 32 x 384 x 1248: cost
     volume 5.9 GB bf16, trunk 15.7 TFLOP), split into depth slabs over the ranks with a conv3d halo exchange (NCCL P2P over
     NVLink) after every layer and a z-partitioned lift.  Strong scaling: the work is fixed, ranks divide it."""
@@ -282,9 +282,29 @@ def stress_leg(dev, rank, world, dist, steps=3):
     slab = par.DepthSlab(D, world, rank)
     comm = par.HaloComm(world, rank, dev) if world > 1 else None
     ev = lambda: torch.cuda.Event(enable_timing=True)
+    eager = lambda: par.slab_global_forward(m, lf, rf, shift, proj, slab, out_dtype=torch.bfloat16, layout_out="NDHWC", comm=comm)
     with torch.no_grad():
         for _ in range(2):
-            par.slab_global_forward(m, lf, rf, shift, proj, slab, out_dtype=torch.bfloat16, layout_out="NDHWC", comm=comm)
+            eager()
+        torch.cuda.synchronize()
+        run, launch = eager, "eager (one Python -> C-ABI launch per kernel / exchange)"
+        g = None
+        if os.environ.get("SNVC_STRESS_GRAPH", "1") != "0":
+            # one graph per rank holding the whole slab forward incl. the 10 NCCL halo exchanges; all ranks agree on
+            # whether the capture worked before anyone replays (the graphs contain matching sends / receives)
+            ok = torch.ones(1, device=dev)
+            try:
+                g = par.GraphedSlabForward(m, lf, rf, shift, proj, slab, comm=comm, warmup=0)
+            except Exception as e:                                     # noqa: BLE001 -- fall back to eager launches
+                ok.zero_()
+                g = None
+                sys.stderr.write(f"[rank {rank}] stress: graph capture failed ({str(e)[:120]}); eager launches\n")
+            if world > 1:
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() > 0:
+                run, launch = g.replay, "CUDA-graph replay (one graph per rank: kernels + halo exchanges)"
+        for _ in range(2):
+            run()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -292,9 +312,11 @@ def stress_leg(dev, rank, world, dist, steps=3):
         e0, e1 = ev(), ev()
         e0.record()
         for _ in range(steps):
-            par.slab_global_forward(m, lf, rf, shift, proj, slab, out_dtype=torch.bfloat16, layout_out="NDHWC", comm=comm)
+            run()
         e1.record()
         torch.cuda.synchronize()
+    if g is not None:
+        g.close()                                           # before the communicator: ncclCommDestroy waits for graphs that captured it
     if comm is not None:
         comm.close()
     ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
@@ -305,7 +327,8 @@ def stress_leg(dev, rank, world, dist, steps=3):
     torch.cuda.empty_cache()
     return {"workload": "configs[4] stress: 1 volume, D=96, features 32x384x1248 (cost volume 5.9 GB bf16, trunk 15.7 TFLOP)",
             "parallelism": f"depth slabs x{world}" + (", conv3d halo exchange: snvc_halo_exchange (one ncclGroup of send/recv with ranks r-1 / r+1 over NVLink) after each of the 10 layers" if world > 1 else ""),
-            "scaling": "strong", "ms_per_volume": ms.item(), "volumes_per_s": 1e3 / ms.item(),
+            "scaling": "strong", "launch": launch, "cost_volume_form": "split" if m.split_supported(D) else "full",
+            "ms_per_volume": ms.item(), "volumes_per_s": 1e3 / ms.item(),
             "aggregate_tflops": gflop / ms.item(), "slab_planes": slab.Dl,
             "halo_mb_per_rank_per_direction": halo_mb if world > 1 else 0.0}
 
@@ -581,10 +604,29 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(launches),
             "roofline": roof,
         }
+        # configs[3] / configs[4] sub-records: top-level keys for readers of the raw line, and inside `roofline` (next to
+        # the other per-stage fractions) because consumers that keep only the contract's keys drop unknown top-level ones
         if instance is not None:
             line["instance"] = instance
+            roof["stages"]["instance_roi_sampling"] = {
+                "bound": "hbm", "kernel": "roi_sample_fast_bf16_kernel (+ feature transposition), per proposal",
+                "ms_per_proposal": instance["roi_sampling"]["ms_per_proposal"], "achieved": instance["roi_sampling"]["achieved_gbs"],
+                "peak": peaks["hbm"], "unit": "GB/s", "frac": instance["roi_sampling"]["frac_hbm"], "traffic": None,
+                "algorithmic_bytes_per_launch": instance["roi_sampling"]["bytes_per_proposal"]}
+            roof["stages"]["instance_cnn"] = {
+                "bound": "tensor", "kernel": "instance 3-D CNN + BEV tail (conv3d_bigk / kdpair / conv2d kernels), per proposal",
+                "ms_per_proposal": instance["cnn"]["ms_per_proposal"], "achieved": instance["cnn"]["achieved_tflops"],
+                "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": instance["cnn"]["frac_tensor"],
+                "proposals_per_s": instance["proposals_per_s"], "parallelism": instance["parallelism"]}
         if stress is not None:
             line["stress"] = stress
+            if "ms_per_volume" in stress:
+                roof["stages"]["stress_volume"] = {
+                    "bound": "tensor", "kernel": "configs[4]: whole depth-slab forward of one D=96 full-resolution volume",
+                    "ms_per_volume": stress["ms_per_volume"], "achieved": stress["aggregate_tflops"],
+                    "peak": peaks["tf_sustained"] * world, "unit": "TFLOP/s",
+                    "frac": stress["aggregate_tflops"] / (peaks["tf_sustained"] * world), "scaling": "strong",
+                    "parallelism": stress["parallelism"]}
         if gpu_base is not None:
             line["gpu_baseline"] = gpu_base
         if cpu_v is not None:

@@ -185,7 +185,10 @@ typedef struct snvc_conv3d_desc {
   int32_t res_coffset;
   int32_t in_cstride;        /* channel stride of x's innermost dim (>= Cin); 0 -> Cin */
   int32_t in_coffset;        /* first channel read inside that stride (multiple of 8) */
-  int32_t reserved[2];
+  int32_t addend_edge_lo;    /* snvc_conv3d_fwd_addend only: which output planes are the FIRST / LAST plane of the whole   */
+  int32_t addend_edge_hi;    /* volume (they take addend plane 0 / 2): 0 = this tensor's own plane 0 / Do-1 (default);     */
+                             /* k > 0 = plane k / Do-1-k (a depth slab whose view starts k planes outside the volume);     */
+                             /* < 0 = none (an interior depth slab).  Ignored (keep 0) by snvc_conv3d_fwd.                 */
 } snvc_conv3d_desc;
 
 /* w: Conv3d [Cout,Cin,k,k,k] fp32 (transposed=0) or ConvTranspose3d [Cin,Cout,k,k,k] fp32

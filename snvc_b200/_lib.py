@@ -18,7 +18,7 @@ class ConvDesc(ctypes.Structure):
     _fields_ = [(n, _i32) for n in (
         "N", "Cin", "Cout", "Di", "Hi", "Wi", "Do", "Ho", "Wo", "kernel", "stride", "pad", "dilation",
         "transposed", "relu", "residual_mode", "sigmoid", "out_dtype", "out_cstride", "out_coffset",
-        "res_cstride", "res_coffset", "in_cstride", "in_coffset")] + [("reserved", _i32 * 2)]
+        "res_cstride", "res_coffset", "in_cstride", "in_coffset", "addend_edge_lo", "addend_edge_hi")]
 
 
 class Conv2dDesc(ctypes.Structure):

@@ -50,11 +50,13 @@ class PackedConv3d:
         return N, f(Di), f(Hi), f(Wi)
 
     def __call__(self, x, *, relu=False, residual=None, residual_mode=0, sigmoid=False, out_dtype=torch.bfloat16,
-                 out=None, out_coffset=0, res_coffset=0, in_coffset=0, addend=None):
+                 out=None, out_coffset=0, res_coffset=0, in_coffset=0, addend=None, addend_edges=(0, 0)):
         """x [N,D,H,W,Cin] bf16 -> y [N,Do,Ho,Wo,Cout] (or the channel slice [out_coffset, +Cout) of `out`).
         `in_coffset` / `res_coffset` select channel slices of wider x / residual buffers.
         `addend` (fp32 [N,3,Ho,Wo,Cout]): depth-invariant term added to the accumulator before scale / bias
-        (snvc_conv3d_fwd_addend; plane 0 / 1 / 2 for output depth 0 / interior / last)."""
+        (snvc_conv3d_fwd_addend; plane 0 / 1 / 2 for output depth 0 / interior / last).  `addend_edges` = (lo, hi) says
+        which output planes are the volume's first / last plane when x is a depth slab: 0 = the tensor's own edge plane,
+        k > 0 = plane k / Do-1-k, -1 = the slab does not contain that edge."""
         _lib.require_cuda(x)
         if x.dtype != torch.bfloat16 or not x.is_contiguous() or x.shape[-1] < in_coffset + self.cin:
             raise RuntimeError(f"conv3d: x must be contiguous NDHWC bf16 with >= {in_coffset + self.cin} channels, "
@@ -78,7 +80,9 @@ class PackedConv3d:
                           out_dtype=_lib.BF16 if out.dtype == torch.bfloat16 else _lib.F32,
                           out_cstride=out.shape[-1], out_coffset=out_coffset,
                           res_cstride=residual.shape[-1] if residual is not None else 0, res_coffset=res_coffset,
-                          in_cstride=x.shape[-1], in_coffset=in_coffset)
+                          in_cstride=x.shape[-1], in_coffset=in_coffset,
+                          addend_edge_lo=int(addend_edges[0]) if addend is not None else 0,
+                          addend_edge_hi=int(addend_edges[1]) if addend is not None else 0)
         if addend is not None:
             if residual is not None or sigmoid:
                 raise RuntimeError("conv3d: addend cannot be combined with a residual or sigmoid")

@@ -469,6 +469,7 @@ struct HaloParams {
   const float* scale;
   const float* bias;
   const float* addend;         // v8 only: fp32 [N,3,H,W,Cout] added to the accumulator (first / interior / last plane)
+  int add_lo, add_hi;          // output planes that take addend plane 0 / 2 (default 0 / D-1; -1 = none: depth slabs)
   EpiParams epi;
 };
 
@@ -1582,8 +1583,8 @@ conv3d_kdpair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
               tmem_ld_wait();
             }
             if (ADD) {
-              const bool edge = od == 0 || od == p.D - 1;              // output plane 0 / D-1: their own addend planes
-              const float* ep = arow + (od == 0 ? 0 : 2 * plane_vox * CP) + c0;
+              const bool edge = od == p.add_lo || od == p.add_hi;      // output plane 0 / D-1 of the VOLUME: their own addend planes
+              const float* ep = arow + (od == p.add_lo ? 0 : 2 * plane_vox * CP) + c0;
 #pragma unroll
               for (int j = 0; j < 16; j += 4) {
                 float4 t = make_float4(addm[c0 + j], addm[c0 + j + 1], addm[c0 + j + 2], addm[c0 + j + 3]);
@@ -2818,6 +2819,10 @@ int launch_kdpair(const void* x, const void* w_packed, const float* scale, const
   p.N = d.N; p.Cin = d.Cin; p.D = d.Di; p.H = d.Hi; p.W = d.Wi;
   p.K = 3; p.dil = 1; p.pad = 1;
   p.scale = scale; p.bias = bias; p.addend = addend;
+  // addend edge planes: desc.addend_edge_lo / _hi = 0 -> the tensor's own first / last plane; k > 0 -> plane k / Do-1-k
+  // (a depth slab whose view starts k planes before the volume); < 0 -> this slab does not hold that edge of the volume
+  p.add_lo = d.addend_edge_lo < 0 ? -1 : d.addend_edge_lo;
+  p.add_hi = d.addend_edge_hi < 0 ? -1 : d.Do - 1 - d.addend_edge_hi;
   p.epi.Cout = cp.Cout; p.epi.CoutPad = cp.CoutPad; p.epi.relu = cp.relu; p.epi.residual_mode = cp.residual_mode;
   p.epi.sigmoid = 0; p.epi.out_f32 = cp.out_f32; p.epi.out_cstride = cp.out_cstride;
   p.epi.out_coffset = cp.out_coffset; p.epi.res_cstride = cp.res_cstride; p.epi.res_coffset = cp.res_coffset;

@@ -87,12 +87,14 @@ def build_cost_volume_ndhwc_bf16(left, right, shift, downsample=1):
     return _forward(left, right, shift, downsample, _lib.BF16, _lib.NDHWC)
 
 
-def build_cost_volume_split_bf16(left, right, shift, downsample=1, parts="both"):
+def build_cost_volume_split_bf16(left, right, shift, downsample=1, parts="both", out_right=None):
     """Split form of the NDHWC bf16 cost volume (snvc_cost_volume_split_fwd): the left half is a pure broadcast over
     depth (BuildCostVolume_cuda.cu:84-86), so it is written once.  Returns
     (right_vol [N,D,H,W,C] = channels [C,2C) of the full volume, left_planes [N,3,H,W,C] = the left features on three
     identical planes, the input of the depth-invariant part of the first trunk convolution).
-    `parts` = "right" / "left" builds (and returns) only that half: the two are independent launches."""
+    `parts` = "right" / "left" builds (and returns) only that half: the two are independent launches.
+    `out_right`: a contiguous [N,D,H,W,C] bf16 tensor (e.g. the real planes of a depth slab's extended buffer, N = 1) that
+    receives the right half instead of a fresh allocation."""
     _check_inputs(left, right, shift)
     if left.dtype != torch.float32:
         raise RuntimeError("build_cost_volume_split_bf16: fp32 features only")
@@ -103,7 +105,13 @@ def build_cost_volume_split_bf16(left, right, shift, downsample=1, parts="both")
     H, W = IH // ds, IW // ds
     right_vol = left_planes = None
     if parts in ("both", "right"):
-        right_vol = torch.empty((N, D, H, W, C), dtype=torch.bfloat16, device=left.device)
+        if out_right is not None:
+            if tuple(out_right.shape) != (N, D, H, W, C) or out_right.dtype != torch.bfloat16 or not out_right.is_contiguous() \
+                    or out_right.device != left.device:
+                raise RuntimeError("build_cost_volume_split_bf16: out_right must be a contiguous [N,D,H,W,C] bf16 tensor")
+            right_vol = out_right
+        else:
+            right_vol = torch.empty((N, D, H, W, C), dtype=torch.bfloat16, device=left.device)
     if parts in ("both", "left"):
         left_planes = torch.empty((N, 3, H, W, C), dtype=torch.bfloat16, device=left.device)
     with torch.cuda.device(left.device):

@@ -229,10 +229,24 @@ class SlabTrunk:
             kw["residual"] = residual
         return self._xchg(layer.fused(x[:, 1:-1], **kw))
 
-    def __call__(self, cost):
-        """cost: extended cost-volume slab [1, Dl+2*HALO, H, W, 2F] (inner halo planes valid, or zero at the boundary)."""
+    def head_split(self, right_ext, addend):
+        """dres0.conv1 on the SPLIT cost volume of a slab (models/stereonet.py:trunk_head_split): `right_ext` is the extended
+        right-half slab [1, Dl+2*HALO, H, W, F], `addend` the fp32 [1,3,H,W,ch] share of the depth-constant left half.  The
+        addend's edge variants belong to the first / last plane of the WHOLE volume, which sit one plane inside the
+        convolved view on the first / last rank and nowhere on interior ranks."""
+        plan = self.m._split_plans()[1]
+        out = torch.empty(tuple(right_ext.shape[:-1]) + (plan.cout,), dtype=right_ext.dtype, device=right_ext.device)
+        out[:, 0].zero_()
+        out[:, -1].zero_()
+        edges = (1 if self.slab.first else -1, 1 if self.slab.last else -1)
+        plan(right_ext[:, 1:-1], relu=True, addend=addend, addend_edges=edges, out=out[:, 1:-1])
+        return self._xchg(out)
+
+    def __call__(self, cost=None, head=None):
+        """cost: extended cost-volume slab [1, Dl+2*HALO, H, W, 2F] (inner halo planes valid, or zero at the boundary);
+        or `head` = the output of `head_split` (dres0.conv1 already applied to the split volume)."""
         m = self.m
-        x = self._s1(m.dres0[0], cost)
+        x = head if head is not None else self._s1(m.dres0[0], cost)
         x = self._s1(m.dres0[1], x)
         y = self._s1(m.dres1[0], x)
         x = self._s1(m.dres1[1], y, residual=x, residual_mode=1)
@@ -262,6 +276,16 @@ def slab_z_range(zs, cv_z_min, cv_z_max, D, slab, align_corners=True):
     return int(idx[0]), int(idx[-1]) + 1
 
 
+def _cached_z_range(model, D, slab):
+    """slab_z_range of the model's voxel grid, computed once per (model, D, world, rank): it reads `model.zs` back to the
+    host, which would otherwise synchronise every forward."""
+    cache = model.__dict__.setdefault("_snvc_slab_z", {})
+    key = (D, slab.world, slab.rank, model.zs.data_ptr(), model.zs._version)
+    if key not in cache:
+        cache[key] = slab_z_range(model.zs.cpu().numpy(), model.cv_range[4], model.cv_range[5], D, slab, model.align_corners)
+    return cache[key]
+
+
 def slab_global_forward(model, left_feat, right_feat, shift, proj, slab, group=None, out_dtype=torch.float32,
                         layout_out="NCDHW", comm=None):
     """Depth-slab-parallel GlobalHotPath.forward for ONE pair (N == 1).
@@ -269,7 +293,7 @@ def slab_global_forward(model, left_feat, right_feat, shift, proj, slab, group=N
     Every rank passes the same (replicated) inputs and returns (voxels[:, zlo:zhi] slice, (zlo, zhi)):
     its slice of the lifted voxel grid along Z (layout as `GlobalHotPath.forward`)."""
     from snvc_b200 import functional as SF
-    from snvc_b200.extension.build_cost_volume import build_cost_volume_ndhwc_bf16
+    from snvc_b200.extension.build_cost_volume import build_cost_volume_ndhwc_bf16, build_cost_volume_split_bf16
     if left_feat.shape[0] != 1:
         raise RuntimeError("slab_global_forward handles one pair (the stress configuration)")
     D = shift.shape[1]
@@ -277,17 +301,87 @@ def slab_global_forward(model, left_feat, right_feat, shift, proj, slab, group=N
         raise RuntimeError("shift / slab depth mismatch")
     bins = slab.ext_bins()
     keep = [b for b in bins if 0 <= b < D]
-    cost_in = build_cost_volume_ndhwc_bf16(left_feat, right_feat, shift[:, keep[0]:keep[-1] + 1].contiguous(), 1)
     lo_pad, hi_pad = keep[0] - bins[0], bins[-1] - keep[-1]
-    if lo_pad or hi_pad:
-        cost = torch.zeros((1, len(bins)) + tuple(cost_in.shape[2:]), dtype=cost_in.dtype, device=cost_in.device)
-        cost[:, lo_pad:lo_pad + len(keep)] = cost_in
-    else:
-        cost = cost_in
-    feat = SlabTrunk(model, slab, group, comm)(cost)                  # [1, Dl+2*HALO, H, W, ch]
-    zlo, zhi = slab_z_range(model.zs.cpu().numpy(), model.cv_range[4], model.cv_range[5], D, slab,
-                            model.align_corners)
+    sh = shift[:, keep[0]:keep[-1] + 1].contiguous()
+    trunk = SlabTrunk(model, slab, group, comm)
+    F, H, W = left_feat.shape[1], left_feat.shape[2], left_feat.shape[3]
+    split = hasattr(model, "split_supported") and model.split_supported(D)
+
+    def ext_buffer(ch):
+        """extended slab [1, Dl+2*HALO, H, W, ch]; planes outside the volume are the convolution's zero padding.  The
+        volume kernels write the slab's real planes straight into it (batch 1: a depth range is a contiguous view)."""
+        buf = torch.empty((1, len(bins), H, W, ch), dtype=torch.bfloat16, device=left_feat.device)
+        if lo_pad:
+            buf[:, :lo_pad].zero_()
+        if hi_pad:
+            buf[:, len(bins) - hi_pad:].zero_()
+        return buf, buf[:, lo_pad:lo_pad + len(keep)]
+
+    feat = None
+    if split:
+        # split cost volume (models/stereonet.py): right half per slab, the depth-constant left half as a 3-plane addend
+        right_ext, real = ext_buffer(F)
+        _, left_planes = build_cost_volume_split_bf16(left_feat, right_feat, sh, 1, out_right=real)
+        try:
+            feat = trunk(head=trunk.head_split(right_ext, model.trunk_head_addend(left_planes)))
+        except RuntimeError as e:
+            if "(-2)" not in str(e):          # SNVC_E_UNSUPPORTED: no cluster launch on this device -> unsplit volume
+                raise
+    if feat is None:
+        cost_in = build_cost_volume_ndhwc_bf16(left_feat, right_feat, sh, 1)
+        if lo_pad or hi_pad:
+            cost, real = ext_buffer(2 * F)
+            real.copy_(cost_in)
+        else:
+            cost = cost_in
+        feat = trunk(cost)                                            # [1, Dl+2*HALO, H, W, ch]
+    zlo, zhi = _cached_z_range(model, D, slab)
     vox = SF.frustum_lift(feat, proj, model.zs[zlo:zhi].contiguous(), model.ys, model.xs, model.cv_range,
                           model.align_corners, layout_in="NDHWC", out_dtype=out_dtype, layout_out=layout_out,
                           d_total=D, d_base=bins[0])
     return vox, (zlo, zhi)
+
+
+class GraphedSlabForward:
+    """CUDA-graph replay of `slab_global_forward` for fixed inputs shapes: the ~45 kernel launches, 15 allocations and 10
+    halo exchanges (ncclSend / ncclRecv groups are capturable) of one slab forward become one `cudaGraphLaunch`.  With 8
+    ranks a slab forward is ~2.5 ms of GPU work, less than the host needs to enqueue it eagerly from Python.
+    Every rank must construct and replay it collectively (the captured graphs contain matching sends / receives)."""
+
+    def __init__(self, model, left_feat, right_feat, shift, proj, slab, comm=None, out_dtype=torch.bfloat16,
+                 layout_out="NDHWC", warmup=2):
+        self.inputs = tuple(t.clone() for t in (left_feat, right_feat, shift, proj))
+        self.args = (model, slab, comm, out_dtype, layout_out)
+        dev = left_feat.device
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(warmup):                              # library / NCCL connection set-up happens outside the capture
+                self._run()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.vox, self.z_range = self._run()
+
+    def _run(self):
+        model, slab, comm, out_dtype, layout_out = self.args
+        l, r, sh, pr = self.inputs
+        return slab_global_forward(model, l, r, sh, pr, slab, out_dtype=out_dtype, layout_out=layout_out, comm=comm)
+
+    def load(self, left_feat, right_feat, shift, proj):
+        for d, s_ in zip(self.inputs, (left_feat, right_feat, shift, proj)):
+            d.copy_(s_, non_blocking=True)
+
+    def replay(self):
+        self.graph.replay()
+        return self.vox, self.z_range
+
+    def close(self):
+        """Destroy the captured graph.  Must happen BEFORE the HaloComm is closed: NCCL keeps a communicator alive while a
+        captured graph references it, and ncclCommDestroy blocks until that graph is gone (measured: a 60 s hang)."""
+        if self.graph is not None:
+            self.graph.reset()
+            self.graph = None
+        self.vox = None
+
