@@ -573,6 +573,10 @@ int launch_cv_ndhwc(const void* left, const void* right, const void* shift, void
     if (rows + (size_t)W * 8 <= 225 * 1024) {
       int d_per = (int)D;
       if (rows + (size_t)W * D * 8 > budget) d_per = (int)std::max<int64_t>(1, ((int64_t)std::max<size_t>(budget, rows + W * 8) - (int64_t)rows) / (W * 8));
+      // a row wider than the 3-CTA budget (full-resolution stress volume: 1248 x 32 x 4 B = 160 KB) runs one CTA per SM
+      // anyway: give that CTA as many bins as the 225 KB allow, instead of staging 160 KB for ONE 80 KB output row
+      if (rows + (size_t)W * 8 > budget)
+        d_per = (int)std::max<int64_t>(1, std::min<int64_t>(D, (int64_t)(225 * 1024 - rows) / (W * 8)));
       // fill whole waves: more depth splits when the grid would leave SMs idle
       const double wave = (rows + (size_t)W * d_per * 8 <= budget ? 3.0 : 2.0) * sm_count();
       double best = -1;
