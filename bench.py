@@ -280,9 +280,14 @@ def stress_leg(dev, rank, world, dist, steps=5):
     shift = torch.from_numpy(plane_sweep_shifts(cfg, 1)).to(dev)
     proj = torch.from_numpy(KITTI_P2[None].copy()).to(dev)
     slab = par.DepthSlab(D, world, rank)
-    comm = par.HaloComm(world, rank, dev) if world > 1 else None
+    # halo exchange: peer-memory push (snvc_halo_push over a CUDA-IPC-mapped arena; default) or NCCL point-to-point through
+    # the C ABI (SNVC_STRESS_HALO=nccl, the A/B baseline: 146 GB/s per direction and neighbour on the 8-GPU box)
+    use_peer = world > 1 and os.environ.get("SNVC_STRESS_HALO", "peer") != "nccl"
+    comm = par.HaloComm(world, rank, dev) if (world > 1 and not use_peer) else None
+    arena = par.PeerArena(world, rank, dev, par.slab_arena_bytes(slab, H, W)) if use_peer else None
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    eager = lambda: par.slab_global_forward(m, lf, rf, shift, proj, slab, out_dtype=torch.bfloat16, layout_out="NDHWC", comm=comm)
+    eager = lambda: par.slab_global_forward(m, lf, rf, shift, proj, slab, out_dtype=torch.bfloat16, layout_out="NDHWC", comm=comm,
+                                            arena=arena)
     with torch.no_grad():
         for _ in range(2):
             eager()
@@ -294,7 +299,7 @@ def stress_leg(dev, rank, world, dist, steps=5):
             # whether the capture worked before anyone replays (the graphs contain matching sends / receives)
             ok = torch.ones(1, device=dev)
             try:
-                g = par.GraphedSlabForward(m, lf, rf, shift, proj, slab, comm=comm, warmup=0)
+                g = par.GraphedSlabForward(m, lf, rf, shift, proj, slab, comm=comm, warmup=0, arena=arena)
             except Exception as e:                                     # noqa: BLE001 -- fall back to eager launches
                 ok.zero_()
                 g = None
@@ -319,6 +324,8 @@ def stress_leg(dev, rank, world, dist, steps=5):
         g.close()                                           # before the communicator: ncclCommDestroy waits for graphs that captured it
     if comm is not None:
         comm.close()
+    if arena is not None:
+        arena.close()
     ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -326,7 +333,9 @@ def stress_leg(dev, rank, world, dist, steps=5):
     halo_mb = 384 * 1248 * 2 / 1e6 * (32 * 5 + 64 * (2 / 4 + 3 / 16))        # one plane per direction per layer, summed over the 10 layers
     torch.cuda.empty_cache()
     return {"workload": "configs[4] stress: 1 volume, D=96, features 32x384x1248 (cost volume 5.9 GB bf16, trunk 15.7 TFLOP)",
-            "parallelism": f"depth slabs x{world}" + (", conv3d halo exchange: snvc_halo_exchange (one ncclGroup of send/recv with ranks r-1 / r+1 over NVLink) after each of the 10 layers" if world > 1 else ""),
+            "parallelism": f"depth slabs x{world}" + ((", conv3d halo exchange after each of the 10 layers: " +
+                                                               ("snvc_halo_push (one kernel: 16-byte peer stores of the boundary planes into the neighbours' CUDA-IPC-mapped slabs over NVLink + epoch barrier)"
+                                                                if use_peer else "snvc_halo_exchange (one ncclGroup of send/recv with ranks r-1 / r+1)")) if world > 1 else ""),
             "scaling": "strong", "launch": launch, "cost_volume_form": "split" if m.split_supported(D) else "full",
             "ms_per_volume": ms.item(), "volumes_per_s": 1e3 / ms.item(),
             "aggregate_tflops": gflop / ms.item(), "slab_planes": slab.Dl,

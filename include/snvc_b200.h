@@ -353,6 +353,27 @@ int snvc_halo_comm_destroy(void* comm);
 int snvc_halo_exchange(void* comm, void* x, int64_t planes_ext, int64_t plane_bytes, int32_t halo, int32_t rank,
                        int32_t world, void* stream);
 
+/* The same exchange over NVLink / NVSwitch PEER MEMORY, without NCCL on the data path (the product path of the stress
+ * configuration; snvc_halo_exchange measures 146 GB/s per direction and neighbour on an 8 x B200 box, this 4-5 x that).
+ * Every rank keeps its slab buffers in an arena from snvc_peer_alloc (a cudaMalloc block, zero-filled); the 64-byte CUDA
+ * IPC handle from snvc_peer_export is distributed out of band and the two neighbours map the arena with snvc_peer_open.
+ * Because all ranks carve the arena identically, a slab at offset o of the local arena is at offset o of a neighbour's
+ * mapping.  The first snvc_peer_ctl_bytes() bytes of an arena are its control block (epoch words; keep them zero).
+ * snvc_halo_push(x, ...): ONE kernel that stores the slab's first / last real plane into the lower / upper neighbour's
+ * inner halo plane (x_in_lo_peer / x_in_hi_peer = the address of the same slab in that neighbour's mapped arena; NULL at
+ * an end of the volume, where the local inner halo plane is zero-filled instead) and then acts as the neighbour barrier:
+ * it returns on the stream once both neighbours' planes have landed in x.  ctl / ctl_lo_peer / ctl_hi_peer: the control
+ * blocks of the local arena and of the two mappings.  Every rank must call it for the same sequence of slabs.  A wait
+ * longer than ~4 s traps (a lost neighbour must not hang the device).  Capturable in a CUDA graph. */
+int snvc_peer_alloc(int64_t bytes, void** ptr);
+int snvc_peer_free(void* ptr);
+int snvc_peer_export(void* ptr, void* handle64);
+int snvc_peer_open(const void* handle64, void** peer_ptr);
+int snvc_peer_close(void* peer_ptr);
+int64_t snvc_peer_ctl_bytes(void);
+int snvc_halo_push(void* x, void* x_in_lo_peer, void* x_in_hi_peer, int64_t planes_ext, int64_t plane_bytes, int32_t halo,
+                   void* ctl, void* ctl_lo_peer, void* ctl_hi_peer, int32_t max_blocks, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Host return of a row-masked volume (end-to-end path of the global branch).
  * Replaces the blocking dense `.cpu()` the reference's driver does on its outputs

@@ -70,6 +70,13 @@ _SIGS = {
     "snvc_halo_comm_create": ([_p, _i32, _i32, ctypes.POINTER(ctypes.c_void_p)], _i32),
     "snvc_halo_comm_destroy": ([_p], _i32),
     "snvc_halo_exchange": ([_p, _p, _i64, _i64, _i32, _i32, _i32, _p], _i32),
+    "snvc_peer_alloc": ([_i64, ctypes.POINTER(ctypes.c_void_p)], _i32),
+    "snvc_peer_free": ([_p], _i32),
+    "snvc_peer_export": ([_p, _p], _i32),
+    "snvc_peer_open": ([_p, ctypes.POINTER(ctypes.c_void_p)], _i32),
+    "snvc_peer_close": ([_p], _i32),
+    "snvc_peer_ctl_bytes": ([], _i64),
+    "snvc_halo_push": ([_p, _p, _p, _i64, _i64, _i32, _p, _p, _p, _i32, _p], _i32),
     "snvc_masked_rows_to_host": ([_p, _p, _p, _p, _i64, _i32, _i32, _p, _p], _i32),
 }
 

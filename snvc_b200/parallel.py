@@ -123,6 +123,107 @@ class HaloComm:
             self.comm = None
 
 
+class _RawCuda:
+    """`__cuda_array_interface__` view of raw device memory (torch.as_tensor wraps it without a copy)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+class PeerArena:
+    """Slab buffers in NVLink / NVSwitch PEER MEMORY: the product path of the depth-slab halo exchange (snvc_halo_push).
+
+    Every rank allocates one arena with the library (snvc_peer_alloc: a cudaMalloc block, so it can be exported through
+    CUDA IPC), the 64-byte handles travel through `torch.distributed.all_gather`, and each rank maps the arenas of ranks
+    r-1 and r+1.  All ranks carve their arena identically (`reset()` at the start of a forward, then the same sequence of
+    `empty()` calls), so a slab at offset o here is at offset o in a neighbour's mapping, and `push(x)` can store this
+    slab's first / last real plane straight into the neighbours' inner halo planes -- one kernel that is also the neighbour
+    barrier -- instead of an ncclSend / ncclRecv group (146 GB/s per direction on the 8 x B200 box)."""
+
+    ALIGN = 256
+
+    def __init__(self, world, rank, device, nbytes, group=None):
+        import ctypes
+        from snvc_b200 import _lib
+        self.world, self.rank, self.device, self.group = world, rank, device, group
+        L = _lib.lib()
+        self.ctl_bytes = int(L.snvc_peer_ctl_bytes())
+        self.nbytes = int(nbytes) + self.ctl_bytes + self.ALIGN
+        self.base, self.lo, self.hi = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(L.snvc_peer_alloc(self.nbytes, ctypes.byref(self.base)), "snvc_peer_alloc")
+            handle = (ctypes.c_ubyte * 64)()
+            _lib.check(L.snvc_peer_export(self.base, handle), "snvc_peer_export")
+            # (gloo -- the CPU-side tests with both ranks on one GPU -- gathers host tensors)
+            mine = torch.tensor(list(handle), dtype=torch.uint8, device="cpu" if dist.get_backend(group) == "gloo" else device)
+            every = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(every, mine, group=group)
+            for attr, peer in (("lo", rank - 1), ("hi", rank + 1)):
+                if 0 <= peer < world:
+                    raw = (ctypes.c_ubyte * 64)(*every[peer].cpu().tolist())
+                    _lib.check(L.snvc_peer_open(raw, ctypes.byref(getattr(self, attr))), "snvc_peer_open")
+        self.mem = torch.as_tensor(_RawCuda(self.base.value, self.nbytes), device=device)
+        self.off = self.ctl_bytes
+        dist.barrier(group=group)                               # every mapping exists before anyone pushes
+
+    def reset(self):
+        self.off = self.ctl_bytes
+
+    def empty(self, shape, dtype=torch.bfloat16):
+        n = 1
+        for v in shape:
+            n *= int(v)
+        nb = n * torch.empty((), dtype=dtype).element_size()
+        start = (self.off + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        if start + nb > self.nbytes:
+            raise RuntimeError(f"PeerArena: {start + nb} bytes needed, {self.nbytes} allocated")
+        self.off = start + nb
+        return self.mem[start:start + nb].view(dtype).view(tuple(shape))
+
+    def owns(self, x):
+        return self.base.value <= x.data_ptr() < self.base.value + self.nbytes
+
+    def push(self, x):
+        """Halo exchange of the extended slab x [1, planes, H, W, C] (allocated by `empty`), in place, on the current stream."""
+        from snvc_b200 import _lib
+        o = x.data_ptr() - self.base.value
+        planes = x.shape[1]
+        plane_bytes = x[0, 0].numel() * x.element_size()
+        lo = self.lo.value + o if self.lo else None
+        hi = self.hi.value + o if self.hi else None
+        with torch.cuda.device(x.device):
+            st = _lib.lib().snvc_halo_push(x.data_ptr(), lo, hi, planes, plane_bytes, HALO, self.base.value,
+                                           self.lo.value if self.lo else None, self.hi.value if self.hi else None, 0,
+                                           _lib.stream_ptr())
+        _lib.check(st, "snvc_halo_push")
+        return x
+
+    def close(self):
+        from snvc_b200 import _lib
+        if self.base:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)                      # nobody unmaps an arena a neighbour may still push into
+            L = _lib.lib()
+            self.mem = None
+            with torch.cuda.device(self.device):
+                for h in (self.lo, self.hi):
+                    if h:
+                        L.snvc_peer_close(h)
+                dist.barrier(group=self.group)
+                L.snvc_peer_free(self.base)
+            self.base = self.lo = self.hi = None
+
+
+def slab_arena_bytes(slab, H, W, ch=32):
+    """Upper bound of the arena bytes one `slab_global_forward` carves: five full-resolution ch-channel slabs (dres0 x 2,
+    dres1 x 2, hourglass output), three half-resolution and two quarter-resolution 2*ch-channel slabs, each with 2*HALO
+    extra planes, + alignment slack."""
+    full = (slab.Dl + 2 * HALO) * H * W * ch * 2
+    half = (slab.Dl // 2 + 2 * HALO) * ((H + 1) // 2) * ((W + 1) // 2) * 2 * ch * 2
+    quarter = (slab.Dl // 4 + 2 * HALO) * ((H + 3) // 4) * ((W + 3) // 4) * 2 * ch * 2
+    return 5 * full + 3 * half + 2 * quarter + 16 * PeerArena.ALIGN
+
+
 def exchange_depth_halo(x, slab, group=None, comm=None):
     """x: [1, Dl_level + 2*HALO, H, W, C] extended slab at any pyramid level (in place).
 
@@ -181,11 +282,18 @@ class SlabTrunk:
     exchange after every layer.  `model` needs attributes dres0, dres1, hg with the fused-layer
     interface; tensors are NDHWC with N == 1 (depth slices of an N=1 volume are contiguous views)."""
 
-    def __init__(self, model, slab, group=None, comm=None):
-        self.m, self.slab, self.group, self.comm = model, slab, group, comm
+    def __init__(self, model, slab, group=None, comm=None, arena=None):
+        self.m, self.slab, self.group, self.comm, self.arena = model, slab, group, comm, arena
 
     def _xchg(self, x):
+        if self.arena is not None and x.is_cuda and self.arena.owns(x):
+            return self.arena.push(x)                            # NVLink peer stores + neighbour barrier in one kernel
         return exchange_depth_halo(x, self.slab, self.group, self.comm)
+
+    def _empty(self, shape, like):
+        if self.arena is not None and like.is_cuda and like.dtype == torch.bfloat16:
+            return self.arena.empty(shape, like.dtype)
+        return torch.empty(shape, dtype=like.dtype, device=like.device)
 
     @staticmethod
     def _cout(layer):
@@ -202,7 +310,7 @@ class SlabTrunk:
         convolved (input view x[:, 1:-1], zero padding beyond it), so the slab costs (Dl + 2) planes of work instead of
         (Dl + 4); the two inner halo outputs lack a depth tap and are overwritten by the exchange."""
         cout = self._cout(layer)
-        out = torch.empty(tuple(x.shape[:-1]) + (cout,), dtype=x.dtype, device=x.device)
+        out = self._empty(tuple(x.shape[:-1]) + (cout,), x)
         out[:, 0].zero_()
         out[:, -1].zero_()
         if residual is not None:
@@ -217,7 +325,7 @@ class SlabTrunk:
         assert N == 1 and (De - 2 * HALO) % 2 == 0
         Do = (De - 2 * HALO) // 2 + 2 * HALO
         cout = self._cout(layer)
-        out = torch.empty((1, Do, (H + 1) // 2, (W + 1) // 2, cout), dtype=x.dtype, device=x.device)
+        out = self._empty((1, Do, (H + 1) // 2, (W + 1) // 2, cout), x)
         out[:, 0].zero_()
         out[:, -1].zero_()
         layer.fused(x, out=out[:, 1:-1], **kw)
@@ -227,6 +335,9 @@ class SlabTrunk:
         """transposed conv (k3,s2,p1,op1): input planes [1, -1) of the ext slab -> ext slab at 2x resolution."""
         if residual is not None:
             kw["residual"] = residual
+        if self.arena is not None and x.is_cuda:
+            N, De, H, W, _ = x.shape
+            kw["out"] = self._empty((N, 2 * (De - 2), 2 * H, 2 * W, self._cout(layer)), x)
         return self._xchg(layer.fused(x[:, 1:-1], **kw))
 
     def head_split(self, right_ext, addend):
@@ -235,7 +346,7 @@ class SlabTrunk:
         addend's edge variants belong to the first / last plane of the WHOLE volume, which sit one plane inside the
         convolved view on the first / last rank and nowhere on interior ranks."""
         plan = self.m._split_plans()[1]
-        out = torch.empty(tuple(right_ext.shape[:-1]) + (plan.cout,), dtype=right_ext.dtype, device=right_ext.device)
+        out = self._empty(tuple(right_ext.shape[:-1]) + (plan.cout,), right_ext)
         out[:, 0].zero_()
         out[:, -1].zero_()
         edges = (1 if self.slab.first else -1, 1 if self.slab.last else -1)
@@ -287,11 +398,13 @@ def _cached_z_range(model, D, slab):
 
 
 def slab_global_forward(model, left_feat, right_feat, shift, proj, slab, group=None, out_dtype=torch.float32,
-                        layout_out="NCDHW", comm=None):
+                        layout_out="NCDHW", comm=None, arena=None):
     """Depth-slab-parallel GlobalHotPath.forward for ONE pair (N == 1).
 
     Every rank passes the same (replicated) inputs and returns (voxels[:, zlo:zhi] slice, (zlo, zhi)):
-    its slice of the lifted voxel grid along Z (layout as `GlobalHotPath.forward`)."""
+    its slice of the lifted voxel grid along Z (layout as `GlobalHotPath.forward`).
+    Halo exchange: `arena` (PeerArena: NVLink peer stores, the product path) > `comm` (HaloComm: NCCL point-to-point through
+    the C ABI) > torch.distributed point-to-point ops (gloo in the CPU tests)."""
     from snvc_b200 import functional as SF
     from snvc_b200.extension.build_cost_volume import build_cost_volume_ndhwc_bf16, build_cost_volume_split_bf16
     if left_feat.shape[0] != 1:
@@ -303,7 +416,9 @@ def slab_global_forward(model, left_feat, right_feat, shift, proj, slab, group=N
     keep = [b for b in bins if 0 <= b < D]
     lo_pad, hi_pad = keep[0] - bins[0], bins[-1] - keep[-1]
     sh = shift[:, keep[0]:keep[-1] + 1].contiguous()
-    trunk = SlabTrunk(model, slab, group, comm)
+    if arena is not None:
+        arena.reset()                                                 # same carving on every rank and in every forward
+    trunk = SlabTrunk(model, slab, group, comm, arena)
     F, H, W = left_feat.shape[1], left_feat.shape[2], left_feat.shape[3]
     split = hasattr(model, "split_supported") and model.split_supported(D)
 
@@ -349,9 +464,9 @@ class GraphedSlabForward:
     Every rank must construct and replay it collectively (the captured graphs contain matching sends / receives)."""
 
     def __init__(self, model, left_feat, right_feat, shift, proj, slab, comm=None, out_dtype=torch.bfloat16,
-                 layout_out="NDHWC", warmup=2):
+                 layout_out="NDHWC", warmup=2, arena=None):
         self.inputs = tuple(t.clone() for t in (left_feat, right_feat, shift, proj))
-        self.args = (model, slab, comm, out_dtype, layout_out)
+        self.args = (model, slab, comm, out_dtype, layout_out, arena)
         dev = left_feat.device
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
@@ -365,9 +480,10 @@ class GraphedSlabForward:
             self.vox, self.z_range = self._run()
 
     def _run(self):
-        model, slab, comm, out_dtype, layout_out = self.args
+        model, slab, comm, out_dtype, layout_out, arena = self.args
         l, r, sh, pr = self.inputs
-        return slab_global_forward(model, l, r, sh, pr, slab, out_dtype=out_dtype, layout_out=layout_out, comm=comm)
+        return slab_global_forward(model, l, r, sh, pr, slab, out_dtype=out_dtype, layout_out=layout_out, comm=comm,
+                                   arena=arena)
 
     def load(self, left_feat, right_feat, shift, proj):
         for d, s_ in zip(self.inputs, (left_feat, right_feat, shift, proj)):

@@ -47,7 +47,7 @@ def _model(cfg, dev):
     return m.to(dev)
 
 
-def _slab_run(rank, world, dev, use_comm=False):
+def _slab_run(rank, world, dev, use_comm=False, use_arena=False):
     from snvc_b200 import parallel as par
     cfg, lf, rf, shift, P = _cfg_and_inputs()
     with torch.no_grad():
@@ -56,10 +56,16 @@ def _slab_run(rank, world, dev, use_comm=False):
         full = m(*args)                                                   # [1, C, Z, Y, X] fp32
         slab = par.DepthSlab(shift.shape[1], world, rank)
         comm = par.HaloComm(world, rank, dev) if use_comm else None      # C-ABI snvc_halo_exchange over its own NCCL communicator
-        part, (zlo, zhi) = par.slab_global_forward(m, *args, slab, comm=comm)
+        # peer-memory path: slabs in a CUDA-IPC-mapped arena, snvc_halo_push (NVLink peer stores + neighbour barrier)
+        arena = par.PeerArena(world, rank, dev, par.slab_arena_bytes(slab, lf.shape[2], lf.shape[3])) if use_arena else None
+        for _ in range(3 if use_arena else 1):                            # repeated forwards reuse the arena (epochs advance)
+            part, (zlo, zhi) = par.slab_global_forward(m, *args, slab, comm=comm, arena=arena)
+        part = part.clone()
         torch.cuda.synchronize(dev)
         if comm is not None:
             comm.close()
+        if arena is not None:
+            arena.close()
     ref = full[:, :, zlo:zhi]
     err = float((part - ref).abs().max() / full.abs().max()) if zhi > zlo else 0.0
     return zlo, zhi, err, int(full.shape[2])
@@ -82,7 +88,7 @@ def test_slab_world1_matches_unsplit(mode, tol, monkeypatch):
     assert err <= tol, err           # same planes, same weights: only the slab bookkeeping differs
 
 
-def _worker(rank, world, port, use_nccl, q):
+def _worker(rank, world, port, use_nccl, q, use_arena=False):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -90,7 +96,7 @@ def _worker(rank, world, port, use_nccl, q):
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl" if use_nccl else "gloo", rank=rank, world_size=world)
     try:
-        q.put((rank,) + _slab_run(rank, world, dev, use_comm=use_nccl))
+        q.put((rank,) + _slab_run(rank, world, dev, use_comm=use_nccl and not use_arena, use_arena=use_arena))
     finally:
         dist.destroy_process_group()
 
@@ -115,3 +121,28 @@ def test_slab_world2_matches_unsplit(mode, tol, monkeypatch):
     assert lo0 == 0 and hi0 == lo1 and hi1 == Z and hi0 > 0 and hi1 > lo1
     # identical inputs; slabs see identical planes after the exchange ("kw": bf16-identical features)
     assert e0 <= tol and e1 <= tol, (e0, e1)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_slab_peer_memory_halo_matches_unsplit(world, monkeypatch):
+    """The product halo path of the stress configuration: slabs in CUDA-IPC-mapped peer memory, snvc_halo_push (peer stores
+    over NVLink + neighbour barrier in one kernel) instead of NCCL.  Needs one GPU per rank (the push kernels of the
+    ranks wait for each other on the device)."""
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    set_opt(monkeypatch, "SNVC_CONV_MODE", "kw")           # geometry-independent summation order: exact bookkeeping check
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, True, q, True)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    Z = res[0][4]
+    assert res[0][1] == 0 and res[-1][2] == Z and all(res[i][2] == res[i + 1][1] for i in range(world - 1))
+    assert all(r[3] <= 1e-6 for r in res), [r[3] for r in res]
+
