@@ -97,8 +97,23 @@ def _worker(rank, world, port, use_nccl, q, use_arena=False):
     dist.init_process_group("nccl" if use_nccl else "gloo", rank=rank, world_size=world)
     try:
         q.put((rank,) + _slab_run(rank, world, dev, use_comm=use_nccl and not use_arena, use_arena=use_arena))
+    except Exception as e:                                   # noqa: BLE001 -- the parent must not wait for a dead rank
+        q.put((rank, "error", repr(e)))
+        raise
     finally:
         dist.destroy_process_group()
+
+
+def _collect(q, procs, world):
+    res = [q.get(timeout=150) for _ in range(world)]
+    bad = [r for r in res if len(r) > 1 and r[1] == "error"]
+    for p in procs:
+        p.join(timeout=30)
+        if p.is_alive():
+            p.kill()
+    assert not bad, bad
+    assert all(p.exitcode == 0 for p in procs)
+    return sorted(res)
 
 
 @pytest.mark.parametrize("mode,tol", MODES)
@@ -113,17 +128,14 @@ def test_slab_world2_matches_unsplit(mode, tol, monkeypatch):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, use_nccl, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = sorted(q.get(timeout=300) for _ in range(2))
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    res = _collect(q, procs, 2)
     (_, lo0, hi0, e0, Z), (_, lo1, hi1, e1, _) = res
     assert lo0 == 0 and hi0 == lo1 and hi1 == Z and hi0 > 0 and hi1 > lo1
     # identical inputs; slabs see identical planes after the exchange ("kw": bf16-identical features)
     assert e0 <= tol and e1 <= tol, (e0, e1)
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2])                     # (the 16-plane test volume holds two slabs of >= 4*HALO planes)
 def test_slab_peer_memory_halo_matches_unsplit(world, monkeypatch):
     """The product halo path of the stress configuration: slabs in CUDA-IPC-mapped peer memory, snvc_halo_push (peer stores
     over NVLink + neighbour barrier in one kernel) instead of NCCL.  Needs one GPU per rank (the push kernels of the
@@ -138,10 +150,7 @@ def test_slab_peer_memory_halo_matches_unsplit(world, monkeypatch):
     procs = [ctx.Process(target=_worker, args=(r, world, port, True, q, True)) for r in range(world)]
     for p in procs:
         p.start()
-    res = sorted(q.get(timeout=300) for _ in range(world))
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    res = _collect(q, procs, world)
     Z = res[0][4]
     assert res[0][1] == 0 and res[-1][2] == Z and all(res[i][2] == res[i + 1][1] for i in range(world - 1))
     assert all(r[3] <= 1e-6 for r in res), [r[3] for r in res]
