@@ -838,6 +838,117 @@ lift_ndhwc_coop_kernel(const __nv_bfloat16* __restrict__ vol, const float* __res
   }
 }
 
+// v4 of the NDHWC lift, bf16 output (the product path).  ncu on the cooperative kernel above (r02): issue slots 73 % busy,
+// but only 10 % of the executed instructions are the FFMA2 of the interpolation and ~20 % the bf16 -> fp32 unpacks; the
+// rest is ten set-up shuffles per round, per-corner predicates with zero-initialised registers (CS2R 7 %), 64-bit address
+// chains, constant reloads.  Same recipe as the ROI sampler v4:
+//   * the set-up (same arithmetic: validity and corner indices stay bit-exact) leaves 8 corner weights that are ZERO for a
+//     corner outside the volume (or an invalid voxel) and a clamped, always valid corner-0 index + per-axis step flags;
+//     every load is unconditional, fma(v, 0, acc) == acc for the finite values of the trunk, so the result is
+//     bit-identical to the kernel above (tests/test_gpu_voxel_sample.py);
+//   * the set-up travels through shared memory (2 STS.128 + 1 STS.64 per lane and chunk; 2 LDS.128 + 1 LDS.64 per round);
+//   * one IMAD.WIDE per corner address, offsets in 16-byte units.
+template <int LOG_LPV>   // lanes per voxel: C / 8 == 1 << LOG_LPV
+__global__ void __launch_bounds__(256, 4)
+lift_fast_bf16_kernel(const __nv_bfloat16* __restrict__ vol, const float* __restrict__ proj, const float* __restrict__ zs,
+                      const float* __restrict__ ys, const float* __restrict__ xs, __nv_bfloat16* __restrict__ out,
+                      uint8_t* __restrict__ valid, LiftGeom g, LiftDivs dv, uint32_t total /* N*Z*Y*X < 2^31 */) {
+  constexpr int LPV = 1 << LOG_LPV, VPR = 32 >> LOG_LPV, ROUNDS = LPV, C = 8 * LPV;
+  constexpr uint32_t ROW16 = LPV;                                // 16-byte pieces per voxel row
+  __shared__ float4 s_w[8][2][2][32];                            // [warp][buffer][weights 0-3 | 4-7][voxel of the chunk]
+  __shared__ uint2 s_i[8][2][32];                                // corner-0 voxel index (clamped), step flags | valid bit
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int sub = lane & (LPV - 1);
+  const int vsel = lane >> LOG_LPV;
+  const int HW = g.H * g.W;
+  const int DHW = g.D * HW;
+  const uint32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint4* const vol16 = reinterpret_cast<const uint4*>(vol) + sub;
+  uint4* const out16 = reinterpret_cast<uint4*>(out) + (size_t)vsel * ROW16 + sub;
+  int buf = 0;
+  for (uint32_t chunk = warp0; chunk * 32u < total; chunk += nwarps, buf ^= 1) {
+    // ---- phase A: lane i sets up voxel chunk*32 + i (arithmetic of lift_ndhwc_coop_kernel, bit-exact indices / validity)
+    const uint32_t nv = chunk * 32u + lane;
+    float4 wa = make_float4(0.f, 0.f, 0.f, 0.f), wb = wa;
+    uint2 id = make_uint2(0u, 0u);
+    if (nv < total) {
+      const uint32_t q1 = fdiv(nv, dv.X), xi = nv - q1 * dv.X.d;
+      const uint32_t q2 = fdiv(q1, dv.Y), yi = q1 - q2 * dv.Y.d;
+      const uint32_t n = fdiv(q2, dv.Z), zi = q2 - n * dv.Z.d;
+      const float zc = __ldg(zs + zi);
+      float uh, vh, wh;
+      projection_dots(proj + n * 12, __ldg(xs + xi), __ldg(ys + yi), zc, uh, vh, wh);
+      bool tvalid = false;
+      if (!(g.range_ordered && clearly_outside(uh, vh, wh, zc, g))) {
+        const Trilinear t = trilinear_finish(uh, vh, wh, zc, g);
+        tvalid = t.valid;
+        if (t.valid) {
+          const int z0 = t.z0 - g.d_base;
+          // per-axis weights, zero where that corner coordinate is outside the volume
+          const float wx0 = (unsigned)t.x0 < (unsigned)g.W ? t.wx[0] : 0.f, wx1 = (unsigned)(t.x0 + 1) < (unsigned)g.W ? t.wx[1] : 0.f;
+          const float wy0 = (unsigned)t.y0 < (unsigned)g.H ? t.wy[0] : 0.f, wy1 = (unsigned)(t.y0 + 1) < (unsigned)g.H ? t.wy[1] : 0.f;
+          const float wz0 = (unsigned)z0 < (unsigned)g.D ? t.wz[0] : 0.f, wz1 = (unsigned)(z0 + 1) < (unsigned)g.D ? t.wz[1] : 0.f;
+          const float w00 = __fmul_rn(wx0, wy0), w10 = __fmul_rn(wx1, wy0), w01 = __fmul_rn(wx0, wy1), w11 = __fmul_rn(wx1, wy1);
+          wa = make_float4(__fmul_rn(w00, wz0), __fmul_rn(w10, wz0), __fmul_rn(w01, wz0), __fmul_rn(w11, wz0));
+          wb = make_float4(__fmul_rn(w00, wz1), __fmul_rn(w10, wz1), __fmul_rn(w01, wz1), __fmul_rn(w11, wz1));
+          const int x0c = min(max(t.x0, 0), g.W - 1), x1c = min(max(t.x0 + 1, 0), g.W - 1);
+          const int y0c = min(max(t.y0, 0), g.H - 1), y1c = min(max(t.y0 + 1, 0), g.H - 1);
+          const int z0c = min(max(z0, 0), g.D - 1), z1c = min(max(z0 + 1, 0), g.D - 1);
+          id.x = (uint32_t)((int)n * DHW + (z0c * g.H + y0c) * g.W + x0c);
+          id.y = 8u | (x1c != x0c ? 1u : 0u) | (y1c != y0c ? 2u : 0u) | (z1c != z0c ? 4u : 0u);
+        }
+      }
+      if (valid) valid[nv] = tvalid ? 1 : 0;
+    }
+    // ---- whole chunk outside the frustum (42 % of the KITTI grid, in long runs): write its zero rows and move on
+    if (__ballot_sync(0xffffffffu, id.y != 0u) == 0u && chunk * 32u + 32u <= total) {
+      uint4* z = reinterpret_cast<uint4*>(out) + (size_t)chunk * 32u * ROW16;
+      for (uint32_t i = lane; i < 32u * ROW16; i += 32u) st_cs_v4(z + i, make_uint4(0u, 0u, 0u, 0u));
+      continue;
+    }
+    s_w[wib][buf][0][lane] = wa;
+    s_w[wib][buf][1][lane] = wb;
+    s_i[wib][buf][lane] = id;
+    __syncwarp();
+    // ---- phase B: LPV rounds of VPR consecutive voxels; lane group `vsel` gathers voxel r*VPR + vsel
+    uint4* o = out16 + (size_t)chunk * 32u * ROW16;
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+      const int src = r * VPR + vsel;
+      const uint2 idr = s_i[wib][buf][src];
+      const bool live = chunk * 32u + (uint32_t)src < total;
+      float2 acc[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+      if (__ballot_sync(0xffffffffu, idr.y != 0u) != 0u) {   // (a round of voxels outside the frustum writes zeros)
+        const float4 w0 = s_w[wib][buf][0][src], w1 = s_w[wib][buf][1][src];
+        const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const uint32_t o000 = idr.x * ROW16;
+        const uint32_t dx = (idr.y & 1u) ? ROW16 : 0u, dy = (idr.y & 2u) ? (uint32_t)g.W * ROW16 : 0u,
+                       dz = (idr.y & 4u) ? (uint32_t)HW * ROW16 : 0u;
+        uint4 q[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t off = o000 + ((k & 1) ? dx : 0u) + ((k & 2) ? dy : 0u) + ((k & 4) ? dz : 0u);
+          uint64_t a;
+          asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(a) : "r"(off), "l"(reinterpret_cast<uint64_t>(vol16)));
+          q[k] = __ldg(reinterpret_cast<const uint4*>(a));
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t u[4] = {q[k].x, q[k].y, q[k].z, q[k].w};
+          const float2 wk = make_float2(w[k], w[k]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[j] = __ffma2_rn(make_float2(bf16_lo(u[j]), bf16_hi(u[j])), wk, acc[j]);
+        }
+      }
+      if (live)
+        st_cs_v4(o + (size_t)r * VPR * ROW16,
+                 make_uint4(pack_bf16x2(acc[0].x, acc[0].y), pack_bf16x2(acc[1].x, acc[1].y), pack_bf16x2(acc[2].x, acc[2].y),
+                            pack_bf16x2(acc[3].x, acc[3].y)));
+    }
+  }
+}
+
 // NCDHW fp32 volume (the reference's layout) -> NCDHW fp32; one thread per voxel, channel loop.
 __global__ void __launch_bounds__(256)
 lift_ncdhw_kernel(const float* __restrict__ vol, const float* __restrict__ proj, const float* __restrict__ zs,
@@ -1086,6 +1197,15 @@ static int lift_fwd_impl(const void* vol, const float* proj, const float* zs, co
       while ((1 << log_lpv) < lpv) ++log_lpv;
       LiftDivs dv{make_fastdiv(X), make_fastdiv(Y), make_fastdiv(Z)};
       const int cblocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(nvox, 256), (int64_t)sm_count() * 4));   // 4 resident blocks / SM, one wave
+      if (out_dtype == SNVC_BF16 && log_lpv >= 1 && log_lpv <= 3 && !lmode) {     // v4 (SNVC_LIFT_MODE=coop keeps v3)
+        if (log_lpv == 1)
+          lift_fast_bf16_kernel<1><<<cblocks, 256, 0, stream>>>((const __nv_bfloat16*)vol, proj, zs, ys, xs, (__nv_bfloat16*)out, valid, g, dv, (uint32_t)nvox);
+        else if (log_lpv == 2)
+          lift_fast_bf16_kernel<2><<<cblocks, 256, 0, stream>>>((const __nv_bfloat16*)vol, proj, zs, ys, xs, (__nv_bfloat16*)out, valid, g, dv, (uint32_t)nvox);
+        else
+          lift_fast_bf16_kernel<3><<<cblocks, 256, 0, stream>>>((const __nv_bfloat16*)vol, proj, zs, ys, xs, (__nv_bfloat16*)out, valid, g, dv, (uint32_t)nvox);
+        return launch_status("lift_fast_bf16_kernel");
+      }
       if (out_dtype == SNVC_BF16)
         lift_ndhwc_coop_kernel<__nv_bfloat16, false><<<cblocks, 256, 0, stream>>>(
             (const __nv_bfloat16*)vol, proj, zs, ys, xs, (__nv_bfloat16*)out, valid, (int)C, log_lpv, g, dv, (uint32_t)nvox);

@@ -199,10 +199,15 @@ def test_lift_cooperative_kernel_matches_thread_per_voxel_kernel(C, monkeypatch)
     zs, ys, xs = (torch.from_numpy(a).cuda() for a in ogb.voxel_centres(geom))
     assert (N * zs.numel() * ys.numel() * xs.numel()) % 32 != 0
     Ps = torch.from_numpy(np.stack([geom.P] * N)).cuda()
+    # v4, the default bf16 kernel (zero-weight masking, set-up through shared memory): same numbers as the others
+    fast, fv = F.frustum_lift(vol, Ps, zs, ys, xs, geom.cv_ranges(), True, layout_in="NDHWC", out_dtype=torch.bfloat16,
+                              return_valid=True)
     for od in (torch.bfloat16, torch.float32):
         set_opt(monkeypatch, "SNVC_LIFT_MODE", "thread")
         want, wv = F.frustum_lift(vol, Ps, zs, ys, xs, geom.cv_ranges(), True, layout_in="NDHWC", out_dtype=od,
                                   return_valid=True)
+        if od == torch.bfloat16:
+            assert torch.equal(fv, wv) and torch.equal(fast.view(torch.int16), want.view(torch.int16))
         set_opt(monkeypatch, "SNVC_LIFT_MODE", "coop")
         got, gv = F.frustum_lift(vol, Ps, zs, ys, xs, geom.cv_ranges(), True, layout_in="NDHWC", out_dtype=od,
                                  return_valid=True)
