@@ -88,6 +88,31 @@ def test_slab_world1_matches_unsplit(mode, tol, monkeypatch):
     assert err <= tol, err           # same planes, same weights: only the slab bookkeeping differs
 
 
+def test_graphed_slab_forward_world1_replays_eager():
+    """`GraphedSlabForward` (the stress leg's launch mode): the captured slab forward replays to the eager result, also after
+    the inputs were reloaded."""
+    from snvc_b200 import parallel as par
+    dev = torch.device("cuda", 0)
+    cfg, lf, rf, shift, P = _cfg_and_inputs()
+    with torch.no_grad():
+        m = _model(cfg, dev)
+        args = [torch.from_numpy(a).to(dev) for a in (lf, rf, shift, P)]
+        slab = par.DepthSlab(shift.shape[1], 1, 0)
+        want, zr = par.slab_global_forward(m, *args, slab, out_dtype=torch.bfloat16, layout_out="NDHWC")
+        g = par.GraphedSlabForward(m, *[torch.zeros_like(a) for a in args[:2]], args[2], args[3], slab)
+        g.load(*args)
+        got, zr2 = g.replay()
+        torch.cuda.synchronize()
+        assert zr == zr2 and torch.equal(got.view(torch.int16), want.view(torch.int16))
+        g.load(args[1], args[0], args[2], args[3])           # swapped views: a different result, then back
+        other = g.replay()[0].clone()
+        g.load(*args)
+        again = g.replay()[0]
+        torch.cuda.synchronize()
+        assert not torch.equal(other, want) and torch.equal(again.view(torch.int16), want.view(torch.int16))
+        g.close()
+
+
 def _worker(rank, world, port, use_nccl, q, use_arena=False):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
