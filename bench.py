@@ -629,7 +629,8 @@ def run_ours(args, rank, world, local_rank):
             roof["stages"]["instance_roi_sampling"] = {
                 "bound": "hbm", "kernel": "roi_sample_fast_bf16_kernel (+ feature transposition), per proposal",
                 "ms_per_proposal": instance["roi_sampling"]["ms_per_proposal"], "achieved": instance["roi_sampling"]["achieved_gbs"],
-                "peak": peaks["hbm"], "unit": "GB/s", "frac": instance["roi_sampling"]["frac_hbm"], "traffic": None,
+                "peak": peaks["hbm"], "unit": "GB/s", "frac": instance["roi_sampling"]["frac_hbm"],
+                "traffic": (traffic["roi_dram_bytes_per_launch"] // 8) if "roi_dram_bytes_per_launch" in traffic else None,
                 "algorithmic_bytes_per_launch": instance["roi_sampling"]["bytes_per_proposal"]}
             roof["stages"]["instance_cnn"] = {
                 "bound": "tensor", "kernel": "instance 3-D CNN + BEV tail (conv3d_bigk / kdpair / conv2d kernels), per proposal",
