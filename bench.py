@@ -57,7 +57,8 @@ def workload_config(world, eager=False):
                         "192x20x304 voxels), random init, BN eval folded",
             "pairs_per_gpu_per_step": PAIRS_PER_GPU, "parallelism": f"pair-sharded x{world}, no collective",
             "launch": "eager (one Python launch per kernel)" if eager else
-                      "CUDA-graph replay (GraphedHotPath, one graph per stage, inputs copied device-to-device per step)",
+                      "CUDA-graph replay (GraphedHotPath, one graph per stage; one graph set per resident input set, the graphs read "
+                      "the inputs in place)",
             "cost_volume_form": "split (default): the depth-invariant left half of the 64-channel volume is kept as 3 planes "
                                 "and enters dres0.conv1 as an addend; SNVC_SPLIT_CV=0 materialises the full volume",
             "l2": "inputs rotate over 4 sets (245 MB) and each step streams >3 GB of intermediates; "
@@ -391,21 +392,31 @@ def run_ours(args, rank, world, local_rank):
     # 3-plane addend conv | dres0.conv1 | rest of the trunk | lift -- so that events between them time each stage inside
     # the timed region.
     # --eager launches the same kernels one by one from Python (host launch overhead then bounds the step).
-    graphed = None if args.eager else GraphedHotPath(model, B, FEAT_C, (FEAT_H, FEAT_W), DEPTH_BINS, out_dtype,
-                                                     layout_out, stages=True)
+    # One captured graph set PER INPUT SET: the graphs read the resident inputs in place (a producer -- the 2-D backbone -- would
+    # write its features into a graph's static input buffers), so the timed region holds no input copy.
+    graphs = None
+    if not args.eager:
+        graphs = [GraphedHotPath(model, B, FEAT_C, (FEAT_H, FEAT_W), DEPTH_BINS, out_dtype, layout_out, stages=True)
+                  for _ in range(NSETS)]
+        for g_, l_, r_ in zip(graphs, lefts, rights):
+            g_.load(l_, r_, shift, proj)
+        torch.cuda.synchronize()
+        lefts = [g_.inputs[0] for g_ in graphs]               # (the staging copies are dropped: 4 x 61 MB stay resident)
+        rights = [g_.inputs[1] for g_ in graphs]
+    graphed = graphs[0] if graphs else None
 
     def step(i, timed):
         l, r = lefts[i % NSETS], rights[i % NSETS]
         e = [ev() for _ in range(6)] if timed else None
         if graphed is not None:
-            graphed.load(l, r, shift, proj)                 # device-to-device copy into the graph's input buffers
+            g_ = graphs[i % NSETS]                          # the graph set captured on this input set
             if timed:
                 e[0].record()
             # events: e0 start | e1 after the volume build | e5 after the addend conv (split form) | e2 after conv1 |
             # e3 after the rest of the trunk | e4 after the lift
             order = {"cost_volume": 1, "conv1_addend": 5, "conv1": 2, "trunk_rest": 3, "lift": 4}
             names = graphed.stage_names
-            vox = graphed.replay((lambda k: e[order[names[k]]].record()) if timed else None)
+            vox = g_.replay((lambda k: e[order[names[k]]].record()) if timed else None)
             return vox, e
         if timed:
             e[0].record()
