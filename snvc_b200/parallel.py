@@ -155,16 +155,20 @@ class PeerArena:
             handle = (ctypes.c_ubyte * 64)()
             _lib.check(L.snvc_peer_export(self.base, handle), "snvc_peer_export")
             # (gloo -- the CPU-side tests with both ranks on one GPU -- gathers host tensors)
-            mine = torch.tensor(list(handle), dtype=torch.uint8, device="cpu" if dist.get_backend(group) == "gloo" else device)
-            every = [torch.empty_like(mine) for _ in range(world)]
-            dist.all_gather(every, mine, group=group)
+            every = []
+            if world > 1:
+                mine = torch.tensor(list(handle), dtype=torch.uint8,
+                                    device="cpu" if dist.get_backend(group) == "gloo" else device)
+                every = [torch.empty_like(mine) for _ in range(world)]
+                dist.all_gather(every, mine, group=group)
             for attr, peer in (("lo", rank - 1), ("hi", rank + 1)):
                 if 0 <= peer < world:
                     raw = (ctypes.c_ubyte * 64)(*every[peer].cpu().tolist())
                     _lib.check(L.snvc_peer_open(raw, ctypes.byref(getattr(self, attr))), "snvc_peer_open")
         self.mem = torch.as_tensor(_RawCuda(self.base.value, self.nbytes), device=device)
         self.off = self.ctl_bytes
-        dist.barrier(group=group)                               # every mapping exists before anyone pushes
+        if world > 1:
+            dist.barrier(group=group)                           # every mapping exists before anyone pushes
 
     def reset(self):
         self.off = self.ctl_bytes
@@ -202,14 +206,15 @@ class PeerArena:
         from snvc_b200 import _lib
         if self.base:
             torch.cuda.synchronize(self.device)
-            dist.barrier(group=self.group)                      # nobody unmaps an arena a neighbour may still push into
+            sync = (lambda: dist.barrier(group=self.group)) if self.world > 1 else (lambda: None)
+            sync()                                              # nobody unmaps an arena a neighbour may still push into
             L = _lib.lib()
             self.mem = None
             with torch.cuda.device(self.device):
                 for h in (self.lo, self.hi):
                     if h:
                         L.snvc_peer_close(h)
-                dist.barrier(group=self.group)
+                sync()
                 L.snvc_peer_free(self.base)
             self.base = self.lo = self.hi = None
 

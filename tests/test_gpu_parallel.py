@@ -88,6 +88,15 @@ def test_slab_world1_matches_unsplit(mode, tol, monkeypatch):
     assert err <= tol, err           # same planes, same weights: only the slab bookkeeping differs
 
 
+def test_slab_world1_peer_arena_matches_unsplit(monkeypatch):
+    """World 1 through the peer-memory halo path: the slabs live in a `PeerArena` (library-allocated, carved identically
+    on every forward) and every layer's exchange is `snvc_halo_push` -- without neighbours it zero-fills both inner halo
+    planes, the convolution's depth padding.  (World 2 on two GPUs: test_slab_peer_memory_halo_matches_unsplit.)"""
+    set_opt(monkeypatch, "SNVC_CONV_MODE", "kw")
+    zlo, zhi, err, Z = _slab_run(0, 1, torch.device("cuda", 0), use_arena=True)
+    assert (zlo, zhi) == (0, Z) and err <= 1e-6, err
+
+
 def test_graphed_slab_forward_world1_replays_eager():
     """`GraphedSlabForward` (the stress leg's launch mode): the captured slab forward replays to the eager result, also after
     the inputs were reloaded."""
