@@ -293,8 +293,14 @@ def stress_leg(dev, rank, world, dist, steps=5):
     # halo exchange: peer-memory push (snvc_halo_push over a CUDA-IPC-mapped arena; default) or NCCL point-to-point through
     # the C ABI (SNVC_STRESS_HALO=nccl, the A/B baseline: 146 GB/s per direction and neighbour on the 8-GPU box)
     use_peer = world > 1 and os.environ.get("SNVC_STRESS_HALO", "peer") != "nccl"
+    arena = None
+    if use_peer:
+        try:                                                   # (PeerArena fails on ALL ranks alike or on none)
+            arena = par.PeerArena(world, rank, dev, par.slab_arena_bytes(slab, H, W))
+        except RuntimeError as e:
+            sys.stderr.write(f"[rank {rank}] stress: {str(e)[:160]}; NCCL halo exchange instead\n")
+            use_peer = False
     comm = par.HaloComm(world, rank, dev) if (world > 1 and not use_peer) else None
-    arena = par.PeerArena(world, rank, dev, par.slab_arena_bytes(slab, H, W)) if use_peer else None
     ev = lambda: torch.cuda.Event(enable_timing=True)
     eager = lambda: par.slab_global_forward(m, lf, rf, shift, proj, slab, out_dtype=torch.bfloat16, layout_out="NDHWC", comm=comm,
                                             arena=arena)

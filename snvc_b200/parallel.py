@@ -150,25 +150,54 @@ class PeerArena:
         self.ctl_bytes = int(L.snvc_peer_ctl_bytes())
         self.nbytes = int(nbytes) + self.ctl_bytes + self.ALIGN
         self.base, self.lo, self.hi = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
-        with torch.cuda.device(device):
-            _lib.check(L.snvc_peer_alloc(self.nbytes, ctypes.byref(self.base)), "snvc_peer_alloc")
-            handle = (ctypes.c_ubyte * 64)()
-            _lib.check(L.snvc_peer_export(self.base, handle), "snvc_peer_export")
-            # (gloo -- the CPU-side tests with both ranks on one GPU -- gathers host tensors)
-            every = []
+        on_cpu = world > 1 and dist.get_backend(group) == "gloo"       # (CPU-side tests: both ranks on one GPU, host tensors)
+        flag_dev = "cpu" if on_cpu else device
+
+        def agree(err):
+            """Collective: every rank learns whether ANY rank failed the local step just done (a rank that raised on its own
+            would leave the others waiting in the next collective).  Raises on all ranks alike."""
+            bad = torch.tensor([1 if err else 0], dtype=torch.int32, device=flag_dev)
             if world > 1:
-                mine = torch.tensor(list(handle), dtype=torch.uint8,
-                                    device="cpu" if dist.get_backend(group) == "gloo" else device)
-                every = [torch.empty_like(mine) for _ in range(world)]
-                dist.all_gather(every, mine, group=group)
-            for attr, peer in (("lo", rank - 1), ("hi", rank + 1)):
-                if 0 <= peer < world:
-                    raw = (ctypes.c_ubyte * 64)(*every[peer].cpu().tolist())
-                    _lib.check(L.snvc_peer_open(raw, ctypes.byref(getattr(self, attr))), "snvc_peer_open")
-        self.mem = torch.as_tensor(_RawCuda(self.base.value, self.nbytes), device=device)
-        self.off = self.ctl_bytes
+                dist.all_reduce(bad, op=dist.ReduceOp.MAX, group=group)
+            if int(bad.item()):
+                self._release(L)
+                raise RuntimeError(f"PeerArena: peer-memory set-up failed on some rank ({err or 'another rank'})")
+
+        handle = (ctypes.c_ubyte * 64)()
+        err = None
+        try:                                                    # local: allocate + export
+            with torch.cuda.device(device):
+                _lib.check(L.snvc_peer_alloc(self.nbytes, ctypes.byref(self.base)), "snvc_peer_alloc")
+                _lib.check(L.snvc_peer_export(self.base, handle), "snvc_peer_export")
+        except Exception as e:                                  # noqa: BLE001
+            err = str(e)[:200]
+        agree(err)
+        every = []
         if world > 1:
-            dist.barrier(group=group)                           # every mapping exists before anyone pushes
+            mine = torch.tensor(list(handle), dtype=torch.uint8, device=flag_dev)
+            every = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(every, mine, group=group)
+        try:                                                    # local: map the neighbours' arenas
+            with torch.cuda.device(device):
+                for attr, peer in (("lo", rank - 1), ("hi", rank + 1)):
+                    if 0 <= peer < world:
+                        raw = (ctypes.c_ubyte * 64)(*every[peer].cpu().tolist())
+                        _lib.check(L.snvc_peer_open(raw, ctypes.byref(getattr(self, attr))), "snvc_peer_open")
+            self.mem = torch.as_tensor(_RawCuda(self.base.value, self.nbytes), device=device)
+        except Exception as e:                                  # noqa: BLE001
+            err = str(e)[:200]
+        agree(err)                                              # also the barrier: every mapping exists before anyone pushes
+        self.off = self.ctl_bytes
+
+    def _release(self, L):
+        with torch.cuda.device(self.device):
+            for h in (self.lo, self.hi):
+                if h:
+                    L.snvc_peer_close(h)
+            if self.base:
+                L.snvc_peer_free(self.base)
+        self.mem = None
+        self.base = self.lo = self.hi = None
 
     def reset(self):
         self.off = self.ctl_bytes
