@@ -325,7 +325,8 @@ class SlabTrunk:
         return exchange_depth_halo(x, self.slab, self.group, self.comm)
 
     def _empty(self, shape, like):
-        if self.arena is not None and like.is_cuda and like.dtype == torch.bfloat16:
+        """Every layer's extended output slab; from the arena when there is one (same carving order on every rank)."""
+        if self.arena is not None:
             return self.arena.empty(shape, like.dtype)
         return torch.empty(shape, dtype=like.dtype, device=like.device)
 
@@ -369,7 +370,7 @@ class SlabTrunk:
         """transposed conv (k3,s2,p1,op1): input planes [1, -1) of the ext slab -> ext slab at 2x resolution."""
         if residual is not None:
             kw["residual"] = residual
-        if self.arena is not None and x.is_cuda:
+        if self.arena is not None:
             N, De, H, W, _ = x.shape
             kw["out"] = self._empty((N, 2 * (De - 2), 2 * H, 2 * W, self._cout(layer)), x)
         return self._xchg(layer.fused(x[:, 1:-1], **kw))

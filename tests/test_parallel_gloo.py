@@ -124,6 +124,52 @@ def _wrap_trunk(trunk):
     return m
 
 
+class _CountingArena:
+    """Stand-in for PeerArena on the CPU: hands out ordinary tensors and records what SlabTrunk carves, in order."""
+
+    ALIGN = par.PeerArena.ALIGN
+
+    def __init__(self):
+        self.shapes, self.elements = [], 0
+
+    def reset(self):
+        self.shapes, self.elements = [], 0
+
+    def empty(self, shape, dtype=torch.float32):
+        self.shapes.append(tuple(int(v) for v in shape))
+        n = int(np.prod(shape))
+        self.elements += (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN     # (alignment slack counted in elements: >= bytes / 2)
+        return torch.empty(tuple(shape), dtype=dtype)
+
+    def owns(self, x):
+        return False                                   # -> the exchange takes the torch.distributed / boundary path
+
+
+@pytest.mark.parametrize("world,rank", [(1, 0), (2, 0), (4, 1), (4, 3)])
+def test_slab_arena_bytes_bounds_what_the_trunk_carves(world, rank, monkeypatch):
+    """`slab_arena_bytes` must bound the slabs one forward carves from a PeerArena (the arena is sized with it before any
+    rank has run a layer), and every rank must carve the same sequence -- that is what makes `offset here == offset in the
+    neighbour's mapping` true.  CPU: the trunk runs plain torch layers, the exchange is stubbed out."""
+    import synth
+    from oracle import blocks as oblocks
+    monkeypatch.setattr(par, "exchange_depth_halo", lambda x, slab, group=None, comm=None: x)
+    D, H, W, Cin, ch = 32, 8, 12, 8, 4
+    with torch.no_grad():
+        trunk = oblocks.GlobalTrunk(Cin, ch).eval()
+        trunk.load_state_dict(synth.det_state_dict(trunk, 7))
+        slab = par.DepthSlab(D, world, rank)
+        arena = _CountingArena()
+        ext = torch.zeros((1, slab.Dl + 2 * par.HALO, H, W, Cin))
+        out = par.SlabTrunk(_wrap_trunk(trunk), slab, arena=arena)(ext)
+    assert tuple(out.shape) == (1, slab.Dl + 2 * par.HALO, H, W, ch)
+    assert len(arena.shapes) == 10                                      # one extended slab per layer of the trunk
+    assert 2 * arena.elements <= par.slab_arena_bytes(slab, H, W, ch)    # bf16 bytes incl. alignment slack
+    other = _CountingArena()                                             # the carving depends on the slab thickness only
+    with torch.no_grad():
+        par.SlabTrunk(_wrap_trunk(trunk), par.DepthSlab(D, world, (rank + 1) % world), arena=other)(ext)
+    assert other.shapes == arena.shapes
+
+
 def _slab_worker(rank, world, port, q):
     _init(rank, world, port)
     try:
