@@ -599,7 +599,7 @@ def run_ours(args, rank, world, local_rank):
                       "frac_of_burst_peak": conv1_tflops / peaks["tf_burst"],
                       "traffic": traffic.get("dres0.conv1_split_dram_bytes_per_launch" if split else "dres0.conv1_dram_bytes_per_launch"),
                       "algorithmic_flop_per_launch": conv1_gflop * 1e9 * B, "share_of_step": conv1_ms / elapsed_ms},
-            "cost_volume": {"bound": "hbm", "kernel": "cv_split_bf16_kernel (2 launches / step: right-half volume, left planes)" if split
+            "cost_volume": {"bound": "hbm", "kernel": "cv_split_bf16_kernel (right-half volume) + cv_left_planes_kernel (2 launches / step)" if split
                             else "cv_ndhwc_bf16_kernel", "ms_per_step": cv_ms / K, "achieved": cv_gbs, "peak": peaks["hbm"],
                             "unit": "GB/s", "frac": cv_gbs / peaks["hbm"], "traffic": traffic.get("cost_volume_dram_bytes_per_step"),
                             "algorithmic_bytes_per_launch": cv_bytes * B, "share_of_step": cv_ms / elapsed_ms},

@@ -295,6 +295,33 @@ cv_ndhwc_bf16_kernel(const float* __restrict__ left, const float* __restrict__ r
   }
 }
 
+// Left planes of the split form: left_planes[n, v, ph, pw, :] = bf16(left[n, :, ph*ds, pw*ds]) for v = 0, 1, 2 -- a
+// transposition of 30 MB.  Lanes run over (pw, 8-channel group) with the group fastest: a warp reads, per channel of the
+// group, four 32-byte runs of the NCHW rows and writes 512 contiguous bytes of each plane; no shared memory.  (Round 2:
+// this was a second launch of the staged split kernel, 19 us of mostly cp.async latency for 0.1 % of the step's bytes.)
+__global__ void __launch_bounds__(256)
+cv_left_planes_kernel(const float* __restrict__ left, __nv_bfloat16* __restrict__ left_planes, int C, int img_h, int img_w,
+                      int H, int W, int ds, int64_t total /* N*H*W*C/8 */) {
+  const int CG = C >> 3;
+  const int64_t cstride = (int64_t)img_h * img_w;
+  const int64_t plane = (int64_t)H * W * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % CG);
+    int64_t t = i / CG;
+    const int pw = (int)(t % W); t /= W;
+    const int ph = (int)(t % H);
+    const int64_t n = t / H;
+    const float* src = left + ((n * C + cg * 8) * img_h + (int64_t)ph * ds) * img_w + (int64_t)pw * ds;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __ldg(src + j * cstride);
+    const uint4 q = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    __nv_bfloat16* o = left_planes + (n * 3 * H + ph) * (int64_t)W * C + (int64_t)pw * C + cg * 8;
+#pragma unroll
+    for (int p3 = 0; p3 < 3; ++p3) *reinterpret_cast<uint4*>(o + p3 * plane) = q;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Split form (snvc_cost_volume_split_fwd), whole rows in shared memory.  ncu on the kernel above in split mode: 248 M
 // warp instructions for 0.84 GB (issue slots 83 % busy, 48 % of the HBM peak) -- a lane owns a (column, 8 channels)
@@ -308,37 +335,27 @@ cv_ndhwc_bf16_kernel(const float* __restrict__ left, const float* __restrict__ r
 // split.  grid = (H, N, depth splits).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512)
-cv_split_bf16_kernel(const float* __restrict__ left, const float* __restrict__ right, const float* __restrict__ shift,
-                     __nv_bfloat16* __restrict__ right_vol, __nv_bfloat16* __restrict__ left_planes, int C, int img_h,
-                     int img_w, int D, int H, int W, int ds, int d_per_cta, int mask, int mode) {
-  // mode 1: right half only (grid.z = depth splits; shared memory = one right row + the sample table -> 3 CTAs per SM);
-  // mode 2: left planes only (grid.z = 1; shared memory = one left row).  Two launches, so that the 40 KB left row does
-  // not sit in the shared memory of every depth split.
+cv_split_bf16_kernel(const float* __restrict__ right, const float* __restrict__ shift, __nv_bfloat16* __restrict__ right_vol,
+                     int C, int img_h, int img_w, int D, int H, int W, int ds, int d_per_cta, int mask) {
+  // right half only (grid.z = depth splits; shared memory = one right row + the sample table -> 3 CTAs per SM); the left
+  // planes are cv_left_planes_kernel's, so that no left row sits in the shared memory of every depth split
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int ph = blockIdx.x, n = blockIdx.y, dsplit = blockIdx.z;
   const int d0 = dsplit * d_per_cta;
-  const bool do_left = mode == 2, do_right = mode == 1;
-  const int dn = do_right ? min(d_per_cta, D - d0) : 0;
-  if (do_right && dn <= 0) return;
-  const int lw = (W - 1) * ds + 1;                      // left columns [0, lw)
-  float* sR = reinterpret_cast<float*>(smem_raw);       // [img_w][C], 16-byte chunks XOR-swizzled by column (mode 1)
-  float* sL = sR;                                       // [lw][C] (mode 2)
-  int2* sT = reinterpret_cast<int2*>(sR + (size_t)img_w * C);   // [dn][W]: {code, lx} (mode 1)
+  const int dn = min(d_per_cta, D - d0);
+  if (dn <= 0) return;
+  float* sR = reinterpret_cast<float*>(smem_raw);       // [img_w][C], 16-byte chunks XOR-swizzled by column
+  int2* sT = reinterpret_cast<int2*>(sR + (size_t)img_w * C);   // [dn][W]: {code, lx}
   const int ih = ph * ds;
   const int64_t cstride = (int64_t)img_h * img_w;
   const float* rrow = right + ((int64_t)n * C * img_h + ih) * img_w;
-  const float* lrow = left + ((int64_t)n * C * img_h + ih) * img_w;
   // staging: a warp takes one channel at a time and runs along the row (coalesced 4-byte cp.async, no divisions).  The
   // transposing scatter is a 4-way bank conflict (a fifth of the kernel's shared-memory wavefronts, ncu r02); the
   // conflict-free mapping -- 8 columns x the 4 channels of a chunk per warp instruction -- was measured SLOWER (180 vs
   // 156 us: every lane quartet then pulls a different 32-byte sector, four times the L2 requests) and dropped.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-  for (int c = warp; c < C; c += nwarp) {
-    if (do_right)
-      for (int col = lane; col < img_w; col += 32) cp_async_4(&sR[swz(col, c, C, mask)], rrow + c * cstride + col);
-    if (do_left)
-      for (int col = lane; col < lw; col += 32) cp_async_4(&sL[swz(col, c, C, mask)], lrow + c * cstride + col);
-  }
+  for (int c = warp; c < C; c += nwarp)
+    for (int col = lane; col < img_w; col += 32) cp_async_4(&sR[swz(col, c, C, mask)], rrow + c * cstride + col);
   asm volatile("cp.async.commit_group;" ::: "memory");
   for (int dd = warp; dd < dn; dd += nwarp) {
     const float ns = -shift[(int64_t)n * D + d0 + dd];
@@ -353,19 +370,6 @@ cv_split_bf16_kernel(const float* __restrict__ left, const float* __restrict__ r
   __syncthreads();
 
   const int CG = C >> 3;                                // 8-channel groups
-  if (do_left) {                                        // left half: three identical planes, written once per row
-    for (int i = threadIdx.x; i < W * CG; i += blockDim.x) {
-      const int pw = i / CG, cg = i - pw * CG;
-      const int col = pw * ds;
-      const float4 a = *chunk_ptr(sL, col, 2 * cg, C, mask);
-      const float4 b = *chunk_ptr(sL, col, 2 * cg + 1, C, mask);
-      const uint4 vl = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
-      __nv_bfloat16* lo = left_planes + ((((int64_t)n * 3) * H + ph) * W + pw) * C + cg * 8;
-#pragma unroll
-      for (int v = 0; v < 3; ++v) *reinterpret_cast<uint4*>(lo + (int64_t)v * H * W * C) = vl;
-    }
-  }
-  if (!do_right) return;
   // right half: item = (bin, strip, channel group); the CG lanes of an item's pixel are adjacent (64-byte segments)
   const int nstrips = max(1, (int)blockDim.x / (dn * CG));
   // odd strip length: the 8 lane groups of a warp then sit on columns with 8 different (col & 7), i.e. 8 different
@@ -567,7 +571,7 @@ int launch_cv_ndhwc(const void* left, const void* right, const void* shift, void
   const bool split_form = left_planes != nullptr || parts != 3;
   if (split_form && H <= 2147483647ll && N <= 65535 && (!opt(OPT_CV_SPLIT_OLD) || parts != 3)) {
     // split form, whole rows staged: the right row [img_w][C] fp32 + the sample table of one depth split (the left planes
-    // are a second, small launch of the same kernel)
+    // are cv_left_planes_kernel, a plain transposition)
     const size_t rows = (size_t)IW * C * 4;
     const size_t budget = 74 * 1024;                                    // three CTAs per SM
     if (rows + (size_t)W * 8 <= 225 * 1024) {
@@ -597,15 +601,12 @@ int launch_cv_ndhwc(const void* left, const void* right, const void* shift, void
         // (ncu: with the default carve-out only two of the 70 KB CTAs were resident per SM)
         SNVC_CUDA_OK(cudaFuncSetAttribute(cv_split_bf16_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                           (int)cudaSharedmemCarveoutMaxShared));
-        const size_t smem_left = (size_t)((W - 1) * ds + 1) * C * 4;
-        if (std::max(smem, smem_left) > 48 * 1024)
-          SNVC_CUDA_OK(cudaFuncSetAttribute(cv_split_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)std::max(smem, smem_left)));
         if (parts & 2) {
-          cv_split_bf16_kernel<<<dim3((unsigned)H, (unsigned)N, 1), 512, smem_left, stream>>>(
-              (const float*)left, (const float*)right, (const float*)shift, (__nv_bfloat16*)cost, (__nv_bfloat16*)left_planes,
-              (int)C, (int)IH, (int)IW, (int)D, (int)H, (int)W, ds, d_per, mask, 2);
-          if (int e = launch_status("cv_split_bf16_kernel")) return e;
+          const int64_t items = N * H * W * (C / 8);
+          const int lblocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(items, 256), (int64_t)sm_count() * 8));
+          cv_left_planes_kernel<<<lblocks, 256, 0, stream>>>((const float*)left, (__nv_bfloat16*)left_planes, (int)C, (int)IH,
+                                                           (int)IW, (int)H, (int)W, ds, items);
+          if (int e = launch_status("cv_left_planes_kernel")) return e;
         }
         if (!(parts & 1)) return 0;
         dim3 grid((unsigned)H, (unsigned)N, (unsigned)dsplit);
@@ -624,9 +625,8 @@ int launch_cv_ndhwc(const void* left, const void* right, const void* shift, void
             }
             if (const char* o = opt(OPT_CV_THREADS)) threads = std::max(32, std::min(512, atoi(o) / 32 * 32));
         }
-        cv_split_bf16_kernel<<<grid, threads, smem, stream>>>((const float*)left, (const float*)right, (const float*)shift,
-                                                           (__nv_bfloat16*)cost, (__nv_bfloat16*)left_planes, (int)C, (int)IH,
-                                                           (int)IW, (int)D, (int)H, (int)W, ds, d_per, mask, 1);
+        cv_split_bf16_kernel<<<grid, threads, smem, stream>>>((const float*)right, (const float*)shift, (__nv_bfloat16*)cost,
+                                                           (int)C, (int)IH, (int)IW, (int)D, (int)H, (int)W, ds, d_per, mask);
         return launch_status("cv_split_bf16_kernel");
       }
     }
