@@ -52,7 +52,7 @@ const char* snvc_last_error(void);
  * its timed region as `gpu_launches`. */
 int64_t snvc_launch_count(void);
 /* Debug / A-B switches (kernel-generation selection, grid clamps for the ring wrap-around tests): SNVC_CONV_MODE,
- * SNVC_CONV_STORE, SNVC_CONV_OCC, SNVC_CONV_MAXGRID, SNVC_CV_SPLIT_OLD, SNVC_CV_THREADS, SNVC_ROI_MODE, SNVC_LIFT_MODE.  Each is read from
+ * SNVC_CONV_STORE, SNVC_CONV_OCC, SNVC_CONV_MAXGRID, SNVC_CV_SPLIT_OLD, SNVC_CV_THREADS, SNVC_CV_WALK, SNVC_ROI_MODE, SNVC_LIFT_MODE.  Each is read from
  * the environment once, when the library is loaded; snvc_set_option changes one afterwards (value NULL or "" = unset;
  * name NULL = unset all).  Not synchronised with concurrent launches: set options before starting work.  Launches never
  * call getenv. */

@@ -18,7 +18,13 @@ def t(parts, n=20):
     for i in range(n): build_cost_volume_split_bf16(*sets[i % 4], sh, 1, parts=parts)
     b.record(); torch.cuda.synchronize(); return a.elapsed_time(b) / n
 ref = None
-for th in (None, 512, 448, 384, 288):
+for walk in (None, "general", None, "general"):
+    _lib.set_option("SNVC_CV_WALK", walk)
+    r = build_cost_volume_split_bf16(*sets[0], sh, 1, parts="right")
+    if ref is None: ref = r.clone()
+    print(f"walk {walk or 'two-region'}: right {t('right')*1e3:.1f} us, both {t('both')*1e3:.1f} us, identical {torch.equal(r, ref)}", flush=True)
+_lib.set_option("SNVC_CV_WALK", None)
+for th in (None, 384):
     _lib.set_option("SNVC_CV_THREADS", th)
     r = build_cost_volume_split_bf16(*sets[0], sh, 1, parts="right")
     if ref is None: ref = r.clone()

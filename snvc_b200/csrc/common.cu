@@ -38,7 +38,7 @@ int sm_count() {
 
 namespace {
 const char* const kOptNames[OPT_COUNT] = {"SNVC_CONV_MODE", "SNVC_CONV_STORE", "SNVC_CONV_OCC", "SNVC_CONV_MAXGRID",
-                                          "SNVC_CV_SPLIT_OLD", "SNVC_CV_THREADS", "SNVC_ROI_MODE", "SNVC_LIFT_MODE"};
+                                          "SNVC_CV_SPLIT_OLD", "SNVC_CV_THREADS", "SNVC_ROI_MODE", "SNVC_LIFT_MODE", "SNVC_CV_WALK"};
 struct Options {
   char val[OPT_COUNT][32];
   bool set[OPT_COUNT];

@@ -42,7 +42,7 @@ int sm_count();  // cached per device
 // Debug / A-B switches of the library (kernel-generation selection, grid clamps used by the ring wrap-around tests).
 // Read from the environment ONCE, when the library is loaded; changed afterwards only through snvc_set_option().
 // A launch never calls getenv.
-enum OptId { OPT_CONV_MODE, OPT_CONV_STORE, OPT_CONV_OCC, OPT_CONV_MAXGRID, OPT_CV_SPLIT_OLD, OPT_CV_THREADS, OPT_ROI_MODE, OPT_LIFT_MODE, OPT_COUNT };
+enum OptId { OPT_CONV_MODE, OPT_CONV_STORE, OPT_CONV_OCC, OPT_CONV_MAXGRID, OPT_CV_SPLIT_OLD, OPT_CV_THREADS, OPT_ROI_MODE, OPT_LIFT_MODE, OPT_CV_WALK, OPT_COUNT };
 const char* opt(OptId id);   // current value, or nullptr when unset
 
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -336,7 +336,7 @@ cv_left_planes_kernel(const float* __restrict__ left, __nv_bfloat16* __restrict_
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512)
 cv_split_bf16_kernel(const float* __restrict__ right, const float* __restrict__ shift, __nv_bfloat16* __restrict__ right_vol,
-                     int C, int img_h, int img_w, int D, int H, int W, int ds, int d_per_cta, int mask) {
+                     int C, int img_h, int img_w, int D, int H, int W, int ds, int d_per_cta, int mask, int general_only) {
   // right half only (grid.z = depth splits; shared memory = one right row + the sample table -> 3 CTAs per SM); the left
   // planes are cv_left_planes_kernel's, so that no left row sits in the shared memory of every depth split
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -357,14 +357,29 @@ cv_split_bf16_kernel(const float* __restrict__ right, const float* __restrict__ 
   for (int c = warp; c < C; c += nwarp)
     for (int col = lane; col < img_w; col += 32) cp_async_4(&sR[swz(col, c, C, mask)], rrow + c * cstride + col);
   asm volatile("cp.async.commit_group;" ::: "memory");
+  // sReg[dd] = first column from which the bin is REGULAR up to the end of the row: every sample is inside the image, reads two
+  // different columns and sits exactly one column right of its predecessor's (true right of the zero region x < 0, unless an
+  // fp32 rounding of pw - shift jumps an integer or the last column is clamped).  Strips inside that range take the
+  // branch-free walk below; the table decides, so the result stays bit-identical.
+  int* sReg = reinterpret_cast<int*>(sT + (size_t)dn * W);
   for (int dd = warp; dd < dn; dd += nwarp) {
     const float ns = -shift[(int64_t)n * D + d0 + dd];
-    for (int pw = lane; pw < W; pw += 32) {
-      int xl, xh;
-      float lx;
-      const bool ok = sample_pos<float>(pw * ds, ns, img_w, xl, xh, lx);
-      sT[dd * W + pw] = make_int2(ok ? (xl | (xh != xl ? 0x40000000 : 0)) : -1, __float_as_int(lx));
+    int reg_lo = 0, prev_last = -0x40000000;              // prev_last: x_low of column (chunk base - 1)
+    for (int pw0 = 0; pw0 < W; pw0 += 32) {
+      const int pw = pw0 + lane;
+      int xl = -0x40000000, xh = 0;
+      float lx = 0.f;
+      const bool ok = pw < W && sample_pos<float>(pw * ds, ns, img_w, xl, xh, lx);
+      if (pw < W) sT[dd * W + pw] = make_int2(ok ? (xl | (xh != xl ? 0x40000000 : 0)) : -1, __float_as_int(lx));
+      const int xl_ok = ok ? xl : -0x40000000;
+      int before = __shfl_up_sync(0xffffffffu, xl_ok, 1);
+      if (lane == 0) before = prev_last;
+      const bool regular = ok && xh == xl + 1 && (pw == 0 || xl == before + 1);
+      const unsigned irr = __ballot_sync(0xffffffffu, pw < W && !regular);
+      if (irr) reg_lo = pw0 + 32 - __clz(irr);            // one past the last irregular column so far
+      prev_last = __shfl_sync(0xffffffffu, xl_ok, 31);
     }
+    if (lane == 0) sReg[dd] = (ds == 1 && !general_only) ? reg_lo : W;   // (SNVC_CV_WALK=general: A/B switch)
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
@@ -372,62 +387,105 @@ cv_split_bf16_kernel(const float* __restrict__ right, const float* __restrict__ 
   const int CG = C >> 3;                                // 8-channel groups
   // right half: item = (bin, strip, channel group); the CG lanes of an item's pixel are adjacent (64-byte segments)
   const int nstrips = max(1, (int)blockDim.x / (dn * CG));
+  // The row is walked in two regions so that a warp never mixes the two kinds of step: [0, R0) holds the irregular columns
+  // of every bin of this CTA (the zero region left of x = 0: up to max shift columns) and takes the general step; [R0, W)
+  // is regular for all bins and takes the branch-free step.  (First version: per-strip choice -- the 8 strips of a bin
+  // share a warp, so every warp ran both paths and the kernel got SLOWER, 0.22 vs 0.185 ms.)
+  int R0 = 0;
+  for (int dd = 0; dd < dn; ++dd) R0 = max(R0, sReg[dd]);
+  R0 = min(R0, W);
+  auto load_col_g = [&](float2 (&dst)[4], int col, int cg) {
+    const float4 a = *chunk_ptr(sR, col, 2 * cg, C, mask), b = *chunk_ptr(sR, col, 2 * cg + 1, C, mask);
+    dst[0] = make_float2(a.x, a.y); dst[1] = make_float2(a.z, a.w); dst[2] = make_float2(b.x, b.y); dst[3] = make_float2(b.z, b.w);
+  };
+  // ---- region A = [R0, W): regular.  Column x_low advances by one per step, so a step is ONE new column (2 LDS.128), the
+  // interpolation weight from the table, 4 FMUL2 + 4 FFMA2, 4 packs and the store -- no position decode, no branches.
   // odd strip length: the 8 lane groups of a warp then sit on columns with 8 different (col & 7), i.e. 8 different
   // swizzle phases -> every LDS.128 is served in the minimum 4 wavefronts (an even length -- 26 for KITTI -- measured
   // 27 M bank conflicts per launch, L1 data pipe 85 % busy)
-  const int L = ((W + nstrips - 1) / nstrips) | 1;
-  const int items = dn * nstrips * CG;
-  for (int it = threadIdx.x; it < items; it += blockDim.x) {
-    const int cg = it % CG;
-    const int t2 = it / CG;
-    const int strip = t2 % nstrips, dd = t2 / nstrips;
-    const int w_begin = strip * L, w_end = min(W, w_begin + L);
-    const int2* tab = sT + dd * W;
-    __nv_bfloat16* o = right_vol + ((((int64_t)n * D + d0 + dd) * H + ph) * W + w_begin) * C + cg * 8;
-    // Two register sets that swap roles every step (the step is unrolled by two), so that the column shared by two
-    // consecutive steps is never moved; values as packed fp32 pairs: one FMUL2 + one FFMA2 per two channels, the same
-    // roundings as the scalar lx*v2 then fma(hx, v1, .) (ncu on the first version: 88 instructions per warp step,
-    // issue slots 79 % busy -- the kernel was issue-bound at 64 % of the HBM peak).
-    int held = -0x40000000;                             // column held in the set that is "high" after the last step
-    float2 ra[4], rb[4];
-    auto load_col = [&](float2 (&dst)[4], int col) {
-      const float4 a = *chunk_ptr(sR, col, 2 * cg, C, mask), b = *chunk_ptr(sR, col, 2 * cg + 1, C, mask);
-      dst[0] = make_float2(a.x, a.y); dst[1] = make_float2(a.z, a.w); dst[2] = make_float2(b.x, b.y); dst[3] = make_float2(b.z, b.w);
-    };
-    // one step: `lo` must end up holding column xl, `hi` column xh; on entry `lo` holds column `held` (the previous
-    // step's high column), `hi` is free
-    auto step = [&](float2 (&lo)[4], float2 (&hi)[4], int pw, __nv_bfloat16* op) {
-      const int2 te = tab[pw];
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (te.x >= 0) {
-        const int xl = te.x & 0x3fffffff, xh = xl + ((te.x >> 30) & 1);
-        const float lx = __int_as_float(te.y);
-        if (xl != held) load_col(lo, xl);
-        if (xh != xl) load_col(hi, xh);
-        else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) hi[j] = lo[j];
-        }
-        held = xh;
+  if (R0 < W) {
+    const int LA = ((W - R0 + nstrips - 1) / nstrips) | 1;
+    const int items = dn * nstrips * CG;
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+      const int cg = it % CG;
+      const int t2 = it / CG;
+      const int strip = t2 % nstrips, dd = t2 / nstrips;
+      const int w_begin = R0 + strip * LA, w_end = min(W, w_begin + LA);
+      if (w_begin >= w_end) continue;
+      const int2* tab = sT + dd * W;
+      __nv_bfloat16* o = right_vol + ((((int64_t)n * D + d0 + dd) * H + ph) * W + w_begin) * C + cg * 8;
+      // two register sets that swap roles every step (unrolled by two): the column shared by consecutive steps never moves
+      float2 ra[4], rb[4];
+      const int x0 = tab[w_begin].x & 0x3fffffff;
+      load_col_g(ra, x0, cg);
+      auto fstep = [&](const float2 (&lo)[4], float2 (&hi)[4], int col_hi, int p, __nv_bfloat16* op) {
+        load_col_g(hi, col_hi, cg);
+        const float lx = __int_as_float(tab[p].y);
         const float hx = __fsub_rn(1.f, lx);
         const float2 lx2 = make_float2(lx, lx), hx2 = make_float2(hx, hx);
         float2 r[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) r[j] = __ffma2_rn(hx2, lo[j], __fmul2_rn(lx2, hi[j]));
-        v = make_uint4(pack_bf16x2(r[0].x, r[0].y), pack_bf16x2(r[1].x, r[1].y), pack_bf16x2(r[2].x, r[2].y),
-                       pack_bf16x2(r[3].x, r[3].y));
-      } else {
-        held = -0x40000000;                             // nothing usable is held (hi was not written)
+        *reinterpret_cast<uint4*>(op) = make_uint4(pack_bf16x2(r[0].x, r[0].y), pack_bf16x2(r[1].x, r[1].y),
+                                                   pack_bf16x2(r[2].x, r[2].y), pack_bf16x2(r[3].x, r[3].y));
+      };
+      int pw = w_begin, xh = x0 + 1;
+      for (; pw + 1 < w_end; pw += 2, xh += 2, o += 2 * C) {
+        fstep(ra, rb, xh, pw, o);
+        fstep(rb, ra, xh + 1, pw + 1, o + C);
       }
-      *reinterpret_cast<uint4*>(op) = v;
-    };
-    int pw = w_begin;
-    for (; pw + 1 < w_end; pw += 2, o += 2 * C) {
-      step(ra, rb, pw, o);                              // after it: rb holds the high column
-      step(rb, ra, pw + 1, o + C);                      // rb is the low set now; after it: ra holds the high column
-      // restore the invariant "the set passed as `lo` next holds `held`": the next pair starts with (ra, rb) again
+      if (pw < w_end) fstep(ra, rb, xh, pw, o);
     }
-    if (pw < w_end) step(ra, rb, pw, o);
+  }
+  // ---- region B = [0, R0): the general step (values as packed fp32 pairs: one FMUL2 + one FFMA2 per two channels, the same
+  // roundings as the scalar lx*v2 then fma(hx, v1, .)); short odd strips over all threads
+  if (R0 > 0) {
+    const int LB = ((R0 + nstrips - 1) / nstrips) | 1;
+    const int items = dn * nstrips * CG;
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+      const int cg = it % CG;
+      const int t2 = it / CG;
+      const int strip = t2 % nstrips, dd = t2 / nstrips;
+      const int w_begin = strip * LB, w_end = min(R0, w_begin + LB);
+      if (w_begin >= w_end) continue;
+      const int2* tab = sT + dd * W;
+      __nv_bfloat16* o = right_vol + ((((int64_t)n * D + d0 + dd) * H + ph) * W + w_begin) * C + cg * 8;
+      int held = -0x40000000;                             // column held in the set that is "high" after the last step
+      float2 ra[4], rb[4];
+      // one step: `lo` must end up holding column xl, `hi` column xh; on entry `lo` holds column `held` (the previous
+      // step's high column), `hi` is free
+      auto step = [&](float2 (&lo)[4], float2 (&hi)[4], int pw, __nv_bfloat16* op) {
+        const int2 te = tab[pw];
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (te.x >= 0) {
+          const int xl = te.x & 0x3fffffff, xh = xl + ((te.x >> 30) & 1);
+          const float lx = __int_as_float(te.y);
+          if (xl != held) load_col_g(lo, xl, cg);
+          if (xh != xl) load_col_g(hi, xh, cg);
+          else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) hi[j] = lo[j];
+          }
+          held = xh;
+          const float hx = __fsub_rn(1.f, lx);
+          const float2 lx2 = make_float2(lx, lx), hx2 = make_float2(hx, hx);
+          float2 r[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) r[j] = __ffma2_rn(hx2, lo[j], __fmul2_rn(lx2, hi[j]));
+          v = make_uint4(pack_bf16x2(r[0].x, r[0].y), pack_bf16x2(r[1].x, r[1].y), pack_bf16x2(r[2].x, r[2].y),
+                         pack_bf16x2(r[3].x, r[3].y));
+        } else {
+          held = -0x40000000;                             // nothing usable is held (hi was not written)
+        }
+        *reinterpret_cast<uint4*>(op) = v;
+      };
+      int pw = w_begin;
+      for (; pw + 1 < w_end; pw += 2, o += 2 * C) {
+        step(ra, rb, pw, o);                              // after it: rb holds the high column
+        step(rb, ra, pw + 1, o + C);                      // rb is the low set now; after it: ra holds the high column
+      }
+      if (pw < w_end) step(ra, rb, pw, o);
+    }
   }
 }
 
@@ -593,7 +651,7 @@ int launch_cv_ndhwc(const void* left, const void* right, const void* shift, void
       d_per = (int)ceil_div(D, pick);
       const int dsplit = (int)ceil_div(D, d_per);
       if (dsplit <= 65535) {
-        const size_t smem = rows + (size_t)W * d_per * 8;
+        const size_t smem = rows + (size_t)W * d_per * 8 + (size_t)d_per * 4;   // row + sample table + regular-range starts
         if (smem > 48 * 1024)
           SNVC_CUDA_OK(cudaFuncSetAttribute(cv_split_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int mask = 1;  // largest 2^k - 1 (k <= 3) with 2^k | C/4
@@ -626,7 +684,8 @@ int launch_cv_ndhwc(const void* left, const void* right, const void* shift, void
             if (const char* o = opt(OPT_CV_THREADS)) threads = std::max(32, std::min(512, atoi(o) / 32 * 32));
         }
         cv_split_bf16_kernel<<<grid, threads, smem, stream>>>((const float*)right, (const float*)shift, (__nv_bfloat16*)cost,
-                                                           (int)C, (int)IH, (int)IW, (int)D, (int)H, (int)W, ds, d_per, mask);
+                                                           (int)C, (int)IH, (int)IW, (int)D, (int)H, (int)W, ds, d_per, mask,
+                                                           opt(OPT_CV_WALK) ? 1 : 0);
         return launch_status("cv_split_bf16_kernel");
       }
     }
