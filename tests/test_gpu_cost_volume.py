@@ -49,7 +49,8 @@ def test_ndhwc_bf16_equals_rounded_oracle(shape, ds):
     assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("shape,ds", [((2, 8, 6, 16), 1), ((1, 32, 5, 40), 1), ((2, 16, 8, 24), 2), ((1, 32, 96, 312), 1)])
+@pytest.mark.parametrize("shape,ds", [((2, 8, 6, 16), 1), ((1, 32, 5, 40), 1), ((2, 16, 8, 24), 2), ((1, 32, 96, 312), 1),
+                                      ((1, 32, 3, 1248), 1)])      # last: the stress volume's 160 KB rows (7 bins per CTA)
 def test_split_form_equals_rounded_oracle(shape, ds):
     """snvc_cost_volume_split_fwd: right_vol = channels [C, 2C) of the volume, left_planes = the depth-invariant left
     half on three identical planes; both equal to the bf16-rounded oracle volume (and hence to the unsplit kernel)."""
